@@ -1,0 +1,461 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 hot path (driver contract).
+
+    python bench.py --gpus 1 --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --steps K --warmup W    # reference algorithm on the host CPU
+    torchrun ... bench.py --gpus N ...                       # one rank per GPU, batch sharded
+
+Metric (BASELINE.json): MLP obj+grad evaluations / second, and BFGS H-update HBM GB/s.
+Workload at N = 1: BASELINE configs[1] -- synthetic 60000 x 784 patterns, MLP (784,256,10),
+softplus hidden, softmax + cross entropy, FP64 parity mode.  A step = one full-batch
+objective + gradient evaluation (what every optimizer step and every Wolfe probe calls).
+Multi-GPU: weak scaling, 60000 patterns per GPU, the global batch sharded by rows with one NCCL
+all-reduce of [gradient ; objective] per evaluation; value is reported in 60000-pattern
+evaluations per second so it aggregates over ranks.
+
+The second half of the metric (BFGS) runs at BASELINE configs[2]'s n = 83328 (H = 55.5 GB FP64)
+and is reported in the same JSON line under "bfgs".
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "optimal-py-learning_b200"))
+
+ROWS = 60000
+SHAPE = (784, 256, 10)
+BFGS_N = 83328          # (512,128,128,10): n = 128 + 512*128 + 128*128 + 128*10
+METRIC = "obj+grad evals/sec"
+UNIT = "evals/s (60000-pattern full-batch obj+grad evaluations, MLP (784,256,10) softmax/CE)"
+
+
+def algorithmic_flops(shape, rows):
+    s = sum(a * b for a, b in zip(shape[:-1], shape[1:]))
+    return 2.0 * rows * (3.0 * s - shape[0] * shape[1])
+
+
+def synthetic(rows, seed):
+    """datasets.get_random_classification-style data (data/datasets.py:257-276)."""
+    rng = numpy.random.default_rng(seed)
+    x = rng.random((rows, SHAPE[0])) * 2.0 - 1.0
+    y = numpy.zeros((rows, SHAPE[-1]))
+    y[numpy.arange(rows), rng.integers(0, SHAPE[-1], size=rows)] = 1.0
+    n = SHAPE[1] + sum(a * b for a, b in zip(SHAPE[:-1], SHAPE[1:]))
+    w = (2.0 * rng.random(n) - 1.0) * 0.25
+    return x, y, w
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port (NumPy float64 + host BLAS, all host threads)
+# ----------------------------------------------------------------------------------------------
+def host_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        blas = [i for i in threadpool_info() if i.get("user_api") == "blas"]
+        if blas:
+            return int(blas[0]["num_threads"]), blas[0].get("internal_api", "blas")
+    except Exception:
+        pass
+    return os.cpu_count() or 1, "blas"
+
+
+def cpu_objgrad_times(steps, warmup):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import mlp_oracle as mo
+    x, y, w = synthetic(ROWS, 0)
+    transfers = [(mo.SOFTPLUS, 0.0), (mo.SOFTMAX, 0.0)]
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        mo.objective_gradient(w, SHAPE, transfers, mo.CROSS_ENTROPY, x, y)   # literal reference algorithm
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return times
+
+
+def cpu_bfgs_baseline():
+    """Reference _bfgs_eq (literal, O(n^3)) at a size the host finishes in seconds, and the NumPy
+    rank-2 restatement as the best-case CPU bandwidth number."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import optimize_oracle as oo
+    rng = numpy.random.default_rng(1)
+    out = {}
+    n = 2048
+    h = numpy.identity(n) + 1e-3 * rng.standard_normal((n, n))
+    s, y = rng.standard_normal(n), rng.standard_normal(n)
+    oo.bfgs_update_literal(h, s, y)
+    t0 = time.perf_counter()
+    oo.bfgs_update_literal(h, s, y)
+    t = time.perf_counter() - t0
+    out["literal_n"] = n
+    out["literal_s"] = t
+    out["literal_extrapolated_s_at_%d" % BFGS_N] = t * (BFGS_N / float(n)) ** 3
+    n = 8192
+    h = numpy.identity(n) + 1e-3 * rng.standard_normal((n, n))
+    s, y = rng.standard_normal(n), rng.standard_normal(n)
+    oo.bfgs_update_rank2(h, s, y)
+    t0 = time.perf_counter()
+    oo.bfgs_update_rank2(h, s, y)
+    t = time.perf_counter() - t0
+    out["rank2_n"] = n
+    out["rank2_s"] = t
+    out["rank2_gbs"] = 2.0 * n * n * 8 / t / 1e9
+    return out
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    times = cpu_objgrad_times(args.steps, max(1, args.warmup))
+    threads, api = host_threads()
+    ms = 1e3 * sum(times) / len(times)
+    value = 1e3 / ms
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[1]: 60000x784 synthetic, MLP (784,256,10) softplus/softmax + cross entropy, "
+                               "one full-batch obj+grad evaluation per step (host CPU, NumPy float64 + %s)" % api},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "full workload: %d timed full-batch evaluations after %d warm-up"
+                                   % (args.steps, max(1, args.warmup))},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([f.strip() for f in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                pass
+        sm, mx, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                power.append(float(r[3]))
+                for name, flag in zip(names, r[5:9]):
+                    if flag.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        busy = [c for c, p in zip(sm, power) if p > 0.5 * max(power)] or sm
+        return {"sm_mhz": float(numpy.median(busy)), "sm_max_mhz": max(mx), "power_w_max": max(power),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
+
+
+def fp64_gemm_peak(torch):
+    """Denominator of the FP64 tensor-pipe roofline: cuBLAS DGEMM 8192^3, best of 5 (burst)."""
+    a = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
+    b = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
+    best = float("inf")
+    torch.matmul(a, b)
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    torch.cuda.empty_cache()
+    return 2.0 * 8192 ** 3 / (best * 1e-3) / 1e12
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import learning_b200 as L
+    from learning_b200 import _native as nat, _device as dev
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- workload: every rank owns 60000 rows of a (world*60000)-row batch (weak scaling) -------
+    x, y, w = synthetic(ROWS, 100 + rank)
+    _, _, w = synthetic(8, 0)                      # identical parameters on every rank
+    n = w.size
+    model = L.MLP(SHAPE, transfers=L.SoftmaxTransfer(), error_func=L.CrossEntropyError(),
+                  optimizer=L.optimize.LBFGS())
+    model.logging = False
+    xd, yd = dev.to_device(x), dev.to_device(y)
+    ws = model._make_resident(xd, yd)              # device-resident shard; N of the 1/N scale = world*60000
+    wd = dev.to_device(w)
+    out = torch.empty(n + 1, dtype=torch.float64, device="cuda")
+
+    def device_step():
+        nat.check(nat.lib.opl_mlp_eval_device(ws.pointer, dev.ptr(wd), 0.0, None, 1, dev.ptr(out)))
+        if world > 1:
+            dist.all_reduce(out)
+
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = nat.lib.opl_mlp_launch_count(ws.pointer)
+    profile = world == 1
+    if profile:
+        nat.check(nat.lib.opl_mlp_profile(ws.pointer, 1))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        device_step()
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    launches = nat.lib.opl_mlp_launch_count(ws.pointer) - launches0
+    stage_ms = {}
+    if profile:
+        cap = 64 * args.steps
+        kinds = (ctypes.c_int32 * cap)()
+        ms = (ctypes.c_float * cap)()
+        count = ctypes.c_int32(0)
+        nat.check(nat.lib.opl_mlp_profile_read(ws.pointer, cap, kinds, ms, ctypes.byref(count)))
+        nat.check(nat.lib.opl_mlp_profile(ws.pointer, 0))
+        for i in range(count.value):
+            stage_ms.setdefault(int(kinds[i]), []).append(float(ms[i]))
+    ms_per_step = ms_total / args.steps
+    value = world * 1e3 / ms_per_step              # 60000-pattern evaluations per second, all ranks
+
+    # sanity: objective of the timed evaluation is the cross entropy of a random-init 10-class net
+    scal = (ctypes.c_double * 3)()
+    nat.check(nat.lib.opl_mlp_probe_scalars(ws.pointer, dev.ptr(out), None, 1, scal))
+    assert 2.0 < scal[0] < 2.7 and scal[2] > 0.0, (scal[0], scal[2])
+
+    # ---- end to end through the reference-shaped API with HOST buffers ---------------------------
+    e2e = None
+    e2e_cold = None
+    if world == 1:
+        w_host = torch.empty(n, dtype=torch.float64).pin_memory().numpy()
+        w_host[:] = w
+        model._get_obj_jac(w_host, x, y)            # first call uploads the dataset (outside the timing)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            obj, grad = model._get_obj_jac(w_host, x, y)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        assert abs(obj - scal[0] * 1.0) < 1.0
+        e2e = {"value": args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(n * 8),
+               "d2h_bytes_per_step": int(n * 8 + 8 + 4),
+               "note": "MLP._get_obj_jac(params_host, X_host, Y_host): parameters H2D from pinned memory, gradient + "
+                       "objective D2H every step; the 60000x784 dataset was uploaded by the first call and is "
+                       "recognised as resident (fingerprint) on later calls, as in a train() run"}
+        cold_steps = max(2, min(5, args.steps))
+        t0 = time.perf_counter()
+        for _ in range(cold_steps):
+            model._workspace.resident = None        # force the dataset upload inside the step
+            model._get_obj_jac(w_host, x, y)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        e2e_cold = {"value": cold_steps / dt, "unit": UNIT,
+                    "h2d_bytes_per_step": int((x.size + y.size + n) * 8), "d2h_bytes_per_step": int(n * 8 + 12),
+                    "note": "same call with the dataset re-uploaded from pageable host memory every step"}
+
+    # ---- BFGS fused update + products pass at n = 83328 (H row-sharded over the ranks) ----------
+    bfgs = run_bfgs(args, torch, dist, nat, dev, world, rank, barrier, max_over_ranks)
+
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peaks, peak_src = measured_peaks()
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[1]: 60000x784 synthetic per GPU, MLP (784,256,10) softplus/softmax + cross "
+                               "entropy, FP64 parity mode, one full-batch obj+grad evaluation per step",
+                   "rows_per_gpu": ROWS, "shape": list(SHAPE), "n_weights": int(n),
+                   "parallelism": "batch rows sharded x%d, NCCL all-reduce of [grad;obj]" % world if world > 1 else "single GPU",
+                   "l2": "inputs larger than L2 (X shard 376 MB, activations 3 x 123 MB vs 126 MB L2)"},
+        "gpu_launches": int(launches + bfgs.get("launches", 0)),
+        "clocks": clocks,
+        "bfgs": bfgs,
+    }
+    if e2e:
+        line["e2e"] = e2e
+        line["e2e_cold"] = e2e_cold
+    if profile and stage_ms:
+        flops_eval = algorithmic_flops(SHAPE, ROWS)
+        names = {1: "forward GEMM", 2: "row kernel", 3: "dW GEMM", 4: "dW reduce", 5: "dA GEMM", 6: "bias colsum",
+                 7: "loss", 0: "trial point"}
+        per_kind = {k: sum(v) / args.steps for k, v in stage_ms.items()}
+        total = sum(per_kind.values())
+        line["stage_ms"] = {"%s L%d" % (names.get(k // 100, "?"), k % 100): round(v, 4) for k, v in sorted(per_kind.items())}
+        # dominant kernel: the FP64 DMMA GEMM (forward layer 0 + dW layer 0 are ~98% of the flops)
+        gemm_ms = sum(v for k, v in per_kind.items() if k // 100 in (1, 3, 5))
+        fwd0 = per_kind.get(100, None)
+        fp64_peak = fp64_gemm_peak(torch)
+        gemm_flops = flops_eval
+        achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
+        line["roofline"] = {
+            "bound": "tensor", "kernel": "gemm_f64_kernel (DMMA.8x8x4, FP64 tensor pipe; 5 launches per evaluation)",
+            "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+            "traffic": None,
+            "peak_source": "measured in this run: cuBLAS DGEMM 8192^3 via torch.matmul, best of 5 (MEASURED_PEAKS.json "
+                           "has no FP64 figure)",
+            "algorithmic_flops_per_eval": gemm_flops, "gemm_ms_per_eval": gemm_ms,
+            "gemm_share_of_step": gemm_ms / total if total else None,
+            "fwd_layer0": None if fwd0 is None else {
+                "flops": 2.0 * ROWS * SHAPE[0] * SHAPE[1], "ms": fwd0,
+                "tflops": 2.0 * ROWS * SHAPE[0] * SHAPE[1] / (fwd0 * 1e-3) / 1e12},
+        }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        times = cpu_objgrad_times(5, 1)
+        threads, api = host_threads()
+        line["cpu_baseline"] = {"value": 1.0 / min(times), "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": "full workload (60000 rows), 1 warm-up + best of 5 evaluations of the oracle "
+                                          "port (NumPy float64 + %s, %d threads)" % (api, threads)}
+        line["bfgs"]["cpu_baseline"] = cpu_bfgs_baseline()
+    line["bfgs"]["roofline"]["peak"] = peaks["hbm_gbs"]
+    line["bfgs"]["roofline"]["peak_source"] = peak_src
+    line["bfgs"]["roofline"]["frac"] = line["bfgs"]["roofline"]["achieved"] / (peaks["hbm_gbs"] * world)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_bfgs(args, torch, dist, nat, dev, world, rank, barrier, max_over_ranks):
+    """Time the fused BFGS pass (apply pending rank-2 update in place + H.[y g] + y^T.H) + finish."""
+    n = args.bfgs_n
+    per = -(-n // world)
+    begin, end = min(n, rank * per), min(n, (rank + 1) * per)
+    handle = ctypes.c_void_p()
+    nat.check(nat.lib.opl_bfgs_create(ctypes.byref(handle), n, begin, end, dev.stream_ptr()))
+    nat.check(nat.lib.opl_bfgs_fill_synthetic(handle, 7))
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    g_prev = torch.randn(n, dtype=torch.float64, device="cuda", generator=gen)
+    u = torch.zeros(per * world, dtype=torch.float64, device="cuda")
+    w = torch.zeros_like(u)
+    v = torch.zeros(n, dtype=torch.float64, device="cuda")
+    d = torch.empty(n, dtype=torch.float64, device="cuda")
+    vecs = [(torch.randn(n, dtype=torch.float64, device="cuda", generator=gen) * 1e-2,
+             torch.randn(n, dtype=torch.float64, device="cuda", generator=gen)) for _ in range(4)]
+
+    def step(i):
+        s, g = vecs[i % len(vecs)]
+        nat.check(nat.lib.opl_bfgs_pass_device(handle, dev.ptr(g), dev.ptr(s), dev.ptr(g_prev), 0, dev.ptr(u),
+                                               dev.ptr(v), dev.ptr(w)))
+        if world > 1:
+            dist.all_gather_into_tensor(u, u[begin:begin + per].clone())
+            dist.all_gather_into_tensor(w, w[begin:begin + per].clone())
+            dist.all_reduce(v)
+        nat.check(nat.lib.opl_bfgs_finish_device(handle, dev.ptr(g), dev.ptr(s), dev.ptr(g_prev), 0, dev.ptr(u),
+                                                 dev.ptr(v), dev.ptr(w), dev.ptr(d)))
+
+    steps = max(3, min(args.steps, 10))
+    for i in range(max(3, args.warmup)):
+        step(i)
+    barrier()
+    l0 = nat.lib.opl_bfgs_launch_count(handle)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(i)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    launches = nat.lib.opl_bfgs_launch_count(handle) - l0
+    ok = bool(torch.isfinite(d).all().item())
+    nat.check(nat.lib.opl_bfgs_destroy(handle))
+    bytes_iter = 2.0 * n * n * 8          # one read + one write of H (all ranks together)
+    gbs = bytes_iter / (ms * 1e-3) / 1e9
+    return {"metric": "BFGS H-update HBM GB/s", "n": n, "h_bytes": n * n * 8, "rows_per_gpu": end - begin,
+            "ms_per_iter": ms, "value": gbs, "unit": "GB/s (2*n^2*8 bytes per iteration: in-place rank-2 update fused "
+                                                     "with H.[y g] and y^T.H, all GPUs)",
+            "steps": steps, "finite": ok, "launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "bfgs_pass_kernel", "achieved": gbs, "peak": None, "unit": "GB/s",
+                         "frac": None, "traffic": None}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--bfgs-n", type=int, default=BFGS_N)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

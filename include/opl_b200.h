@@ -1,0 +1,215 @@
+/*
+ * opl_b200.h -- C ABI of the B200-native hot path of optimal-py-learning.
+ *
+ * Drop-in boundary.  Every entry point replaces a NumPy call
+ * site of the reference (`learning` 0.1.0, paths relative to /root/reference/learning);
+ * the reference-side binding (ctypes) is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers + sizes only; no torch / C++ types cross this boundary.
+ *   - `_host` entry points take HOST buffers (what the reference holds: NumPy float64
+ *     arrays) and do the host<->device copies themselves; `_device` entry points take
+ *     DEVICE pointers (float64) valid on the current CUDA device.
+ *   - all work is enqueued on the stream given at create time (NULL = default stream);
+ *     `_host` calls and calls with a `double *host_out` argument synchronise that stream
+ *     before returning, all other calls are asynchronous.
+ *   - every function returns OPL_OK (0) or a negative OPL_E_* code; opl_last_error()
+ *     returns a thread-local message.  There is NO CPU fallback: without a CUDA device
+ *     every compute entry point returns OPL_E_CUDA.
+ *   - flat parameter / gradient layout is the reference's (architecture/mlp.py:313-327):
+ *       [ bias(d1) ; W0 (d0 x d1 row-major) ; W1 (d1 x d2) ; ... ]   length n.
+ */
+#ifndef OPL_B200_H
+#define OPL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OPL_OK           0
+#define OPL_E_ARG       -1   /* bad argument (shape mismatch, unknown id, null pointer) */
+#define OPL_E_CUDA      -2   /* CUDA runtime error / no device                          */
+#define OPL_E_STATE     -3   /* call sequence error (no data set, ...)                  */
+#define OPL_E_DOMAIN    -4   /* log(negative) in cross entropy: the reference raises
+                                FloatingPointError (error.py:89-91)                    */
+
+/* transfer ids: transfer.py:47-130 / calculate.py:91-176 */
+#define OPL_TRANSFER_LINEAR   0
+#define OPL_TRANSFER_TANH     1
+#define OPL_TRANSFER_SOFTPLUS 2   /* the reference's "ReluTransfer" is softplus */
+#define OPL_TRANSFER_GAUSSIAN 3   /* param = variance */
+#define OPL_TRANSFER_SOFTMAX  4
+
+/* error ids: error.py:46-116 */
+#define OPL_ERROR_MSE            0
+#define OPL_ERROR_CROSS_ENTROPY  1
+
+/* arithmetic modes */
+#define OPL_PRECISION_F64   0   /* parity mode: FP64 DMMA, matches NumPy float64 to 1e-10  */
+#define OPL_PRECISION_TF32  1   /* fast mode: tcgen05 TF32, FP32 accumulate (1e-3)         */
+
+const char *opl_last_error(void);
+int opl_version(void);
+/* number of CUDA devices visible (0 on a CPU-only host; never an error) */
+int opl_device_count(void);
+
+/* =====================================================================================
+ * MLP objective / gradient workspace
+ *   replaces MLP.activate / _get_obj / _get_obj_jac / _get_jacobians
+ *   (architecture/mlp.py:134-163, 195-276)
+ * ===================================================================================== */
+typedef struct opl_mlp opl_mlp;
+
+/* widths[0..n_widths-1] = the reference's `shape` tuple; transfer_ids / transfer_params have
+ * n_widths-1 entries.  max_rows = capacity (patterns resident on this device). */
+int opl_mlp_create(opl_mlp **out, int32_t n_widths, const int64_t *widths,
+                   const int32_t *transfer_ids, const double *transfer_params,
+                   int32_t error_id, int64_t max_rows, int32_t precision, void *cuda_stream);
+int opl_mlp_destroy(opl_mlp *ws);
+int64_t opl_mlp_param_count(const opl_mlp *ws);
+
+/* Make `rows` patterns resident (copied into the workspace).  `norm_rows` is the N of the
+ * reference's 1/N (cross entropy, error.py:115-116) and 1/(N*C) (MSE, error.py:62) scales:
+ * rows for a single device, the GLOBAL row count when the batch is sharded over ranks. */
+int opl_mlp_set_data_host(opl_mlp *ws, const double *x, const double *y, int64_t rows, int64_t norm_rows);
+int opl_mlp_set_data_device(opl_mlp *ws, const double *x_dev, const double *y_dev, int64_t rows, int64_t norm_rows);
+
+/* ---- host-buffer calls: exactly what MLP._get_obj / _get_obj_jac / activate receive ---- */
+/* _get_obj (mlp.py:195-199) */
+int opl_mlp_obj_host(opl_mlp *ws, const double *params, double *obj_out);
+/* _get_obj_jac (mlp.py:202-208): grad_out has n entries, flat layout */
+int opl_mlp_obj_jac_host(opl_mlp *ws, const double *params, double *obj_out, double *grad_out);
+/* activate (mlp.py:134-163) on `rows` fresh patterns (rows <= max_rows); out is rows x d_L.
+ * Does not disturb the resident training data. */
+int opl_mlp_activate_host(opl_mlp *ws, const double *params, const double *x, int64_t rows, double *out);
+
+/* ---- device-pointer calls used by the device-resident optimizer stack ---- */
+/* Evaluate at  x + alpha*dir  (dir_dev may be NULL => at x): the line-search probe
+ * `obj_jac_func(parameters + step_size * step_dir)` (linesearch.py:392-399).
+ * grad_out_dev has n+1 entries: [ flat gradient ; objective ].  With want_grad == 0 only
+ * entry n is written (the _get_obj path used by backtracking, linesearch.py:217).
+ * Partial sums only: when the batch is sharded the caller all-reduces the n+1 doubles.
+ * Asynchronous. */
+int opl_mlp_eval_device(opl_mlp *ws, const double *x_dev, double alpha, const double *dir_dev,
+                        int32_t want_grad, double *grad_out_dev);
+/* Read back the probe scalars after (optionally all-reducing) grad_out_dev:
+ *   host_out[0] = objective, [1] = grad . dir (0 if dir NULL), [2] = ||grad||^2.
+ * Synchronises; returns OPL_E_DOMAIN if the evaluation hit log(negative). */
+int opl_mlp_probe_scalars(opl_mlp *ws, const double *grad_dev, const double *dir_dev,
+                          int32_t have_grad, double *host_out);
+/* activate on device buffers: x_dev rows x d0 -> out_dev rows x d_L */
+int opl_mlp_activate_device(opl_mlp *ws, const double *params_dev, const double *x_dev, int64_t rows,
+                            double *out_dev);
+/* number of kernels this workspace has launched since creation (bench.py gpu_launches) */
+int64_t opl_mlp_launch_count(const opl_mlp *ws);
+/* Per-launch device timing for the roofline report: while enabled, a CUDA event is recorded on
+ * the workspace stream before every kernel of an evaluation.  profile_read synchronises and
+ * returns, per launch, kind = stage*100 + layer (stage 0 trial point, 1 forward GEMM, 2 row
+ * kernel, 3 dW GEMM, 4 dW split-K reduce, 5 dA GEMM, 6 bias column sum, 7 loss) and its
+ * duration in ms, then clears the record. */
+int opl_mlp_profile(opl_mlp *ws, int32_t enable);
+int opl_mlp_profile_read(opl_mlp *ws, int32_t capacity, int32_t *kinds, float *ms, int32_t *count);
+
+/* ---- stand-alone host-buffer forms of the plugin objects' own methods (not on the training
+ *      path; they run the same row kernel so the classes stay usable on their own) ---- */
+/* Transfer.__call__ (transfer.py:33-130) on a rows x cols matrix */
+int opl_transfer_apply_host(int32_t transfer_id, double param, const double *x, int64_t rows, int64_t cols,
+                            double *out);
+/* upstream . J_f(x): the product MLP backprop forms (mlp.py:279-295); with upstream = ones and an
+ * element-wise transfer this is Transfer.derivative */
+int opl_transfer_backprop_host(int32_t transfer_id, double param, const double *x, const double *upstream,
+                               int64_t rows, int64_t cols, double *out);
+/* ErrorFunc.__call__ / derivative (error.py:46-116); deriv_out (rows x cols) may be NULL */
+int opl_error_host(int32_t error_id, const double *a, const double *b, int64_t rows, int64_t cols,
+                   double *err_out, double *deriv_out);
+/* calculate.dsoftmax (calculate.py:156-176): rows x cols x cols Jacobians from the softmax OUTPUT */
+int opl_softmax_jacobian_host(const double *y, int64_t rows, int64_t cols, double *jac_out);
+
+/* =====================================================================================
+ * BFGS inverse-Hessian state   (optimize/optimizer.py:234-338)
+ *   H is n x n float64 row-major, rows [row_begin,row_end) resident on this device.
+ *   The rank-2 update  H+ = (I - rho s y^T) H (I - rho y s^T) + rho s s^T  is applied IN
+ *   PLACE and lazily: one fused pass per iteration reads H once, applies the pending
+ *   update, writes H+ and accumulates H+.[y g] and y^T.H+ for the next direction
+ *   (2 n^2 8 bytes per iteration instead of the reference's 4 n^3 flop).
+ * ===================================================================================== */
+typedef struct opl_bfgs opl_bfgs;
+
+#define OPL_BFGS_SEED_IDENTITY         0   /* initial_hessian_identity        optimizer.py:148 */
+#define OPL_BFGS_SEED_SCALED_IDENTITY  1   /* initial_hessian_scaled_identity optimizer.py:154 */
+
+int opl_bfgs_create(opl_bfgs **out, int64_t n, int64_t row_begin, int64_t row_end, void *cuda_stream);
+int opl_bfgs_destroy(opl_bfgs *b);
+/* BFGS.reset (optimizer.py:223-232): forget H */
+int opl_bfgs_reset(opl_bfgs *b);
+
+/* One call of BFGS._get_approx_inv_hessian + `-(H.dot(jac))` (optimizer.py:242-285), single
+ * device.  prev_step_dev == NULL => first iteration (dir = -grad, identity never formed).
+ * Otherwise s = prev_step, y = grad - prev_grad.  Asynchronous. */
+int opl_bfgs_direction_device(opl_bfgs *b, const double *grad_dev, const double *prev_step_dev,
+                              const double *prev_grad_dev, int32_t seed_mode, double *dir_out_dev);
+
+/* Row-sharded form (one rank per GPU): pass -> (caller: all-gather u,w slices; all-reduce v)
+ * -> finish.  u_dev,v_dev,w_dev are full n-vectors owned by the caller; pass writes
+ * u[row_begin:row_end] = (H+ y) rows, w[...] = (H+ g) rows and v = the LOCAL rows'
+ * contribution to y^T H+ (all n columns).  On the first two iterations (no H yet) pass is a
+ * no-op and finish works from vectors alone. */
+int opl_bfgs_pass_device(opl_bfgs *b, const double *grad_dev, const double *prev_step_dev,
+                         const double *prev_grad_dev, int32_t seed_mode,
+                         double *u_dev, double *v_dev, double *w_dev);
+int opl_bfgs_finish_device(opl_bfgs *b, const double *grad_dev, const double *prev_step_dev,
+                           const double *prev_grad_dev, int32_t seed_mode,
+                           const double *u_dev, const double *v_dev, const double *w_dev,
+                           double *dir_out_dev);
+
+/* Apply any pending update and copy the local rows of H (the reference's
+ * `_prev_inv_hessian`) to h_out_dev ((row_end-row_begin) x n).  OPL_E_STATE if no H exists yet. */
+int opl_bfgs_materialize_device(opl_bfgs *b, double *h_out_dev);
+/* Test / benchmark hooks: load an explicit H (device, local rows) as the current state;
+ * run only the fused update+products pass and report nothing (timed by the caller). */
+int opl_bfgs_load_device(opl_bfgs *b, const double *h_dev);
+int opl_bfgs_fill_synthetic(opl_bfgs *b, uint64_t seed);
+int64_t opl_bfgs_launch_count(const opl_bfgs *b);
+/* 0 = no H, 1 = seed pending (H not materialised), 2 = H resident */
+int opl_bfgs_state(const opl_bfgs *b);
+
+/* =====================================================================================
+ * L-BFGS two-loop recursion   (optimize/optimizer.py:414-508)
+ * ===================================================================================== */
+typedef struct opl_lbfgs opl_lbfgs;
+
+#define OPL_LBFGS_GAMMA_ONE     0   /* initial_hessian_one_scalar   optimizer.py:341 */
+#define OPL_LBFGS_GAMMA_OLDEST  1   /* initial_hessian_gamma_scalar optimizer.py:346 (oldest pair) */
+
+/* memory = num_remembered_iterations (<= 0: unbounded, grows on demand) */
+int opl_lbfgs_create(opl_lbfgs **out, int64_t n, int32_t memory, void *cuda_stream);
+int opl_lbfgs_destroy(opl_lbfgs *l);
+int opl_lbfgs_reset(opl_lbfgs *l);
+/* LBFGS._update_diffs + _lbfgs_step_dir: pop the oldest pair if the history is full, push
+ * (s = prev_step, y = grad - prev_grad) when prev_step_dev != NULL, then run the two-loop
+ * recursion on `grad`.  Asynchronous. */
+int opl_lbfgs_direction_device(opl_lbfgs *l, const double *grad_dev, const double *prev_step_dev,
+                               const double *prev_grad_dev, int32_t gamma_mode, double *dir_out_dev);
+int32_t opl_lbfgs_history_len(const opl_lbfgs *l);
+int64_t opl_lbfgs_launch_count(const opl_lbfgs *l);
+
+/* =====================================================================================
+ * n-vector helpers for the optimizer stack (float64, device pointers)
+ *   replace the NumPy expressions at optimizer.py:97,136-141,251-253,429-431,
+ *   linesearch.py:259,397 and initialstep.py:146,223.
+ * ===================================================================================== */
+/* out = x + fl(a*d) (+ fl(b*p) if p != NULL); products and sums rounded separately (no FMA
+ * contraction) so the iterate matches NumPy bit for bit.  out may alias x. */
+int opl_vec_axpy_device(int64_t n, const double *x, double a, const double *d, double b,
+                        const double *p, double *out, void *cuda_stream);
+/* out = a * x */
+int opl_vec_scale_device(int64_t n, double a, const double *x, double *out, void *cuda_stream);
+/* host_out[0] = x . y   (deterministic two-stage reduction; synchronises) */
+int opl_vec_dot_device(int64_t n, const double *x, const double *y, double *host_out, void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPL_B200_H */

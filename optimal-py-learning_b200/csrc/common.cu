@@ -1,0 +1,134 @@
+// Error plumbing, device queries and the n-vector helpers of the optimizer stack.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace opl {
+
+std::string &last_error() {
+    static thread_local std::string msg;
+    return msg;
+}
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    last_error() = buf;
+    return code;
+}
+
+int sm_count() {
+    static int cached = 0;
+    if (cached == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            cached = n;
+        else
+            cached = 148;
+    }
+    return cached;
+}
+
+// ---------------------------------------------------------------------------------------
+// vector kernels.  Products and sums are rounded separately (__dmul_rn/__dadd_rn block FMA
+// contraction) so `x + a*d` is bit-identical to NumPy's two-step evaluation
+// (optimizer.py:97,136-141,253,431; linesearch.py:394).
+// ---------------------------------------------------------------------------------------
+__global__ void axpy_kernel(int64_t n, const double *__restrict__ x, double a, const double *__restrict__ d,
+                            double b, const double *__restrict__ p, double *__restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double v = __dadd_rn(x[i], __dmul_rn(a, d[i]));
+        if (p) v = __dadd_rn(v, __dmul_rn(b, p[i]));
+        out[i] = v;
+    }
+}
+
+__global__ void scale_kernel(int64_t n, double a, const double *__restrict__ x, double *__restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = __dmul_rn(a, x[i]);
+}
+
+// stage 1 of a deterministic dot: one partial per block
+__global__ void dot_partial_kernel(int64_t n, const double *__restrict__ x, const double *__restrict__ y,
+                                   double *__restrict__ partial) {
+    __shared__ double scratch[33];
+    double s = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        s += x[i] * y[i];
+    s = block_sum(s, scratch);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+__global__ void dot_final_kernel(int nparts, const double *__restrict__ partial, double *__restrict__ out) {
+    __shared__ double scratch[33];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x) s += partial[i];
+    s = block_sum(s, scratch);
+    if (threadIdx.x == 0) out[0] = s;
+}
+
+static int vec_grid(int64_t n, int threads) {
+    int64_t g = ceil_div(n, threads);
+    int64_t cap = 4 * (int64_t)sm_count();
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+}  // namespace opl
+
+using namespace opl;
+
+extern "C" {
+
+const char *opl_last_error(void) { return last_error().c_str(); }
+
+int opl_version(void) { return 100; }
+
+int opl_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int opl_vec_axpy_device(int64_t n, const double *x, double a, const double *d, double b, const double *p,
+                        double *out, void *cuda_stream) {
+    if (n < 0 || (n > 0 && (!x || !d || !out))) return fail(OPL_E_ARG, "opl_vec_axpy_device: null pointer");
+    if (n == 0) return OPL_OK;
+    axpy_kernel<<<vec_grid(n, 256), 256, 0, (cudaStream_t)cuda_stream>>>(n, x, a, d, b, p, out);
+    OPL_LAUNCH_CHECK();
+    return OPL_OK;
+}
+
+int opl_vec_scale_device(int64_t n, double a, const double *x, double *out, void *cuda_stream) {
+    if (n < 0 || (n > 0 && (!x || !out))) return fail(OPL_E_ARG, "opl_vec_scale_device: null pointer");
+    if (n == 0) return OPL_OK;
+    scale_kernel<<<vec_grid(n, 256), 256, 0, (cudaStream_t)cuda_stream>>>(n, a, x, out);
+    OPL_LAUNCH_CHECK();
+    return OPL_OK;
+}
+
+int opl_vec_dot_device(int64_t n, const double *x, const double *y, double *host_out, void *cuda_stream) {
+    if (n < 0 || !host_out || (n > 0 && (!x || !y))) return fail(OPL_E_ARG, "opl_vec_dot_device: null pointer");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int blocks = n > 0 ? vec_grid(n, 256) : 1;
+    double *scratch = nullptr;
+    OPL_CUDA(cudaMallocAsync(&scratch, sizeof(double) * (blocks + 1), st));
+    dot_partial_kernel<<<blocks, 256, 0, st>>>(n, x, y, scratch);
+    dot_final_kernel<<<1, 256, 0, st>>>(blocks, scratch, scratch + blocks);
+    cudaError_t e = cudaMemcpyAsync(host_out, scratch + blocks, sizeof(double), cudaMemcpyDeviceToHost, st);
+    cudaFreeAsync(scratch, st);
+    if (e != cudaSuccess) return fail(OPL_E_CUDA, "dot readback: %s", cudaGetErrorString(e));
+    OPL_CUDA(cudaStreamSynchronize(st));
+    OPL_LAUNCH_CHECK();
+    return OPL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,77 @@
+// Shared helpers for the opl_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "opl_b200.h"
+
+namespace opl {
+
+// thread-local error text returned by opl_last_error()
+std::string &last_error();
+int fail(int code, const char *fmt, ...);
+
+#define OPL_CUDA(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            return ::opl::fail(OPL_E_CUDA, "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, \
+                               cudaGetErrorString(_e));                                        \
+    } while (0)
+
+#define OPL_LAUNCH_CHECK()                                                                     \
+    do {                                                                                       \
+        cudaError_t _e = cudaGetLastError();                                                   \
+        if (_e != cudaSuccess)                                                                 \
+            return ::opl::fail(OPL_E_CUDA, "kernel launch failed at %s:%d: %s", __FILE__,      \
+                               __LINE__, cudaGetErrorString(_e));                              \
+    } while (0)
+
+constexpr double kBig = 1.7976931348623157e308;   // numpy.nan_to_num's finite stand-in for inf
+
+int sm_count();   // multiprocessors of the current device (cached)
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------------------
+// device-side reductions
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block-wide sum; result valid in every thread.  `scratch` holds >= 33 doubles.
+__device__ __forceinline__ double block_sum(double v, double *scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarps = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        double t = lane < nwarps ? scratch[lane] : 0.0;
+        t = warp_sum(t);
+        if (lane == 0) scratch[32] = t;
+    }
+    __syncthreads();
+    return scratch[32];
+}
+
+// numpy.nan_to_num for float64: nan -> 0, +inf -> DBL_MAX, -inf -> -DBL_MAX
+__device__ __forceinline__ double nan_to_num(double v) {
+    if (isnan(v)) return 0.0;
+    if (isinf(v)) return v > 0 ? kBig : -kBig;
+    return v;
+}
+
+}  // namespace opl

@@ -1,0 +1,906 @@
+// MLP objective / gradient workspace (parity mode, FP64).
+//
+// Replaces MLP.activate / _get_obj / _get_obj_jac / _get_jacobians of the reference
+// (learning/architecture/mlp.py:134-163, 195-276) with a fixed kernel schedule per evaluation:
+//
+//   trial point   w = x + alpha*dir                                  (linesearch.py:394)
+//   forward       A_{l+1} = f_l(A_l W_l [+ b]);  D_l = f_l'(Z_l)     NN GEMM, fused epilogue
+//   output rows   softmax / elementwise transfer, MSE / cross entropy, delta_L, loss partials
+//   backward      dW_l = A_l^T delta_l        TN split-K GEMM -> fixed-order reduce into the
+//                                             flat gradient (mlp.py:313-315 layout)
+//                 delta_{l-1} = (delta_l W_l^T) o D_{l-1}            NT GEMM, fused epilogue
+//                 db = 1^T delta_0                                   two-stage column sum
+//   loss          obj = -(sum/N)  or  sum/(N*C)                      -> grad_out[n]
+//
+// Everything is enqueued on one stream; the only host sync is the scalar readback in
+// opl_mlp_probe_scalars / the *_host entry points.
+#include <algorithm>
+#include <vector>
+
+#include "gemm_f64.cuh"
+
+namespace opl {
+
+__global__ void axpy_kernel(int64_t n, const double *__restrict__ x, double a, const double *__restrict__ d,
+                            double b, const double *__restrict__ p, double *__restrict__ out);
+
+// ---------------------------------------------------------------------------------------
+// row-wise kernels: `group` lanes (power of two <= 32) cooperate on one pattern
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double group_sum(double v, int group) {
+    for (int o = group >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double group_max(double v, int group) {
+    for (int o = group >> 1; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__device__ __forceinline__ double transfer_value(int tid, double tparam, double z) {
+    switch (tid) {
+        case OPL_TRANSFER_TANH: return tanh(z);
+        case OPL_TRANSFER_SOFTPLUS: {
+            double r = log(1.0 + exp(z));
+            return isinf(r) ? z : r;
+        }
+        case OPL_TRANSFER_GAUSSIAN: return exp(-(z * z / tparam));
+        default: return z;
+    }
+}
+__device__ __forceinline__ double transfer_slope(int tid, double tparam, double z, double a) {
+    switch (tid) {
+        case OPL_TRANSFER_TANH: return 1.0 - a * a;
+        case OPL_TRANSFER_SOFTPLUS: return 1.0 / (1.0 + exp(-z));
+        case OPL_TRANSFER_GAUSSIAN: return -2.0 * z * a / tparam;
+        default: return 1.0;
+    }
+}
+
+struct RowArgs {
+    const double *Z;   // rows x C pre-activations
+    const double *Y;   // rows x C targets, or null (activate only)
+    const double *G;   // rows x C explicit upstream gradient instead of an error function, or null
+    double *A;         // rows x C activations out, or null (may alias Z)
+    double *D;         // rows x C delta out, or null
+    int64_t rows;
+    int C;
+    int tid;           // output transfer
+    double tparam;
+    int eid;           // error id
+    double ce_div;     // -(double)N          (error.py:115-116)
+    double mse_mul;    // 2.0 / (N * C)       (error.py:62)
+    double *loss_partial;   // one per block, or null
+    int *flag;         // set to 1 on log(negative)
+    int group;
+};
+
+// error term for one output element: returns the upstream gradient, adds to `loss`
+__device__ __forceinline__ double error_term(const RowArgs &r, double a, double y, double &loss, bool &bad) {
+    if (r.eid == OPL_ERROR_MSE) {   // error.py:58-64
+        double d = a - y;
+        loss += d * d;
+        return d * r.mse_mul;
+    }
+    // cross entropy, error.py:89-116
+    if (a < 0.0) bad = true;
+    loss += nan_to_num(log(a)) * y;
+    return nan_to_num(y / a) / r.ce_div;
+}
+
+__global__ void __launch_bounds__(256) output_rows_kernel(const RowArgs r) {
+    __shared__ double scratch[33];
+    const int group = r.group;
+    const int gl = threadIdx.x & (group - 1);
+    const int rows_per_block = blockDim.x / group;
+    const int slot = threadIdx.x / group;
+    const bool softmax = r.tid == OPL_TRANSFER_SOFTMAX;
+    double loss = 0.0;
+    bool bad = false;
+    const int64_t nblocks = (r.rows + rows_per_block - 1) / rows_per_block;
+    for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        const int64_t row = blk * rows_per_block + slot;
+        const bool live = row < r.rows;
+        const double *z = r.Z + (live ? row : 0) * (int64_t)r.C;
+        const double *y = r.Y ? r.Y + (live ? row : 0) * (int64_t)r.C : nullptr;
+        double mx = -INFINITY, den = 1.0;
+        if (softmax) {   // calculate.py:152-153
+            if (live)
+                for (int c = gl; c < r.C; c += group) mx = fmax(mx, z[c]);
+            mx = group_max(mx, group);
+            double s = 0.0;
+            if (live)
+                for (int c = gl; c < r.C; c += group) s += exp(z[c] - mx);
+            den = group_sum(s, group);
+        }
+        double t = 0.0;
+        if (live) {
+            for (int c = gl; c < r.C; c += group) {
+                const double zc = z[c];
+                const double a = softmax ? exp(zc - mx) / den : transfer_value(r.tid, r.tparam, zc);
+                if (y || r.G) {
+                    const double g = r.G ? r.G[row * r.C + c] : error_term(r, a, y[c], loss, bad);
+                    if (softmax) t += g * a;
+                    else if (r.D) r.D[row * r.C + c] = g * transfer_slope(r.tid, r.tparam, zc, a);
+                }
+                if (r.A && !(softmax && r.D && r.A == r.Z)) r.A[row * r.C + c] = a;
+            }
+        }
+        if (softmax && r.D && (y || r.G)) {   // delta_k = a_k (g_k - sum_j g_j a_j): dsoftmax contracted (mlp.py:295)
+            t = group_sum(t, group);
+            if (live) {
+                double dummy = 0.0;
+                bool dummy_bad = false;
+                for (int c = gl; c < r.C; c += group) {
+                    const double a = exp(z[c] - mx) / den;
+                    const double g = r.G ? r.G[row * r.C + c] : error_term(r, a, y[c], dummy, dummy_bad);
+                    r.D[row * r.C + c] = a * (g - t);
+                    if (r.A && r.A == r.Z) r.A[row * r.C + c] = a;
+                }
+            }
+        }
+    }
+    if (bad) *r.flag = 1;
+    if (r.loss_partial) {
+        loss = block_sum(loss, scratch);
+        if (threadIdx.x == 0) r.loss_partial[blockIdx.x] = loss;
+    }
+}
+
+// hidden softmax layer backward: delta = a o (g - sum g a), in place over g
+__global__ void __launch_bounds__(256)
+softmax_backward_rows_kernel(double *G, const double *A, int64_t rows, int C, int group) {
+    const int gl = threadIdx.x & (group - 1);
+    const int rows_per_block = blockDim.x / group;
+    const int slot = threadIdx.x / group;
+    const int64_t nblocks = (rows + rows_per_block - 1) / rows_per_block;
+    for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        const int64_t row = blk * rows_per_block + slot;
+        const bool live = row < rows;
+        double t = 0.0;
+        if (live)
+            for (int c = gl; c < C; c += group) t += G[row * C + c] * A[row * C + c];
+        t = group_sum(t, group);
+        if (live)
+            for (int c = gl; c < C; c += group) G[row * C + c] = A[row * C + c] * (G[row * C + c] - t);
+    }
+}
+
+// obj = -(sum/N) for cross entropy, sum/(N*C) for MSE
+__global__ void loss_final_kernel(const double *partial, int nparts, int eid, double n_rows, double n_cols,
+                                  double *out) {
+    __shared__ double scratch[33];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x) s += partial[i];
+    s = block_sum(s, scratch);
+    if (threadIdx.x == 0) out[0] = eid == OPL_ERROR_MSE ? s / (n_rows * n_cols) : -(s / n_rows);
+}
+
+// column sums of a rows x cols matrix, stage 1: partial[blockIdx.y][col]
+__global__ void colsum_partial_kernel(const double *__restrict__ D, int64_t rows, int cols, int64_t rows_per_block,
+                                      double *__restrict__ partial) {
+    __shared__ double tile[8][33];
+    const int col = blockIdx.x * 32 + threadIdx.x;
+    const int64_t r0 = blockIdx.y * rows_per_block;
+    const int64_t r1 = min(rows, r0 + rows_per_block);
+    double s = 0.0;
+    if (col < cols)
+        for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) s += D[r * cols + col];
+    tile[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && col < cols) {
+        double tot = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) tot += tile[k][threadIdx.x];
+        partial[(int64_t)blockIdx.y * cols + col] = tot;
+    }
+}
+
+// trial point w = x + fl(alpha*dir) (or a copy), and per-evaluation flag reset
+__global__ void trial_point_kernel(int64_t n, const double *__restrict__ x, double alpha,
+                                   const double *__restrict__ dir, double *__restrict__ w, int *flag) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *flag = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        w[i] = dir ? __dadd_rn(x[i], __dmul_rn(alpha, dir[i])) : x[i];
+}
+
+// probe scalars: partial[2b] = sum g*d, partial[2b+1] = sum g*g
+__global__ void probe_partial_kernel(int64_t n, const double *__restrict__ g, const double *__restrict__ d,
+                                     double *__restrict__ partial) {
+    __shared__ double scratch[33];
+    double gd = 0.0, gg = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double gi = g[i];
+        if (d) gd += gi * d[i];
+        gg += gi * gi;
+    }
+    gd = block_sum(gd, scratch);
+    gg = block_sum(gg, scratch);
+    if (threadIdx.x == 0) {
+        partial[2 * blockIdx.x] = gd;
+        partial[2 * blockIdx.x + 1] = gg;
+    }
+}
+__global__ void probe_final_kernel(int nparts, const double *__restrict__ partial, const double *obj,
+                                   double *__restrict__ out) {
+    __shared__ double scratch[33];
+    double gd = 0.0, gg = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x) {
+        gd += partial[2 * i];
+        gg += partial[2 * i + 1];
+    }
+    gd = block_sum(gd, scratch);
+    gg = block_sum(gg, scratch);
+    if (threadIdx.x == 0) {
+        out[0] = obj[0];
+        out[1] = gd;
+        out[2] = gg;
+    }
+}
+
+// per-row softmax Jacobian from the OUTPUT y (calculate.py:165-174): J[j][k] = -y_j y_k, J[j][j] = y_j (1 - y_j)
+__global__ void softmax_jacobian_kernel(const double *__restrict__ y, int64_t rows, int C, double *__restrict__ jac) {
+    const int64_t total = rows * (int64_t)C * C;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i % C);
+        const int j = (int)((i / C) % C);
+        const int64_t row = i / ((int64_t)C * C);
+        const double yj = y[row * C + j], yk = y[row * C + k];
+        jac[i] = j == k ? yj * (1. - yj) : -yj * yk;
+    }
+}
+
+}  // namespace opl
+
+using namespace opl;
+
+// ---------------------------------------------------------------------------------------
+// workspace
+// ---------------------------------------------------------------------------------------
+struct opl_mlp {
+    int layers = 0;                    // weight matrices
+    std::vector<int64_t> width;        // layers + 1
+    std::vector<int> transfer;
+    std::vector<double> tparam;
+    std::vector<int64_t> w_off;        // offset of W_l in the flat vector
+    int error_id = 0;
+    int precision = 0;
+    int64_t n = 0, max_rows = 0, rows = 0, norm_rows = 0;
+    cudaStream_t stream = nullptr;
+
+    double *x_own = nullptr, *y_own = nullptr;   // owned copies (set_data_host)
+    const double *x = nullptr, *y = nullptr;     // resident data (owned or borrowed)
+    double *x_scratch = nullptr;                 // activate() on fresh patterns
+    std::vector<double *> act;      // act[l], l = 1..layers (act[layers] holds Z_L)
+    std::vector<double *> deriv;    // D_l or null
+    std::vector<double *> delta;    // delta_l (aliases deriv[l] when that exists)
+    double *out_act = nullptr;      // A_L
+    double *w_trial = nullptr;      // n + 1
+    double *host_grad = nullptr;    // device staging for *_host calls, n + 1
+    double *partials = nullptr;
+    int64_t partials_len = 0;
+    double *loss_partial = nullptr;
+    int loss_blocks = 0;
+    double *probe_partial = nullptr;
+    int probe_blocks = 0;
+    double *scal = nullptr;         // device: 4 doubles
+    int *flag = nullptr;
+    double *pinned = nullptr;       // host pinned: 4 doubles + flag
+    int64_t launches = 0;
+    // optional per-launch timing (CUDA events on the launch stream): kind = stage*100 + layer
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<int> ev_kind;
+    size_t ev_used = 0;
+};
+
+enum { STAGE_TRIAL = 0, STAGE_FWD = 1, STAGE_ROWS = 2, STAGE_DW = 3, STAGE_DW_REDUCE = 4, STAGE_DA = 5,
+       STAGE_BIAS = 6, STAGE_LOSS = 7, STAGE_END = 9 };
+
+namespace {
+
+// record "a launch of `kind` starts here" (no-op unless profiling)
+void mark(opl_mlp *ws, int kind) {
+    if (!ws->profiling) return;
+    if (ws->ev_used == ws->ev_pool.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        ws->ev_pool.push_back(e);
+        ws->ev_kind.push_back(0);
+    }
+    ws->ev_kind[ws->ev_used] = kind;
+    cudaEventRecord(ws->ev_pool[ws->ev_used], ws->stream);
+    ++ws->ev_used;
+}
+
+int row_group(int c) {
+    int g = 1;
+    while (g < c && g < 32) g <<= 1;
+    return g;
+}
+
+int row_grid(int64_t rows, int group) {
+    const int rows_per_block = 256 / group;
+    int64_t blocks = ceil_div(rows, rows_per_block);
+    const int64_t cap = 8 * (int64_t)sm_count();
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+int free_all(opl_mlp *ws) {
+    cudaFree(ws->x_own);
+    cudaFree(ws->y_own);
+    cudaFree(ws->x_scratch);
+    for (size_t l = 0; l < ws->act.size(); ++l) cudaFree(ws->act[l]);
+    for (size_t l = 0; l < ws->deriv.size(); ++l) cudaFree(ws->deriv[l]);
+    for (size_t l = 0; l < ws->delta.size(); ++l)
+        if (l >= ws->deriv.size() || ws->delta[l] != ws->deriv[l]) cudaFree(ws->delta[l]);
+    cudaFree(ws->out_act);
+    cudaFree(ws->w_trial);
+    cudaFree(ws->host_grad);
+    cudaFree(ws->partials);
+    cudaFree(ws->loss_partial);
+    cudaFree(ws->probe_partial);
+    cudaFree(ws->scal);
+    cudaFree(ws->flag);
+    cudaFreeHost(ws->pinned);
+    for (cudaEvent_t e : ws->ev_pool) cudaEventDestroy(e);
+    return OPL_OK;
+}
+
+int epilogue_for(int transfer) {
+    switch (transfer) {
+        case OPL_TRANSFER_TANH: return EPI_TANH;
+        case OPL_TRANSFER_SOFTPLUS: return EPI_SOFTPLUS;
+        case OPL_TRANSFER_GAUSSIAN: return EPI_GAUSSIAN;
+        default: return EPI_STORE;
+    }
+}
+
+// forward through all layers; leaves Z_L in act[layers]
+int forward(opl_mlp *ws, const double *w, const double *x, int64_t rows, bool keep_deriv) {
+    const double *in = x;
+    for (int l = 0; l < ws->layers; ++l) {
+        GemmArgs a = {};
+        a.A = in;
+        a.lda = ws->width[l];
+        a.B = w + ws->w_off[l];
+        a.ldb = ws->width[l + 1];
+        a.C = ws->act[l + 1];
+        a.ldc = ws->width[l + 1];
+        a.M = (int)rows;
+        a.N = (int)ws->width[l + 1];
+        a.K = (int)ws->width[l];
+        a.k_per_split = (int)(ceil_div(a.K, GEMM_BK) * GEMM_BK);
+        a.bias = l == 0 ? w : nullptr;   // only the first layer has a bias (mlp.py:150-151)
+        a.ldaux = ws->width[l + 1];
+        a.tparam = ws->tparam[l];
+        const bool last = l == ws->layers - 1;
+        a.epi = last ? EPI_STORE : epilogue_for(ws->transfer[l]);
+        a.aux_out = (!last && keep_deriv) ? ws->deriv[l] : nullptr;
+        mark(ws, STAGE_FWD * 100 + l);
+        int rc = launch_gemm_f64(GEMM_NN, a, 1, ws->stream, &ws->launches);
+        if (rc != OPL_OK) return rc;
+        if (!last && ws->transfer[l] == OPL_TRANSFER_SOFTMAX) {
+            mark(ws, STAGE_ROWS * 100 + l);   // hidden softmax: row kernel in place
+            RowArgs r = {};
+            r.Z = ws->act[l + 1];
+            r.A = ws->act[l + 1];
+            r.rows = rows;
+            r.C = a.N;
+            r.tid = OPL_TRANSFER_SOFTMAX;
+            r.flag = ws->flag;
+            r.group = row_group(r.C);
+            output_rows_kernel<<<row_grid(rows, r.group), 256, 0, ws->stream>>>(r);
+            OPL_LAUNCH_CHECK();
+            ++ws->launches;
+        }
+        in = ws->act[l + 1];
+    }
+    return OPL_OK;
+}
+
+int output_stage(opl_mlp *ws, const double *y, int64_t rows, bool want_act, bool want_delta, double *obj_out) {
+    const int L = ws->layers;
+    RowArgs r = {};
+    r.Z = ws->act[L];
+    r.Y = y;
+    r.A = want_act ? ws->out_act : nullptr;
+    r.D = want_delta ? ws->delta[L - 1] : nullptr;
+    r.rows = rows;
+    r.C = (int)ws->width[L];
+    r.tid = ws->transfer[L - 1];
+    r.tparam = ws->tparam[L - 1];
+    r.eid = ws->error_id;
+    r.ce_div = -(double)ws->norm_rows;
+    r.mse_mul = 2.0 / ((double)ws->norm_rows * (double)r.C);
+    r.flag = ws->flag;
+    r.group = row_group(r.C);
+    int grid = row_grid(rows, r.group);
+    if (grid > ws->loss_blocks) grid = ws->loss_blocks;
+    r.loss_partial = y ? ws->loss_partial : nullptr;
+    mark(ws, STAGE_ROWS * 100 + L);
+    output_rows_kernel<<<grid, 256, 0, ws->stream>>>(r);
+    OPL_LAUNCH_CHECK();
+    ++ws->launches;
+    if (y && obj_out) {
+        mark(ws, STAGE_LOSS * 100);
+        loss_final_kernel<<<1, 256, 0, ws->stream>>>(ws->loss_partial, grid, ws->error_id, (double)ws->norm_rows,
+                                                      (double)r.C, obj_out);
+        OPL_LAUNCH_CHECK();
+        ++ws->launches;
+    }
+    return OPL_OK;
+}
+
+int backward(opl_mlp *ws, const double *w, const double *x, int64_t rows, double *grad) {
+    for (int l = ws->layers - 1; l >= 0; --l) {
+        const int din = (int)ws->width[l], dout = (int)ws->width[l + 1];
+        // dW_l = A_l^T delta_l  (mlp.py:269-273), reduction over the patterns
+        {
+            SplitPlan plan = plan_split_k(din, dout, (int)rows);
+            if ((int64_t)plan.splits * din * dout > ws->partials_len)
+                return fail(OPL_E_STATE, "split-K scratch too small (layer %d)", l);
+            GemmArgs a = {};
+            a.A = l == 0 ? x : ws->act[l];
+            a.lda = din;
+            a.B = ws->delta[l];
+            a.ldb = dout;
+            a.M = din;
+            a.N = dout;
+            a.K = (int)rows;
+            a.ldc = dout;
+            a.k_per_split = plan.k_per_split;
+            a.epi = EPI_STORE;
+            mark(ws, STAGE_DW * 100 + l);
+            if (plan.splits == 1) {
+                a.C = grad + ws->w_off[l];
+                int rc = launch_gemm_f64(GEMM_TN, a, 1, ws->stream, &ws->launches);
+                if (rc != OPL_OK) return rc;
+            } else {
+                a.C = ws->partials;
+                a.split_stride = (int64_t)din * dout;
+                int rc = launch_gemm_f64(GEMM_TN, a, plan.splits, ws->stream, &ws->launches);
+                if (rc != OPL_OK) return rc;
+                const int64_t count = (int64_t)din * dout;
+                mark(ws, STAGE_DW_REDUCE * 100 + l);
+                rc = launch_reduce_partials(ws->partials, plan.splits, count, count, grad + ws->w_off[l], ws->stream,
+                                            &ws->launches);
+                if (rc != OPL_OK) return rc;
+            }
+        }
+        if (l == 0) break;
+        // delta_{l-1} = (delta_l W_l^T) o f'_{l-1}   (mlp.py:254-260)
+        GemmArgs a = {};
+        a.A = ws->delta[l];
+        a.lda = dout;
+        a.B = w + ws->w_off[l];   // din x dout row-major == N x K for the NT product
+        a.ldb = dout;
+        a.C = ws->delta[l - 1];
+        a.ldc = din;
+        a.M = (int)rows;
+        a.N = din;
+        a.K = dout;
+        a.k_per_split = (int)(ceil_div(a.K, GEMM_BK) * GEMM_BK);
+        a.ldaux = din;
+        switch (ws->transfer[l - 1]) {
+            case OPL_TRANSFER_SOFTPLUS:
+            case OPL_TRANSFER_GAUSSIAN:
+                a.epi = EPI_MUL_AUX;
+                a.aux_in = ws->deriv[l - 1];
+                break;
+            case OPL_TRANSFER_TANH:
+                a.epi = EPI_MUL_DTANH;
+                a.aux_in = ws->act[l];
+                break;
+            default:
+                a.epi = EPI_STORE;
+        }
+        mark(ws, STAGE_DA * 100 + l);
+        int rc = launch_gemm_f64(GEMM_NT, a, 1, ws->stream, &ws->launches);
+        if (rc != OPL_OK) return rc;
+        if (ws->transfer[l - 1] == OPL_TRANSFER_SOFTMAX) {
+            mark(ws, STAGE_ROWS * 100 + l - 1);
+            const int group = row_group(din);
+            softmax_backward_rows_kernel<<<row_grid(rows, group), 256, 0, ws->stream>>>(ws->delta[l - 1], ws->act[l],
+                                                                                       rows, din, group);
+            OPL_LAUNCH_CHECK();
+            ++ws->launches;
+        }
+    }
+    // db = column sums of delta_0 (mlp.py:276)
+    {
+        const int cols = (int)ws->width[1];
+        int64_t nblk = std::max<int64_t>(1, std::min<int64_t>(ceil_div(rows, 64),
+                                                              (2 * (int64_t)sm_count()) / ceil_div(cols, 32) + 1));
+        if (nblk * cols > ws->partials_len) nblk = std::max<int64_t>(1, ws->partials_len / cols);
+        const int64_t rpb = ceil_div(rows, nblk);
+        nblk = ceil_div(rows, rpb);
+        dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)nblk);
+        mark(ws, STAGE_BIAS * 100);
+        colsum_partial_kernel<<<grid, dim3(32, 8), 0, ws->stream>>>(ws->delta[0], rows, cols, rpb, ws->partials);
+        OPL_LAUNCH_CHECK();
+        ++ws->launches;
+        int rc = launch_reduce_partials(ws->partials, (int)nblk, cols, cols, grad, ws->stream, &ws->launches);
+        if (rc != OPL_OK) return rc;
+    }
+    return OPL_OK;
+}
+
+int evaluate(opl_mlp *ws, const double *x_dev, double alpha, const double *dir_dev, bool want_grad,
+             double *grad_out_dev) {
+    if (!ws->x || ws->rows <= 0) return fail(OPL_E_STATE, "no training data resident: call opl_mlp_set_data_* first");
+    const int64_t n = ws->n;
+    int tgrid = (int)std::min<int64_t>(ceil_div(n, 256), 4 * (int64_t)sm_count());
+    mark(ws, STAGE_TRIAL * 100);
+    trial_point_kernel<<<tgrid, 256, 0, ws->stream>>>(n, x_dev, alpha, dir_dev, ws->w_trial, ws->flag);
+    OPL_LAUNCH_CHECK();
+    ++ws->launches;
+    int rc = forward(ws, ws->w_trial, ws->x, ws->rows, want_grad);
+    if (rc != OPL_OK) return rc;
+    rc = output_stage(ws, ws->y, ws->rows, false, want_grad, grad_out_dev + n);
+    if (rc != OPL_OK) return rc;
+    if (want_grad) rc = backward(ws, ws->w_trial, ws->x, ws->rows, grad_out_dev);
+    mark(ws, STAGE_END * 100);
+    return rc;
+}
+
+int read_scalars(opl_mlp *ws, const double *grad_dev, const double *dir_dev, bool have_grad, double *host_out) {
+    const int64_t n = ws->n;
+    if (have_grad) {
+        int grid = (int)std::min<int64_t>(ceil_div(n, 256), (int64_t)ws->probe_blocks);
+        probe_partial_kernel<<<grid, 256, 0, ws->stream>>>(n, grad_dev, dir_dev, ws->probe_partial);
+        probe_final_kernel<<<1, 256, 0, ws->stream>>>(grid, ws->probe_partial, grad_dev + n, ws->scal);
+        OPL_LAUNCH_CHECK();
+        ws->launches += 2;
+        OPL_CUDA(cudaMemcpyAsync(ws->pinned, ws->scal, 3 * sizeof(double), cudaMemcpyDeviceToHost, ws->stream));
+    } else {
+        OPL_CUDA(cudaMemcpyAsync(ws->pinned, grad_dev + n, sizeof(double), cudaMemcpyDeviceToHost, ws->stream));
+    }
+    OPL_CUDA(cudaMemcpyAsync(ws->pinned + 4, ws->flag, sizeof(int), cudaMemcpyDeviceToHost, ws->stream));
+    OPL_CUDA(cudaStreamSynchronize(ws->stream));
+    host_out[0] = ws->pinned[0];
+    host_out[1] = have_grad ? ws->pinned[1] : 0.0;
+    host_out[2] = have_grad ? ws->pinned[2] : 0.0;
+    if (*reinterpret_cast<int *>(ws->pinned + 4) != 0)
+        return fail(OPL_E_DOMAIN, "invalid value encountered in log (negative prediction in cross entropy)");
+    return OPL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int opl_mlp_create(opl_mlp **out, int32_t n_widths, const int64_t *widths, const int32_t *transfer_ids,
+                   const double *transfer_params, int32_t error_id, int64_t max_rows, int32_t precision,
+                   void *cuda_stream) {
+    if (!out || !widths || !transfer_ids || n_widths < 2) return fail(OPL_E_ARG, "opl_mlp_create: bad arguments");
+    if (error_id != OPL_ERROR_MSE && error_id != OPL_ERROR_CROSS_ENTROPY)
+        return fail(OPL_E_ARG, "opl_mlp_create: unknown error id %d", error_id);
+    if (precision != OPL_PRECISION_F64)
+        return fail(OPL_E_ARG, "opl_mlp_create: precision %d not available in this build", precision);
+    if (max_rows < 1) return fail(OPL_E_ARG, "opl_mlp_create: max_rows must be >= 1");
+    for (int i = 0; i < n_widths; ++i)
+        if (widths[i] < 1 || widths[i] > (1 << 24)) return fail(OPL_E_ARG, "opl_mlp_create: bad width");
+    for (int i = 0; i < n_widths - 1; ++i)
+        if (transfer_ids[i] < 0 || transfer_ids[i] > OPL_TRANSFER_SOFTMAX)
+            return fail(OPL_E_ARG, "opl_mlp_create: unknown transfer id %d", transfer_ids[i]);
+    if (max_rows > 0x7fffffff) return fail(OPL_E_ARG, "opl_mlp_create: max_rows too large");
+    if (opl_device_count() < 1) return fail(OPL_E_CUDA, "no CUDA device: opl_b200 has no CPU fallback");
+
+    opl_mlp *ws = new opl_mlp();
+    ws->layers = n_widths - 1;
+    ws->width.assign(widths, widths + n_widths);
+    ws->transfer.assign(transfer_ids, transfer_ids + ws->layers);
+    ws->tparam.resize(ws->layers, 1.0);
+    if (transfer_params)
+        for (int l = 0; l < ws->layers; ++l) ws->tparam[l] = transfer_params[l];
+    ws->error_id = error_id;
+    ws->precision = precision;
+    ws->max_rows = max_rows;
+    ws->stream = (cudaStream_t)cuda_stream;
+    ws->w_off.resize(ws->layers);
+    int64_t at = widths[1];
+    for (int l = 0; l < ws->layers; ++l) {
+        ws->w_off[l] = at;
+        at += widths[l] * widths[l + 1];
+    }
+    ws->n = at;
+
+    const int L = ws->layers;
+    ws->act.assign(L + 1, nullptr);
+    ws->deriv.assign(L, nullptr);
+    ws->delta.assign(L, nullptr);
+    int64_t partials = 0;
+#define OPL_TRY(expr)                 \
+    do {                              \
+        cudaError_t _e = (expr);      \
+        if (_e != cudaSuccess) {      \
+            free_all(ws);             \
+            delete ws;                \
+            return fail(OPL_E_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+        }                             \
+    } while (0)
+    for (int l = 0; l < L; ++l) {
+        const size_t bytes = sizeof(double) * (size_t)max_rows * (size_t)widths[l + 1];
+        OPL_TRY(cudaMalloc(&ws->act[l + 1], bytes));
+        const int t = ws->transfer[l];
+        if (l < L - 1 && (t == OPL_TRANSFER_SOFTPLUS || t == OPL_TRANSFER_GAUSSIAN)) {
+            OPL_TRY(cudaMalloc(&ws->deriv[l], bytes));
+            ws->delta[l] = ws->deriv[l];   // delta_l overwrites D_l element-wise in the NT epilogue
+        } else {
+            OPL_TRY(cudaMalloc(&ws->delta[l], bytes));
+        }
+        SplitPlan plan = plan_split_k((int)widths[l], (int)widths[l + 1], (int)max_rows);
+        partials = std::max<int64_t>(partials, (int64_t)(plan.splits + 1) * widths[l] * widths[l + 1]);
+    }
+    partials = std::max<int64_t>(partials, (int64_t)(4 * sm_count() + 8) * widths[1]);
+    ws->partials_len = partials;
+    OPL_TRY(cudaMalloc(&ws->partials, sizeof(double) * (size_t)partials));
+    OPL_TRY(cudaMalloc(&ws->out_act, sizeof(double) * (size_t)max_rows * (size_t)widths[L]));
+    OPL_TRY(cudaMalloc(&ws->w_trial, sizeof(double) * (size_t)(ws->n + 1)));
+    OPL_TRY(cudaMalloc(&ws->host_grad, sizeof(double) * (size_t)(ws->n + 1)));
+    ws->loss_blocks = 8 * sm_count();
+    OPL_TRY(cudaMalloc(&ws->loss_partial, sizeof(double) * (size_t)ws->loss_blocks));
+    ws->probe_blocks = 2 * sm_count();
+    OPL_TRY(cudaMalloc(&ws->probe_partial, sizeof(double) * 2 * (size_t)ws->probe_blocks));
+    OPL_TRY(cudaMalloc(&ws->scal, sizeof(double) * 4));
+    OPL_TRY(cudaMalloc(&ws->flag, sizeof(int)));
+    OPL_TRY(cudaMemset(ws->flag, 0, sizeof(int)));
+    OPL_TRY(cudaMallocHost(&ws->pinned, sizeof(double) * 8));
+#undef OPL_TRY
+    *out = ws;
+    return OPL_OK;
+}
+
+int opl_mlp_destroy(opl_mlp *ws) {
+    if (!ws) return OPL_OK;
+    cudaStreamSynchronize(ws->stream);
+    free_all(ws);
+    delete ws;
+    return OPL_OK;
+}
+
+int64_t opl_mlp_param_count(const opl_mlp *ws) { return ws ? ws->n : -1; }
+int64_t opl_mlp_launch_count(const opl_mlp *ws) { return ws ? ws->launches : -1; }
+
+int opl_mlp_profile(opl_mlp *ws, int32_t enable) {
+    if (!ws) return fail(OPL_E_ARG, "opl_mlp_profile: null");
+    ws->profiling = enable != 0;
+    ws->ev_used = 0;
+    return OPL_OK;
+}
+
+int opl_mlp_profile_read(opl_mlp *ws, int32_t capacity, int32_t *kinds, float *ms, int32_t *count) {
+    if (!ws || !kinds || !ms || !count) return fail(OPL_E_ARG, "opl_mlp_profile_read: null pointer");
+    OPL_CUDA(cudaStreamSynchronize(ws->stream));
+    int32_t out = 0;
+    for (size_t i = 0; i + 1 < ws->ev_used && out < capacity; ++i) {
+        if (ws->ev_kind[i] == STAGE_END * 100) continue;   // gap between evaluations
+        float t = 0.f;
+        OPL_CUDA(cudaEventElapsedTime(&t, ws->ev_pool[i], ws->ev_pool[i + 1]));
+        kinds[out] = ws->ev_kind[i];
+        ms[out] = t;
+        ++out;
+    }
+    *count = out;
+    ws->ev_used = 0;
+    return OPL_OK;
+}
+
+int opl_mlp_set_data_host(opl_mlp *ws, const double *x, const double *y, int64_t rows, int64_t norm_rows) {
+    if (!ws || !x || !y) return fail(OPL_E_ARG, "opl_mlp_set_data_host: null pointer");
+    if (rows < 1 || rows > ws->max_rows) return fail(OPL_E_ARG, "opl_mlp_set_data_host: rows=%lld outside [1,%lld]",
+                                                      (long long)rows, (long long)ws->max_rows);
+    const int64_t d0 = ws->width[0], dl = ws->width[ws->layers];
+    if (!ws->x_own) OPL_CUDA(cudaMalloc(&ws->x_own, sizeof(double) * (size_t)ws->max_rows * (size_t)d0));
+    if (!ws->y_own) OPL_CUDA(cudaMalloc(&ws->y_own, sizeof(double) * (size_t)ws->max_rows * (size_t)dl));
+    OPL_CUDA(cudaMemcpyAsync(ws->x_own, x, sizeof(double) * (size_t)rows * (size_t)d0, cudaMemcpyHostToDevice, ws->stream));
+    OPL_CUDA(cudaMemcpyAsync(ws->y_own, y, sizeof(double) * (size_t)rows * (size_t)dl, cudaMemcpyHostToDevice, ws->stream));
+    OPL_CUDA(cudaStreamSynchronize(ws->stream));
+    ws->x = ws->x_own;
+    ws->y = ws->y_own;
+    ws->rows = rows;
+    ws->norm_rows = norm_rows > 0 ? norm_rows : rows;
+    return OPL_OK;
+}
+
+int opl_mlp_set_data_device(opl_mlp *ws, const double *x_dev, const double *y_dev, int64_t rows, int64_t norm_rows) {
+    if (!ws || !x_dev || !y_dev) return fail(OPL_E_ARG, "opl_mlp_set_data_device: null pointer");
+    if (rows < 1 || rows > ws->max_rows) return fail(OPL_E_ARG, "opl_mlp_set_data_device: rows out of range");
+    ws->x = x_dev;   // borrowed: the caller keeps the buffers alive
+    ws->y = y_dev;
+    ws->rows = rows;
+    ws->norm_rows = norm_rows > 0 ? norm_rows : rows;
+    return OPL_OK;
+}
+
+int opl_mlp_eval_device(opl_mlp *ws, const double *x_dev, double alpha, const double *dir_dev, int32_t want_grad,
+                        double *grad_out_dev) {
+    if (!ws || !x_dev || !grad_out_dev) return fail(OPL_E_ARG, "opl_mlp_eval_device: null pointer");
+    return evaluate(ws, x_dev, alpha, dir_dev, want_grad != 0, grad_out_dev);
+}
+
+int opl_mlp_probe_scalars(opl_mlp *ws, const double *grad_dev, const double *dir_dev, int32_t have_grad,
+                          double *host_out) {
+    if (!ws || !grad_dev || !host_out) return fail(OPL_E_ARG, "opl_mlp_probe_scalars: null pointer");
+    return read_scalars(ws, grad_dev, dir_dev, have_grad != 0, host_out);
+}
+
+int opl_mlp_obj_host(opl_mlp *ws, const double *params, double *obj_out) {
+    if (!ws || !params || !obj_out) return fail(OPL_E_ARG, "opl_mlp_obj_host: null pointer");
+    // stage the parameters in host_grad (reused as the device-side x)
+    OPL_CUDA(cudaMemcpyAsync(ws->host_grad, params, sizeof(double) * (size_t)ws->n, cudaMemcpyHostToDevice, ws->stream));
+    // objective lands in w_trial[n]
+    int rc = evaluate(ws, ws->host_grad, 0.0, nullptr, false, ws->w_trial);
+    if (rc != OPL_OK) return rc;
+    double s[3];
+    rc = read_scalars(ws, ws->w_trial, nullptr, false, s);
+    *obj_out = s[0];
+    return rc;
+}
+
+int opl_mlp_obj_jac_host(opl_mlp *ws, const double *params, double *obj_out, double *grad_out) {
+    if (!ws || !params || !obj_out || !grad_out) return fail(OPL_E_ARG, "opl_mlp_obj_jac_host: null pointer");
+    const int64_t n = ws->n;
+    // x staged after the trial buffer is formed: use partial scratch-free path -- params go to
+    // w_trial directly through the trial kernel reading host_grad, gradient overwrites host_grad.
+    OPL_CUDA(cudaMemcpyAsync(ws->host_grad, params, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ws->stream));
+    int rc = evaluate(ws, ws->host_grad, 0.0, nullptr, true, ws->host_grad);
+    if (rc != OPL_OK) return rc;
+    OPL_CUDA(cudaMemcpyAsync(grad_out, ws->host_grad, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ws->stream));
+    double s[3];
+    rc = read_scalars(ws, ws->host_grad, nullptr, false, s);
+    *obj_out = s[0];
+    return rc;
+}
+
+int opl_mlp_activate_device(opl_mlp *ws, const double *params_dev, const double *x_dev, int64_t rows, double *out_dev) {
+    if (!ws || !params_dev || !x_dev || !out_dev) return fail(OPL_E_ARG, "opl_mlp_activate_device: null pointer");
+    if (rows < 1 || rows > ws->max_rows) return fail(OPL_E_ARG, "opl_mlp_activate_device: rows out of range");
+    int rc = forward(ws, params_dev, x_dev, rows, false);
+    if (rc != OPL_OK) return rc;
+    rc = output_stage(ws, nullptr, rows, true, false, nullptr);
+    if (rc != OPL_OK) return rc;
+    OPL_CUDA(cudaMemcpyAsync(out_dev, ws->out_act, sizeof(double) * (size_t)rows * (size_t)ws->width[ws->layers],
+                             cudaMemcpyDeviceToDevice, ws->stream));
+    return OPL_OK;
+}
+
+int opl_mlp_activate_host(opl_mlp *ws, const double *params, const double *x, int64_t rows, double *out) {
+    if (!ws || !params || !x || !out) return fail(OPL_E_ARG, "opl_mlp_activate_host: null pointer");
+    if (rows < 1 || rows > ws->max_rows) return fail(OPL_E_ARG, "opl_mlp_activate_host: rows=%lld outside [1,%lld]",
+                                                      (long long)rows, (long long)ws->max_rows);
+    const int64_t d0 = ws->width[0], dl = ws->width[ws->layers];
+    if (!ws->x_scratch) OPL_CUDA(cudaMalloc(&ws->x_scratch, sizeof(double) * (size_t)ws->max_rows * (size_t)d0));
+    OPL_CUDA(cudaMemcpyAsync(ws->w_trial, params, sizeof(double) * (size_t)ws->n, cudaMemcpyHostToDevice, ws->stream));
+    OPL_CUDA(cudaMemcpyAsync(ws->x_scratch, x, sizeof(double) * (size_t)rows * (size_t)d0, cudaMemcpyHostToDevice, ws->stream));
+    int rc = forward(ws, ws->w_trial, ws->x_scratch, rows, false);
+    if (rc != OPL_OK) return rc;
+    rc = output_stage(ws, nullptr, rows, true, false, nullptr);
+    if (rc != OPL_OK) return rc;
+    OPL_CUDA(cudaMemcpyAsync(out, ws->out_act, sizeof(double) * (size_t)rows * (size_t)dl, cudaMemcpyDeviceToHost, ws->stream));
+    OPL_CUDA(cudaStreamSynchronize(ws->stream));
+    return OPL_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------
+// Stand-alone host-buffer forms of Transfer.__call__ / derivative and ErrorFunc.__call__ /
+// derivative (transfer.py:33-130, error.py:31-116): the same row kernel the MLP uses.
+// ---------------------------------------------------------------------------------------
+namespace {
+
+struct Scratch {   // RAII device buffers for the one-shot host calls
+    std::vector<void *> ptrs;
+    ~Scratch() {
+        for (void *p : ptrs) cudaFree(p);
+    }
+    int alloc(void **out, size_t bytes) {
+        OPL_CUDA(cudaMalloc(out, bytes ? bytes : 8));
+        ptrs.push_back(*out);
+        return OPL_OK;
+    }
+};
+
+int rows_call(int tid, double tparam, int eid, const double *z_host, const double *y_host, const double *g_host,
+              int64_t rows, int64_t cols, double *a_out, double *d_out, double *loss_out) {
+    if (rows < 1 || cols < 1 || cols > (1 << 24)) return fail(OPL_E_ARG, "bad matrix shape %lld x %lld", (long long)rows, (long long)cols);
+    if (opl_device_count() < 1) return fail(OPL_E_CUDA, "no CUDA device: opl_b200 has no CPU fallback");
+    Scratch sc;
+    const size_t bytes = sizeof(double) * (size_t)rows * (size_t)cols;
+    double *z = nullptr, *y = nullptr, *g = nullptr, *a = nullptr, *d = nullptr, *lp = nullptr, *res = nullptr;
+    int *flag = nullptr;
+    int rc = sc.alloc((void **)&z, bytes);
+    if (rc == OPL_OK && y_host) rc = sc.alloc((void **)&y, bytes);
+    if (rc == OPL_OK && g_host) rc = sc.alloc((void **)&g, bytes);
+    if (rc == OPL_OK && a_out) rc = sc.alloc((void **)&a, bytes);
+    if (rc == OPL_OK && d_out) rc = sc.alloc((void **)&d, bytes);
+    if (rc == OPL_OK) rc = sc.alloc((void **)&flag, sizeof(int));
+    if (rc != OPL_OK) return rc;
+    OPL_CUDA(cudaMemset(flag, 0, sizeof(int)));
+    OPL_CUDA(cudaMemcpy(z, z_host, bytes, cudaMemcpyHostToDevice));
+    if (y) OPL_CUDA(cudaMemcpy(y, y_host, bytes, cudaMemcpyHostToDevice));
+    if (g) OPL_CUDA(cudaMemcpy(g, g_host, bytes, cudaMemcpyHostToDevice));
+    RowArgs r = {};
+    r.Z = z;
+    r.Y = y;
+    r.G = g;
+    r.A = a;
+    r.D = d;
+    r.rows = rows;
+    r.C = (int)cols;
+    r.tid = tid;
+    r.tparam = tparam;
+    r.eid = eid;
+    r.ce_div = -(double)rows;
+    r.mse_mul = 2.0 / ((double)rows * (double)cols);
+    r.flag = flag;
+    r.group = row_group(r.C);
+    const int grid = row_grid(rows, r.group);
+    if (loss_out) {
+        rc = sc.alloc((void **)&lp, sizeof(double) * (size_t)grid);
+        if (rc == OPL_OK) rc = sc.alloc((void **)&res, sizeof(double));
+        if (rc != OPL_OK) return rc;
+        r.loss_partial = lp;
+    }
+    output_rows_kernel<<<grid, 256>>>(r);
+    OPL_LAUNCH_CHECK();
+    if (loss_out) {
+        loss_final_kernel<<<1, 256>>>(lp, grid, eid, (double)rows, (double)cols, res);
+        OPL_LAUNCH_CHECK();
+        OPL_CUDA(cudaMemcpy(loss_out, res, sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    if (a_out) OPL_CUDA(cudaMemcpy(a_out, a, bytes, cudaMemcpyDeviceToHost));
+    if (d_out) OPL_CUDA(cudaMemcpy(d_out, d, bytes, cudaMemcpyDeviceToHost));
+    int bad = 0;
+    OPL_CUDA(cudaMemcpy(&bad, flag, sizeof(int), cudaMemcpyDeviceToHost));
+    if (bad) return fail(OPL_E_DOMAIN, "invalid value encountered in log (negative prediction in cross entropy)");
+    return OPL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int opl_transfer_apply_host(int32_t transfer_id, double param, const double *x, int64_t rows, int64_t cols,
+                            double *out) {
+    if (!x || !out || transfer_id < 0 || transfer_id > OPL_TRANSFER_SOFTMAX)
+        return fail(OPL_E_ARG, "opl_transfer_apply_host: bad arguments");
+    return rows_call(transfer_id, param, OPL_ERROR_MSE, x, nullptr, nullptr, rows, cols, out, nullptr, nullptr);
+}
+
+int opl_transfer_backprop_host(int32_t transfer_id, double param, const double *x, const double *upstream,
+                               int64_t rows, int64_t cols, double *out) {
+    if (!x || !upstream || !out || transfer_id < 0 || transfer_id > OPL_TRANSFER_SOFTMAX)
+        return fail(OPL_E_ARG, "opl_transfer_backprop_host: bad arguments");
+    return rows_call(transfer_id, param, OPL_ERROR_MSE, x, nullptr, upstream, rows, cols, nullptr, out, nullptr);
+}
+
+int opl_error_host(int32_t error_id, const double *a, const double *b, int64_t rows, int64_t cols,
+                   double *err_out, double *deriv_out) {
+    if (!a || !b || !err_out || (error_id != OPL_ERROR_MSE && error_id != OPL_ERROR_CROSS_ENTROPY))
+        return fail(OPL_E_ARG, "opl_error_host: bad arguments");
+    return rows_call(OPL_TRANSFER_LINEAR, 0.0, error_id, a, b, nullptr, rows, cols, nullptr, deriv_out, err_out);
+}
+
+int opl_softmax_jacobian_host(const double *y, int64_t rows, int64_t cols, double *jac_out) {
+    if (!y || !jac_out || rows < 1 || cols < 1) return fail(OPL_E_ARG, "opl_softmax_jacobian_host: bad arguments");
+    if (opl_device_count() < 1) return fail(OPL_E_CUDA, "no CUDA device: opl_b200 has no CPU fallback");
+    Scratch sc;
+    double *yd = nullptr, *jd = nullptr;
+    const size_t yb = sizeof(double) * (size_t)rows * (size_t)cols, jb = yb * (size_t)cols;
+    int rc = sc.alloc((void **)&yd, yb);
+    if (rc == OPL_OK) rc = sc.alloc((void **)&jd, jb);
+    if (rc != OPL_OK) return rc;
+    OPL_CUDA(cudaMemcpy(yd, y, yb, cudaMemcpyHostToDevice));
+    const int64_t total = rows * cols * cols;
+    softmax_jacobian_kernel<<<(unsigned)std::min<int64_t>(ceil_div(total, 256), 8 * (int64_t)sm_count()), 256>>>(
+        yd, rows, (int)cols, jd);
+    OPL_LAUNCH_CHECK();
+    OPL_CUDA(cudaMemcpy(jac_out, jd, jb, cudaMemcpyDeviceToHost));
+    return OPL_OK;
+}
+
+}  // extern "C"

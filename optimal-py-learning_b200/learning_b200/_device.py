@@ -1,0 +1,83 @@
+"""Device n-vectors for the optimizer stack.
+
+Vectors are ``torch.float64`` CUDA tensors (torch is the allocator / stream owner); the
+arithmetic is done by the kernels behind ``opl_vec_*`` so that iterates round exactly like
+the reference's NumPy expressions (``x + a*d`` as two roundings, deterministic dots).
+"""
+import ctypes
+
+import numpy
+import torch
+
+from . import _native as nat
+
+
+def is_device_vector(value):
+    return isinstance(value, torch.Tensor)
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(tensor):
+    return ctypes.c_void_p(tensor.data_ptr()) if tensor is not None else None
+
+
+def to_device(array):
+    """Host array-like -> contiguous float64 CUDA tensor (H2D copy)."""
+    nat.require_device()
+    if isinstance(array, torch.Tensor):
+        return array.to(device="cuda", dtype=torch.float64).contiguous()
+    host = numpy.ascontiguousarray(array, dtype=numpy.float64)
+    return torch.from_numpy(host).cuda()
+
+
+def to_host(tensor):
+    return tensor.detach().cpu().numpy()
+
+
+def empty(n):
+    nat.require_device()
+    return torch.empty(int(n), dtype=torch.float64, device="cuda")
+
+
+def _check_vec(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if t.dtype != torch.float64 or not t.is_cuda or not t.is_contiguous():
+            raise TypeError("expected contiguous float64 CUDA tensors")
+
+
+def axpy(x, a, d, b=0.0, p=None, out=None):
+    """x + fl(a*d) [+ fl(b*p)]  (optimizer.py:97,136-141,253; linesearch.py:394)."""
+    _check_vec(x, d, p)
+    if out is None:
+        out = torch.empty_like(x)
+    nat.check(nat.lib.opl_vec_axpy_device(x.numel(), ptr(x), float(a), ptr(d), float(b), ptr(p), ptr(out),
+                                          stream_ptr()))
+    return out
+
+
+def scale(a, x, out=None):
+    """fl(a*x)  (prev_step = step_size * step_dir, optimizer.py:251)."""
+    _check_vec(x)
+    if out is None:
+        out = torch.empty_like(x)
+    nat.check(nat.lib.opl_vec_scale_device(x.numel(), float(a), ptr(x), ptr(out), stream_ptr()))
+    return out
+
+
+def dot(x, y):
+    """x . y as a Python float (deterministic two-stage reduction; one host sync)."""
+    _check_vec(x, y)
+    if x.numel() != y.numel():
+        raise ValueError("dot: length mismatch %d vs %d" % (x.numel(), y.numel()))
+    out = ctypes.c_double(0.0)
+    nat.check(nat.lib.opl_vec_dot_device(x.numel(), ptr(x), ptr(y), ctypes.byref(out), stream_ptr()))
+    return out.value
+
+
+def norm(x):
+    return float(numpy.sqrt(dot(x, x)))

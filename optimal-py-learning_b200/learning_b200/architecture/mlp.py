@@ -1,0 +1,332 @@
+"""MultiLayer Perceptron whose objective / gradient evaluation runs on a B200.
+
+Drop-in for learning/architecture/mlp.py:41-327: same constructor, same ``activate`` /
+``train`` / ``train_step`` / ``reset`` / ``serialize`` behaviour, same flat parameter layout
+``[bias(d1); W0.ravel(); W1.ravel(); ...]``, same weight-initialisation draw order.  The hot
+functions -- ``activate``, ``_get_obj``, ``_get_obj_jac`` and the line-search probes that
+call them -- are a fixed schedule of hand-written CUDA kernels behind the C-ABI
+(include/opl_b200.h, csrc/mlp.cu); nothing here does NumPy arithmetic.
+
+Host state: ``_bias_vec`` / ``_weight_matrices`` are NumPy arrays (authoritative between
+training steps, user-editable as in the reference).  During ``train_step`` the flat
+parameter vector lives on the device and only the objective, the slope and the gradient norm
+come back per evaluation.
+"""
+import ctypes
+import functools
+import operator
+
+import numpy
+import torch
+
+from .. import _device as dev
+from .. import _native as nat
+from .. import error as error_mod
+from .. import transfer as transfer_mod
+from ..base import Model
+from ..error import MeanSquaredError
+from ..optimize import Problem, make_optimizer
+from ..transfer import LinearTransfer, ReluTransfer, Transfer
+
+INITIAL_WEIGHTS_RANGE = 0.25
+
+
+def _flatten(bias_vec, weight_matrices):
+    """Flat vector: bias, then each weight matrix row-major (mlp.py:313-315)."""
+    return numpy.hstack([numpy.asarray(bias_vec, dtype=float)]
+                        + [numpy.asarray(m, dtype=float).ravel() for m in weight_matrices])
+
+
+def _unflatten_weights(flat_weights, shape):
+    """Views of the flat vector as (bias, [W_l]) (mlp.py:318-327)."""
+    bias_vec = flat_weights[:shape[1]]
+    matrices, at = [], shape[1]
+    for rows, cols in zip(shape[:-1], shape[1:]):
+        matrices.append(flat_weights[at:at + rows * cols].reshape((rows, cols)))
+        at += rows * cols
+    return bias_vec, matrices
+
+
+class _Workspace(object):
+    """One opl_mlp handle plus the identity of the data currently resident in it."""
+
+    def __init__(self, shape, transfers, error_id, max_rows):
+        widths = (ctypes.c_int64 * len(shape))(*[int(w) for w in shape])
+        tids = (ctypes.c_int32 * len(transfers))(*[t for t, _ in transfers])
+        tparams = (ctypes.c_double * len(transfers))(*[p for _, p in transfers])
+        out = ctypes.c_void_p()
+        nat.check(nat.lib.opl_mlp_create(ctypes.byref(out), len(shape), widths, tids, tparams, error_id,
+                                         int(max_rows), 0, dev.stream_ptr()))
+        self.pointer = out
+        self.max_rows = int(max_rows)
+        self.resident = None      # fingerprint of the (X, Y) resident on the device
+        self.keepalive = None     # device tensors borrowed by the workspace
+
+    def __del__(self):
+        try:
+            if self.pointer:
+                nat.lib.opl_mlp_destroy(self.pointer)
+                self.pointer = None
+        except Exception:
+            pass
+
+
+def _fingerprint(x, y):
+    """Cheap identity of a host dataset: object ids, buffers, shapes and a few sampled values."""
+    def sample(a):
+        flat = a.reshape(-1)
+        idx = numpy.linspace(0, flat.shape[0] - 1, num=min(16, flat.shape[0])).astype(numpy.int64)
+        return tuple(flat[idx].tolist())
+    return (id(x), id(y), x.__array_interface__['data'][0], y.__array_interface__['data'][0],
+            x.shape, y.shape, sample(x), sample(y))
+
+
+class MLP(Model):
+    """MultiLayer Perceptron.
+
+    Args:
+        shape: Number of inputs, followed by number of outputs of each layer.
+        transfers: Optional list of transfer layers, or a single Transfer for the output layer.
+            Defaults to softplus ("ReLU") hidden layers followed by a linear output.
+        optimizer: Optimizer used to optimize the weight matrices
+            (default: BFGS up to 500 weights, else L-BFGS; bias excluded from the count).
+        error_func: ErrorFunc (default MeanSquaredError).
+        jacobian_norm_break: Training ends when the gradient norm falls below this value.
+    """
+
+    def __init__(self, shape, transfers=None, optimizer=None, error_func=None, jacobian_norm_break=1e-10):
+        super(MLP, self).__init__()
+        hidden = len(shape) - 2
+        if transfers is None:
+            transfers = [ReluTransfer() for _ in range(hidden)] + [LinearTransfer()]
+        elif isinstance(transfers, Transfer):
+            transfers = [ReluTransfer() for _ in range(hidden)] + [transfers]
+        if len(transfers) != len(shape) - 1:
+            raise ValueError('Must have exactly 1 transfer between each pair of layers, and after the output')
+        self._shape = shape
+
+        # draw order matters for seeded reproducibility (mlp.py:79-82): bias first, then matrices
+        self._bias_vec = self._random_weight_matrix(shape[1])
+        self._weight_matrices = []
+        self._setup_weight_matrices()
+        self._transfers = transfers
+        self._lowered_transfers = [transfer_mod.lower(t) for t in transfers]
+
+        if optimizer is None:
+            optimizer = make_optimizer(sum(functools.reduce(operator.mul, m.shape)
+                                           for m in self._weight_matrices))
+        self._optimizer = optimizer
+        if error_func is None:
+            error_func = MeanSquaredError()
+        self._error_func = error_func
+        self._lowered_error = error_mod.lower(error_func)
+        self._jacobian_norm_break = jacobian_norm_break
+
+        self._workspace = None
+        self._last_grad_norm = None
+        self.obj_jac_evaluations = 0     # probe counter (bench / diagnostics)
+        self.reset()
+
+    # ------------------------------------------------------------------ weights
+    def _setup_weight_matrices(self):
+        self._weight_matrices = [self._random_weight_matrix((rows, cols))
+                                 for rows, cols in zip(self._shape[:-1], self._shape[1:])]
+
+    def _random_weight_matrix(self, shape):
+        return (2 * numpy.random.random(shape) - 1) * INITIAL_WEIGHTS_RANGE
+
+    def reset(self):
+        """New random weights (matrices first, then bias: mlp.py:125-130) and a reset optimizer."""
+        super(MLP, self).reset()
+        self._setup_weight_matrices()
+        self._bias_vec = self._random_weight_matrix(self._shape[1])
+        self._optimizer.reset()
+
+    # ------------------------------------------------------------------ device workspace
+    def _workspace_for(self, rows):
+        ws = self._workspace
+        if ws is None or ws.max_rows < rows:
+            ws = _Workspace(self._shape, self._lowered_transfers, self._lowered_error, rows)
+            self._workspace = ws
+        return ws
+
+    def _shard(self, rows):
+        """(first row, row count) of this rank's shard of a batch of ``rows`` patterns."""
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            world, rank = torch.distributed.get_world_size(), torch.distributed.get_rank()
+            if world > 1 and rows >= world:
+                per = -(-rows // world)
+                first = min(rows, rank * per)
+                return first, min(rows, first + per) - first, True
+        return 0, rows, False
+
+    def _make_resident(self, input_matrix, target_matrix):
+        """Upload (this rank's shard of) the dataset once; later calls with the same arrays are free."""
+        if dev.is_device_vector(input_matrix):
+            x, y = input_matrix, target_matrix
+            if x.dim() != 2 or y.dim() != 2 or x.shape[0] != y.shape[0]:
+                raise ValueError('input_matrix and target_matrix must be matrices with equal row counts')
+            key = ('device', x.data_ptr(), y.data_ptr(), tuple(x.shape), tuple(y.shape))
+            ws = self._workspace_for(x.shape[0])
+            if ws.resident != key:
+                self._check_widths(x.shape[-1], y.shape[-1])
+                x = x.to(torch.float64).contiguous()
+                y = y.to(torch.float64).contiguous()
+                nat.check(nat.lib.opl_mlp_set_data_device(ws.pointer, dev.ptr(x), dev.ptr(y), x.shape[0],
+                                                          self._global_rows(x.shape[0])))
+                ws.keepalive = (x, y)
+                ws.resident = key
+                ws.sharded = self._world_size() > 1
+            return ws
+        x = numpy.asarray(input_matrix, dtype=numpy.float64)
+        y = numpy.asarray(target_matrix, dtype=numpy.float64)
+        if x.ndim != 2 or y.ndim != 2:
+            raise ValueError('the gradient path needs matrices (patterns in rows), got shapes %s and %s'
+                             % (x.shape, y.shape))
+        if x.shape[0] != y.shape[0]:
+            raise ValueError('input_matrix has %d rows, target_matrix %d' % (x.shape[0], y.shape[0]))
+        self._check_widths(x.shape[-1], y.shape[-1])
+        first, count, sharded = self._shard(x.shape[0])
+        ws = self._workspace_for(count)
+        key = _fingerprint(x, y) + (first, count)
+        if ws.resident != key:
+            xs = numpy.ascontiguousarray(x[first:first + count])
+            ys = numpy.ascontiguousarray(y[first:first + count])
+            nat.check(nat.lib.opl_mlp_set_data_host(ws.pointer, xs.ctypes.data_as(ctypes.c_void_p),
+                                                    ys.ctypes.data_as(ctypes.c_void_p), count, x.shape[0]))
+            ws.resident = key
+            ws.keepalive = None
+            ws.sharded = sharded
+        return ws
+
+    def _world_size(self):
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            return torch.distributed.get_world_size()
+        return 1
+
+    def _global_rows(self, local_rows):
+        """Device-resident shards: every rank passes its own rows; N of the 1/N scale is their sum."""
+        if self._world_size() == 1:
+            return local_rows
+        total = torch.tensor([local_rows], dtype=torch.int64, device='cuda')
+        torch.distributed.all_reduce(total)
+        return int(total.item())
+
+    def _check_widths(self, attrs, outs):
+        if attrs != self._shape[0]:
+            raise ValueError('input_tensor attributes == %s, expected %s' % (attrs, self._shape[0]))
+        if outs != self._shape[-1]:
+            raise ValueError('target attributes == %s, expected %s' % (outs, self._shape[-1]))
+
+    # ------------------------------------------------------------------ forward
+    def activate(self, input_tensor):
+        """Model outputs for one pattern (1-D) or a matrix of patterns (mlp.py:134-163)."""
+        if not isinstance(input_tensor, numpy.ndarray):
+            input_tensor = numpy.array(input_tensor)
+        if input_tensor.shape[-1] != self._shape[0]:
+            raise ValueError('input_tensor attributes == %s, expected %s' % (input_tensor.shape[-1], self._shape[0]))
+        x = numpy.ascontiguousarray(input_tensor, dtype=numpy.float64)
+        vector = x.ndim == 1
+        x2 = x.reshape(1, -1) if vector else x
+        if x2.ndim != 2:
+            raise ValueError('activate expects a vector or a matrix')
+        ws = self._workspace_for(x2.shape[0])
+        params = _flatten(self._bias_vec, self._weight_matrices)
+        out = numpy.empty((x2.shape[0], self._shape[-1]))
+        nat.check(nat.lib.opl_mlp_activate_host(ws.pointer, params.ctypes.data_as(ctypes.c_void_p),
+                                                x2.ctypes.data_as(ctypes.c_void_p), x2.shape[0],
+                                                out.ctypes.data_as(ctypes.c_void_p)))
+        return out[0] if vector else out
+
+    # ------------------------------------------------------------------ training
+    def _pre_train(self, input_matrix, target_matrix):
+        """Model.train hook (base.py:166): the dataset becomes device-resident once per train call."""
+        self._make_resident(input_matrix, target_matrix)
+
+    def train_step(self, input_matrix, target_matrix):
+        """One optimizer step on the full batch (mlp.py:165-182); returns the objective at x_k."""
+        ws = self._make_resident(input_matrix, target_matrix)
+        problem = Problem(obj_func=lambda xk: self._get_obj(xk, input_matrix, target_matrix),
+                          obj_jac_func=lambda xk: self._get_obj_jac(xk, input_matrix, target_matrix))
+        problem.ray_obj_jac = lambda xk, alpha, direction: self._probe(ws, xk, alpha, direction, True)[:2]
+        problem.ray_obj = lambda xk, alpha, direction: self._probe(ws, xk, alpha, direction, False)[0]
+
+        flat = dev.to_device(_flatten(self._bias_vec, self._weight_matrices))
+        error, flat_next = self._optimizer.next(problem, flat)
+        self._bias_vec, self._weight_matrices = _unflatten_weights(dev.to_host(flat_next), self._shape)
+
+        jacobian = self._optimizer.jacobian
+        if jacobian is None:
+            self.converged = False
+        else:
+            norm = dev.norm(jacobian) if dev.is_device_vector(jacobian) else float(numpy.linalg.norm(jacobian))
+            self.converged = norm < self._jacobian_norm_break
+        return error
+
+    def _post_train(self, input_matrix, target_matrix):
+        """Reset optimizer: the problem may change on the next train call (mlp.py:184-190)."""
+        self._optimizer.reset()
+
+    # ------------------------------------------------------------------ objective / gradient
+    def _probe(self, ws, x_dev, alpha, direction, want_grad):
+        """Evaluate at x + alpha*direction on the device.  Returns (obj, slope, grad tensor | None)."""
+        n = x_dev.numel()
+        out = torch.empty(n + 1, dtype=torch.float64, device=x_dev.device)
+        nat.check(nat.lib.opl_mlp_eval_device(ws.pointer, dev.ptr(x_dev), float(alpha), dev.ptr(direction),
+                                              1 if want_grad else 0, dev.ptr(out)))
+        if getattr(ws, 'sharded', False):
+            # batch-sharded ranks hold partial sums of [gradient ; objective]: one NCCL all-reduce
+            torch.distributed.all_reduce(out if want_grad else out[n:])
+        scalars = (ctypes.c_double * 3)()
+        nat.check(nat.lib.opl_mlp_probe_scalars(ws.pointer, dev.ptr(out), dev.ptr(direction),
+                                                1 if want_grad else 0, scalars))
+        self.obj_jac_evaluations += 1
+        self._last_grad_norm = float(numpy.sqrt(scalars[2])) if want_grad else None
+        return scalars[0], scalars[1], (out[:n] if want_grad else None)
+
+    def _get_obj(self, parameter_vec, input_matrix, target_matrix):
+        """Objective at ``parameter_vec`` (mlp.py:195-199).  NumPy in -> host-buffer C-ABI call;
+        device tensor in -> device call."""
+        ws = self._make_resident(input_matrix, target_matrix)
+        if dev.is_device_vector(parameter_vec):
+            return self._probe(ws, parameter_vec, 0.0, None, False)[0]
+        params = numpy.ascontiguousarray(parameter_vec, dtype=numpy.float64)
+        self._adopt(params)
+        if getattr(ws, 'sharded', False):
+            return self._probe(ws, dev.to_device(params), 0.0, None, False)[0]
+        obj = ctypes.c_double(0.0)
+        nat.check(nat.lib.opl_mlp_obj_host(ws.pointer, params.ctypes.data_as(ctypes.c_void_p), ctypes.byref(obj)))
+        return obj.value
+
+    def _get_obj_jac(self, parameter_vec, input_matrix, target_matrix):
+        """(objective, flat gradient) at ``parameter_vec`` (mlp.py:202-208)."""
+        ws = self._make_resident(input_matrix, target_matrix)
+        if dev.is_device_vector(parameter_vec):
+            obj, _, grad = self._probe(ws, parameter_vec, 0.0, None, True)
+            return obj, grad
+        params = numpy.ascontiguousarray(parameter_vec, dtype=numpy.float64)
+        if params.shape != (self._param_count(),):
+            raise ValueError('parameter_vec has shape %s, expected (%d,)' % (params.shape, self._param_count()))
+        self._adopt(params)
+        if getattr(ws, 'sharded', False):
+            obj, _, grad = self._probe(ws, dev.to_device(params), 0.0, None, True)
+            return obj, dev.to_host(grad)
+        obj = ctypes.c_double(0.0)
+        grad = numpy.empty_like(params)
+        nat.check(nat.lib.opl_mlp_obj_jac_host(ws.pointer, params.ctypes.data_as(ctypes.c_void_p),
+                                               ctypes.byref(obj), grad.ctypes.data_as(ctypes.c_void_p)))
+        self.obj_jac_evaluations += 1
+        return obj.value, grad
+
+    def _adopt(self, params):
+        """The reference leaves the model weights at the last evaluated point (mlp.py:197,204)."""
+        self._bias_vec, self._weight_matrices = _unflatten_weights(params, self._shape)
+
+    def _param_count(self):
+        return self._shape[1] + sum(a * b for a, b in zip(self._shape[:-1], self._shape[1:]))
+
+    # ------------------------------------------------------------------ pickling (base.py:350-373)
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state['_workspace'] = None       # device buffers are rebuilt on demand
+        return state

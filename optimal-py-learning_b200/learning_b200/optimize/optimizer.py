@@ -1,0 +1,390 @@
+"""Optimizers (reference: optimize/optimizer.py:33-508) driving device-resident n-vectors.
+
+Plugin API unchanged: ``Optimizer.next(problem, parameters) -> (objective, next_parameters)``,
+``reset()``, attributes ``jacobian`` / ``hessian``.  ``parameters`` may be
+
+  * a float64 CUDA ``torch.Tensor`` -- the native mode used by MLP.train_step: all vectors stay
+    on the device, the problem's callables take and return device vectors;
+  * a NumPy array -- a user-supplied Problem whose callables work on NumPy arrays: vectors are
+    uploaded once per call, the optimizer state (H, histories) still lives on the device and
+    NumPy comes back.
+
+All n-vector and n x n arithmetic runs in the CUDA kernels behind include/opl_b200.h; there
+is no NumPy arithmetic here.
+"""
+import ctypes
+
+import numpy
+import torch
+
+from .. import _device as dev
+from .. import _native as nat
+from .initialstep import FOChangeInitialStep
+from .linesearch import WolfeLineSearch
+
+
+def make_optimizer(num_parameters):
+    """BFGS up to 500 parameters, L-BFGS beyond (optimizer.py:33-43)."""
+    if num_parameters > 500:
+        return LBFGS()
+    return BFGS()
+
+
+def _default_step_size_getter():
+    # c_1 = 1e-4, c_2 = 0.9: Numerical Optimization 2nd ed. p. 161 (optimizer.py:204-210)
+    return WolfeLineSearch(c_1=1e-4, c_2=0.9, initial_step_getter=FOChangeInitialStep())
+
+
+class _HostProblem(object):
+    """Adapts a Problem over NumPy arrays to device vectors (one D2H + one H2D per call)."""
+    ray_obj_jac = None
+    ray_obj = None
+
+    def __init__(self, problem):
+        self._problem = problem
+
+    def get_obj(self, x):
+        return self._problem.get_obj(dev.to_host(x))
+
+    def get_obj_jac(self, x):
+        value, grad = self._problem.get_obj_jac(dev.to_host(x))
+        return value, dev.to_device(grad)
+
+
+class Optimizer(object):
+    """Optimizer for optimizing model parameters (optimizer.py:49-63)."""
+
+    def __init__(self):
+        self.jacobian = None   # last computed gradient (same kind as the parameters passed to next)
+        self.hessian = None
+
+    def reset(self):
+        self.jacobian = None
+        self.hessian = None
+
+    def next(self, problem, parameters):
+        """Return (objective at ``parameters``, next parameters)."""
+        if dev.is_device_vector(parameters):
+            return self._next(problem, parameters)
+        value, following = self._next(_HostProblem(problem), dev.to_device(parameters))
+        if self.jacobian is not None and dev.is_device_vector(self.jacobian):
+            self.jacobian = dev.to_host(self.jacobian)
+        return value, dev.to_host(following)
+
+    def _next(self, problem, x):
+        raise NotImplementedError()
+
+    # device handles never travel through pickle / deepcopy (base.py:350-373)
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        for key, value in list(state.items()):
+            if isinstance(value, torch.Tensor):
+                state[key] = dev.to_host(value)
+        return state
+
+
+class SteepestDescent(Optimizer):
+    """x - alpha * grad, alpha from the step-size getter (optimizer.py:73-97)."""
+
+    def __init__(self, step_size_getter=None):
+        super(SteepestDescent, self).__init__()
+        if step_size_getter is None:
+            step_size_getter = WolfeLineSearch(initial_step_getter=FOChangeInitialStep())
+        self._step_size_getter = step_size_getter
+
+    def reset(self):
+        super(SteepestDescent, self).reset()
+        self._step_size_getter.reset()
+
+    def _next(self, problem, x):
+        value, grad = problem.get_obj_jac(x)
+        self.jacobian = grad
+        downhill = dev.scale(-1.0, grad)
+        step_size = self._step_size_getter(x, value, grad, downhill, problem)
+        return value, dev.axpy(x, -step_size, grad)      # parameters - step_size * jacobian
+
+
+class SteepestDescentMomentum(Optimizer):
+    """Steepest descent plus ``momentum_rate`` times the previous step, added AFTER the line
+    search (optimizer.py:100-145)."""
+
+    def __init__(self, step_size_getter=None, momentum_rate=0.2):
+        super(SteepestDescentMomentum, self).__init__()
+        if step_size_getter is None:
+            step_size_getter = WolfeLineSearch(initial_step_getter=FOChangeInitialStep())
+        self._step_size_getter = step_size_getter
+        self._momentum_rate = momentum_rate
+        self._prev_step = None
+
+    def reset(self):
+        super(SteepestDescentMomentum, self).reset()
+        self._step_size_getter.reset()
+        self._prev_step = None
+
+    def _next(self, problem, x):
+        value, grad = problem.get_obj_jac(x)
+        self.jacobian = grad
+        downhill = dev.scale(-1.0, grad)
+        step_size = self._step_size_getter(x, value, grad, downhill, problem)
+        step = dev.scale(step_size, downhill)
+        if self._prev_step is None:
+            following = dev.axpy(x, 1.0, step)
+        else:
+            following = dev.axpy(x, 1.0, step, self._momentum_rate, self._prev_step)
+        self._prev_step = step
+        return value, following
+
+
+# ----------------------------------------------------------------------------------------
+# BFGS
+# ----------------------------------------------------------------------------------------
+def initial_hessian_identity(param_diff, jacobian, previous_jacobian):
+    """Identity seed (optimizer.py:148-151).  As a BFGS argument it selects the seed kernel
+    mode; the matrix itself is never formed on the training path."""
+    return numpy.identity(jacobian.shape[0])
+
+
+def initial_hessian_scaled_identity(param_diff, jacobian, previous_jacobian):
+    """gamma * I with gamma = (s.y)/(y.y) (optimizer.py:154-167)."""
+    s = dev.to_device(param_diff)
+    y = dev.axpy(dev.to_device(jacobian), -1.0, dev.to_device(previous_jacobian))
+    return numpy.diag(numpy.repeat(initial_hessian_gamma_scalar(s, y), jacobian.shape[0]))
+
+
+_SEED_MODES = {initial_hessian_identity: 0, initial_hessian_scaled_identity: 1}
+
+
+class _NativeHandle(object):
+    """Owns one C-ABI object; destroyed with the Python object, never pickled."""
+
+    def __init__(self, pointer, destroy):
+        self.pointer = pointer
+        self._destroy = destroy
+
+    def __del__(self):
+        try:
+            if self.pointer:
+                self._destroy(self.pointer)
+                self.pointer = None
+        except Exception:
+            pass
+
+
+class BFGS(Optimizer):
+    """Quasi-Newton BFGS (optimizer.py:170-285) on a device-resident inverse Hessian.
+
+    The reference rebuilds H with two dense n x n products per iteration (4 n^3 flop); here the
+    identical rank-2 update is applied in place and lazily by one fused HBM-bound pass per
+    iteration (csrc/bfgs.cu).  ``shard_rows=True`` splits the rows of H over the ranks of an
+    initialised torch.distributed process group (one GPU per rank).
+    """
+
+    def __init__(self, step_size_getter=None, initial_hessian_func=initial_hessian_identity,
+                 iterations_per_reset=100, shard_rows=False):
+        super(BFGS, self).__init__()
+        if step_size_getter is None:
+            step_size_getter = _default_step_size_getter()
+        self._step_size_getter = step_size_getter
+        if initial_hessian_func not in _SEED_MODES:
+            raise TypeError('initial_hessian_func must be initial_hessian_identity or '
+                            'initial_hessian_scaled_identity on the CUDA path (no CPU fallback)')
+        self._initial_hessian_func = initial_hessian_func
+        self._iterations_per_reset = iterations_per_reset
+        self._shard_rows = shard_rows
+        self._iteration = 0
+        self._prev_step = None
+        self._prev_jacobian = None
+        self._native = None
+
+    def reset(self):
+        super(BFGS, self).reset()
+        self._step_size_getter.reset()
+        self._iteration = 0
+        self._prev_step = None
+        self._prev_jacobian = None
+        if self._native is not None:
+            nat.check(nat.lib.opl_bfgs_reset(self._native.pointer))
+
+    def __getstate__(self):
+        state = super(BFGS, self).__getstate__()
+        state['_native'] = None          # H is rebuilt from the next two gradients after a restore
+        state['_prev_step'] = None
+        state['_prev_jacobian'] = None
+        return state
+
+    # ---- native state -------------------------------------------------------------------
+    def _world(self):
+        if self._shard_rows and torch.distributed.is_available() and torch.distributed.is_initialized():
+            return torch.distributed.get_rank(), torch.distributed.get_world_size()
+        return 0, 1
+
+    def _row_range(self, n):
+        rank, world = self._world()
+        per = -(-n // world)
+        return min(n, rank * per), min(n, (rank + 1) * per), per
+
+    def _state(self, n):
+        if self._native is None or self._native_n != n:
+            begin, end, _ = self._row_range(n)
+            out = ctypes.c_void_p()
+            nat.check(nat.lib.opl_bfgs_create(ctypes.byref(out), n, begin, end, dev.stream_ptr()))
+            self._native = _NativeHandle(out, nat.lib.opl_bfgs_destroy)
+            self._native_n = n
+        return self._native.pointer
+
+    def _direction(self, grad):
+        """-(H.dot(jac)) with H from _get_approx_inv_hessian (optimizer.py:242-285)."""
+        n = grad.numel()
+        handle = self._state(n)
+        seed = _SEED_MODES[self._initial_hessian_func]
+        direction = torch.empty_like(grad)
+        rank, world = self._world()
+        if world == 1:
+            nat.check(nat.lib.opl_bfgs_direction_device(handle, dev.ptr(grad), dev.ptr(self._prev_step),
+                                                        dev.ptr(self._prev_jacobian), seed, dev.ptr(direction)))
+            return direction
+        # row-sharded H: local pass, exchange the three n-vectors, redundant finish on every rank
+        begin, end, per = self._row_range(n)
+        u = torch.zeros(per * world, dtype=torch.float64, device=grad.device)
+        w = torch.zeros_like(u)
+        v = torch.zeros(n, dtype=torch.float64, device=grad.device)
+        nat.check(nat.lib.opl_bfgs_pass_device(handle, dev.ptr(grad), dev.ptr(self._prev_step),
+                                               dev.ptr(self._prev_jacobian), seed, dev.ptr(u), dev.ptr(v),
+                                               dev.ptr(w)))
+        if self._prev_step is not None and nat.lib.opl_bfgs_state(handle) == 2:
+            torch.distributed.all_gather_into_tensor(u, u[begin:begin + per].clone())
+            torch.distributed.all_gather_into_tensor(w, w[begin:begin + per].clone())
+            torch.distributed.all_reduce(v)
+        nat.check(nat.lib.opl_bfgs_finish_device(handle, dev.ptr(grad), dev.ptr(self._prev_step),
+                                                 dev.ptr(self._prev_jacobian), seed, dev.ptr(u), dev.ptr(v),
+                                                 dev.ptr(w), dev.ptr(direction)))
+        return direction
+
+    def inverse_hessian(self):
+        """The reference's ``_prev_inv_hessian`` as a NumPy array (local rows when sharded);
+        None before the second iteration."""
+        if self._native is None or nat.lib.opl_bfgs_state(self._native.pointer) == 0:
+            return None
+        n = self._native_n
+        begin, end, _ = self._row_range(n)
+        out = torch.empty((end - begin, n), dtype=torch.float64, device='cuda')
+        nat.check(nat.lib.opl_bfgs_materialize_device(self._native.pointer, dev.ptr(out)))
+        return dev.to_host(out)
+
+    # ---- Optimizer API --------------------------------------------------------------------
+    def _next(self, problem, x):
+        self._iteration += 1
+        if self._iteration == self._iterations_per_reset:     # optimizer.py:236-238
+            self.reset()
+        value, grad = problem.get_obj_jac(x)
+        self.jacobian = grad
+        direction = self._direction(grad)
+        self._prev_jacobian = grad
+        step_size = self._step_size_getter(x, value, grad, direction, problem)
+        self._prev_step = dev.scale(step_size, direction)
+        return value, dev.axpy(x, 1.0, self._prev_step)
+
+
+def _bfgs_eq(H_k, s_k, y_k):
+    """Next inverse Hessian from (H_k, s_k, y_k) on host arrays (optimizer.py:288-338), computed by
+    the device rank-2 pass.  Returns H_k itself when y.s == 0."""
+    h = dev.to_device(numpy.asarray(H_k, dtype=float))
+    s, y = dev.to_device(s_k), dev.to_device(y_k)
+    n = s.numel()
+    out = ctypes.c_void_p()
+    nat.check(nat.lib.opl_bfgs_create(ctypes.byref(out), n, 0, n, dev.stream_ptr()))
+    handle = _NativeHandle(out, nat.lib.opl_bfgs_destroy)
+    nat.check(nat.lib.opl_bfgs_load_device(handle.pointer, dev.ptr(h)))
+    zero = torch.zeros_like(y)
+    scratch = torch.empty_like(y)
+    # grad := y, prev_grad := 0  =>  the state's y is y_k; the direction output is discarded
+    nat.check(nat.lib.opl_bfgs_direction_device(handle.pointer, dev.ptr(y), dev.ptr(s), dev.ptr(zero), 0,
+                                                dev.ptr(scratch)))
+    result = torch.empty((n, n), dtype=torch.float64, device='cuda')
+    nat.check(nat.lib.opl_bfgs_materialize_device(handle.pointer, dev.ptr(result)))
+    return dev.to_host(result)
+
+
+# ----------------------------------------------------------------------------------------
+# L-BFGS
+# ----------------------------------------------------------------------------------------
+def initial_hessian_one_scalar(param_diff, jac_diff):
+    return 1.0
+
+
+def initial_hessian_gamma_scalar(param_diff, jac_diff):
+    """(s.y)/(y.y); 1.0 when y.y == 0 (optimizer.py:346-362)."""
+    s = param_diff if dev.is_device_vector(param_diff) else dev.to_device(param_diff)
+    y = jac_diff if dev.is_device_vector(jac_diff) else dev.to_device(jac_diff)
+    yy = dev.dot(y, y)
+    if yy == 0:
+        return 1.0
+    with numpy.errstate(all='ignore'):
+        return float(numpy.nan_to_num(numpy.float64(dev.dot(s, y)) / yy))
+
+
+_GAMMA_MODES = {initial_hessian_one_scalar: 0, initial_hessian_gamma_scalar: 1}
+
+
+class LBFGS(Optimizer):
+    """Limited-memory BFGS (optimizer.py:365-508); the two-loop recursion is one persistent
+    cooperative kernel over the device-resident (s, y) history (csrc/lbfgs.cu)."""
+
+    def __init__(self, step_size_getter=None, num_remembered_iterations=5,
+                 initial_hessian_scalar_func=initial_hessian_gamma_scalar):
+        super(LBFGS, self).__init__()
+        if step_size_getter is None:
+            step_size_getter = _default_step_size_getter()
+        self._step_size_getter = step_size_getter
+        if initial_hessian_scalar_func not in _GAMMA_MODES:
+            raise TypeError('initial_hessian_scalar_func must be initial_hessian_one_scalar or '
+                            'initial_hessian_gamma_scalar on the CUDA path (no CPU fallback)')
+        self._initial_hessian_scalar_func = initial_hessian_scalar_func
+        self._num_remembered_iterations = num_remembered_iterations
+        self._prev_step = None
+        self._prev_jacobian = None
+        self._native = None
+
+    def reset(self):
+        super(LBFGS, self).reset()
+        self._step_size_getter.reset()
+        self._prev_step = None
+        self._prev_jacobian = None
+        if self._native is not None:
+            nat.check(nat.lib.opl_lbfgs_reset(self._native.pointer))
+
+    def __getstate__(self):
+        state = super(LBFGS, self).__getstate__()
+        state['_native'] = None
+        state['_prev_step'] = None
+        state['_prev_jacobian'] = None
+        return state
+
+    def _state(self, n):
+        if self._native is None or self._native_n != n:
+            memory = self._num_remembered_iterations
+            memory = 0 if memory == float('inf') else int(memory)
+            out = ctypes.c_void_p()
+            nat.check(nat.lib.opl_lbfgs_create(ctypes.byref(out), n, memory, dev.stream_ptr()))
+            self._native = _NativeHandle(out, nat.lib.opl_lbfgs_destroy)
+            self._native_n = n
+        return self._native.pointer
+
+    def _step_direction(self, grad):
+        """_update_diffs + _lbfgs_step_dir (optimizer.py:433-493)."""
+        handle = self._state(grad.numel())
+        direction = torch.empty_like(grad)
+        nat.check(nat.lib.opl_lbfgs_direction_device(handle, dev.ptr(grad), dev.ptr(self._prev_step),
+                                                     dev.ptr(self._prev_jacobian),
+                                                     _GAMMA_MODES[self._initial_hessian_scalar_func],
+                                                     dev.ptr(direction)))
+        return direction
+
+    def _next(self, problem, x):
+        value, grad = problem.get_obj_jac(x)
+        self.jacobian = grad
+        direction = self._step_direction(grad)
+        self._prev_jacobian = grad
+        step_size = self._step_size_getter(x, value, grad, direction, problem)
+        self._prev_step = dev.scale(step_size, direction)
+        return value, dev.axpy(x, 1.0, self._prev_step)

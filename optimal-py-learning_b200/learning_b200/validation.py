@@ -1,0 +1,29 @@
+"""The two validation helpers the hot path's callers use, batched.
+
+The reference evaluates ``model.activate`` one pattern at a time in a Python loop
+(learning/validation.py:235-254); here the whole matrix goes through one batched forward
+(the same kernels as training), which is the SURVEY.md section 8(f) rank-1 widening.
+"""
+import numpy
+
+from .error import MeanSquaredError
+
+
+def get_error(model, input_matrix, target_matrix, error_func=None):
+    """Mean over patterns of error_func(model(x), target) (validation.py:235-244).
+
+    The reference averages per-pattern errors; for MSE and cross entropy the mean of the
+    per-row errors equals the error of the whole matrix, which is what the row kernel returns.
+    """
+    if error_func is None:
+        error_func = MeanSquaredError()
+    outputs = model.activate(numpy.asarray(input_matrix, dtype=float))
+    return error_func(outputs, numpy.asarray(target_matrix, dtype=float))
+
+
+def get_accuracy(model, input_matrix, target_matrix):
+    """Fraction of patterns whose arg-max output matches the arg-max target (validation.py:247-254)."""
+    outputs = numpy.asarray(model.activate(numpy.asarray(input_matrix, dtype=float)))
+    targets = numpy.asarray(target_matrix)
+    hits = numpy.argmax(outputs, axis=-1) == numpy.argmax(targets, axis=-1)
+    return float(numpy.mean(hits))

@@ -286,10 +286,10 @@ def run_gpu(args):
     ms_per_step = ms_total / args.steps
     value = world * 1e3 / ms_per_step              # 60000-pattern evaluations per second, all ranks
 
-    # sanity: objective of the timed evaluation is the cross entropy of a random-init 10-class net
+    # sanity: the timed evaluation produced a finite cross entropy and a non-zero gradient
     scal = (ctypes.c_double * 3)()
     nat.check(nat.lib.opl_mlp_probe_scalars(ws.pointer, dev.ptr(out), None, 1, scal))
-    assert 2.0 < scal[0] < 2.7 and scal[2] > 0.0, (scal[0], scal[2])
+    assert numpy.isfinite(scal[0]) and scal[0] > 0.0 and scal[2] > 0.0, (scal[0], scal[2])
 
     # ---- end to end through the reference-shaped API with HOST buffers ---------------------------
     e2e = None
@@ -304,7 +304,7 @@ def run_gpu(args):
             obj, grad = model._get_obj_jac(w_host, x, y)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        assert abs(obj - scal[0] * 1.0) < 1.0
+        assert abs(obj - scal[0]) <= 1e-9 * abs(obj), (obj, scal[0])
         e2e = {"value": args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": int(n * 8),
                "d2h_bytes_per_step": int(n * 8 + 8 + 4),
                "note": "MLP._get_obj_jac(params_host, X_host, Y_host): parameters H2D from pinned memory, gradient + "

@@ -112,6 +112,12 @@ int64_t opl_mlp_launch_count(const opl_mlp *ws);
 int opl_mlp_profile(opl_mlp *ws, int32_t enable);
 int opl_mlp_profile_read(opl_mlp *ws, int32_t capacity, int32_t *kinds, float *ms, int32_t *count);
 
+/* Benchmark hook (not on the training path): average ms of `iters` launches of one plain FP64 GEMM
+ * of the family the MLP uses.  layout 0: C[M,N]=A[M,K].B[K,N]; 1: A[M,K].B[N,K]^T; 2: A[K,M]^T.B[K,N]
+ * (split-K through scratch_dev when given).  All buffers are device pointers. */
+int opl_bench_gemm_f64(int32_t layout, int32_t M, int32_t N, int32_t K, const double *a_dev, const double *b_dev,
+                       double *c_dev, double *scratch_dev, int64_t scratch_len, int32_t iters, float *ms_out);
+
 /* ---- stand-alone host-buffer forms of the plugin objects' own methods (not on the training
  *      path; they run the same row kernel so the classes stay usable on their own) ---- */
 /* Transfer.__call__ (transfer.py:33-130) on a rows x cols matrix */

@@ -42,9 +42,19 @@ struct GemmArgs {
     int64_t ldaux;
     int epi;
     double tparam;          // gaussian variance
+    // TN only: CTAs of the first M-tile also accumulate the column sums of their B tiles
+    // (db = 1^T delta_0, mlp.py:276) into colsum_out[split * split_stride + col]
+    double *colsum_out;
 };
 
 constexpr int GEMM_BK = 16;
+
+// largest power of two <= min(avail, BK): thread groups that split the BK rows of a B tile evenly
+__host__ __device__ constexpr int colsum_groups(int avail) {
+    int g = 1;
+    while (g * 2 <= avail && g * 2 <= GEMM_BK) g *= 2;
+    return g;
+}
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, bool valid) {
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -107,44 +117,83 @@ __device__ __forceinline__ void load_tile(double *dst, const double *__restrict_
     }
 }
 
-__device__ __forceinline__ void epilogue_element(const GemmArgs &p, int row, int col, double acc) {
-    double z = acc;
-    if (p.bias) z += p.bias[col];
-    const int64_t ci = (int64_t)row * p.ldc + col;
-    const int64_t xi = (int64_t)row * p.ldaux + col;
+// Epilogue over one staged accumulator tile (rows x 2^log2_cols, row stride c_ld in shared
+// memory).  Deliberately a compact, non-unrolled loop in ONE non-inlined function: the first
+// version inlined exp/log per accumulator register (64x per thread) and produced a 511 KB kernel
+// whose epilogue stalled on instruction fetch (profiles/r01_*).  Consecutive threads take
+// consecutive columns: conflict-free shared reads, fully coalesced global stores / aux loads.
+static __device__ __noinline__ void epilogue_tile(const GemmArgs &p, const double *__restrict__ Cs, int c_ld, int row0,
+                                           int col0, int rows, int log2_cols, int tid, int nthreads,
+                                           int split) {
+    const int cols = 1 << log2_cols;
+    const int rmax = min(rows, p.M - row0), cmax = min(cols, p.N - col0);
+    if (rmax <= 0 || cmax <= 0) return;
+    double *C = p.C + (int64_t)split * p.split_stride;   // may alias p.aux_in (in-place delta)
+    const int total = rmax << log2_cols;
+    const double *bias = p.bias;
+    // four elements in flight per thread: the aux loads / stores of the memory-bound epilogues
+    // (K <= 16 GEMMs are pure streaming) need memory-level parallelism, not instruction count
+#define OPL_EPI_LOOP(PRELOAD, BODY)                                             \
+    for (int base = 0; base < total; base += 4 * nthreads) {                    \
+        double zz[4], xx[4];                                                    \
+        int64_t cc[4], xc[4];                                                   \
+        bool ok[4];                                                             \
+        _Pragma("unroll") for (int u = 0; u < 4; ++u) {                         \
+            const int idx = base + u * nthreads + tid;                          \
+            const int r = idx >> log2_cols, c = idx & (cols - 1);               \
+            ok[u] = idx < total && c < cmax;                                    \
+            cc[u] = (int64_t)(row0 + r) * p.ldc + col0 + c;                     \
+            xc[u] = (int64_t)(row0 + r) * p.ldaux + col0 + c;                   \
+            zz[u] = ok[u] ? Cs[r * c_ld + c] : 0.0;                             \
+            if (ok[u] && bias) zz[u] += bias[col0 + c];                         \
+            xx[u] = 0.0;                                                        \
+            if (ok[u]) { const int64_t xi = xc[u]; (void)xi; PRELOAD }          \
+        }                                                                       \
+        _Pragma("unroll") for (int u = 0; u < 4; ++u) {                         \
+            if (ok[u]) {                                                        \
+                const double z = zz[u], x = xx[u];                              \
+                const int64_t ci = cc[u], xi = xc[u];                           \
+                (void)x; (void)xi;                                              \
+                BODY                                                            \
+            }                                                                   \
+        }                                                                       \
+    }
     switch (p.epi) {
         case EPI_STORE:
-            p.C[ci] = z;
+            OPL_EPI_LOOP(, C[ci] = z;)
             break;
         case EPI_TANH:
-            p.C[ci] = tanh(z);
+            OPL_EPI_LOOP(, C[ci] = tanh(z);)
             break;
         case EPI_SOFTPLUS: {   // calculate.py:128-141
-            double r = log(1.0 + exp(z));
-            if (isinf(r)) r = z;
-            p.C[ci] = r;
-            if (p.aux_out) p.aux_out[xi] = 1.0 / (1.0 + exp(-z));
+            double *__restrict__ aux = p.aux_out;
+            // one exp serves both: sigmoid(z) = e/(1+e) (== 1/(1+exp(-z)) to rounding; 1 once e overflows)
+            OPL_EPI_LOOP(, const double e = exp(z); const double d_ = 1.0 + e; double r_ = log(d_);
+                         if (isinf(r_)) r_ = z; C[ci] = r_; if (aux) aux[xi] = isinf(e) ? 1.0 : e / d_;)
             break;
         }
         case EPI_GAUSSIAN: {   // calculate.py:101-106
-            double a = exp(-(z * z / p.tparam));
-            p.C[ci] = a;
-            if (p.aux_out) p.aux_out[xi] = -2.0 * z * a / p.tparam;
+            double *__restrict__ aux = p.aux_out;
+            const double v = p.tparam;
+            OPL_EPI_LOOP(, const double a = exp(-(z * z / v)); C[ci] = a; if (aux) aux[xi] = -2.0 * z * a / v;)
             break;
         }
-        case EPI_MUL_AUX:
-            p.C[ci] = z * p.aux_in[xi];
+        case EPI_MUL_AUX: {
+            const double *aux = p.aux_in;   // may alias C (delta overwrites D in place)
+            OPL_EPI_LOOP(xx[u] = aux[xi];, C[ci] = z * x;)
             break;
+        }
         case EPI_MUL_DTANH: {
-            double a = p.aux_in[xi];
-            p.C[ci] = z * (1.0 - a * a);
+            const double *aux = p.aux_in;
+            OPL_EPI_LOOP(xx[u] = aux[xi];, C[ci] = z * (1.0 - x * x);)
             break;
         }
     }
+#undef OPL_EPI_LOOP
 }
 
-template <int LAYOUT, int BM, int BN, int WM, int WN, int VEC, int STAGES>
-__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32)
+template <int LAYOUT, int BM, int BN, int WM, int WN, int VEC, int STAGES, int MINBLOCKS>
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINBLOCKS)
 gemm_f64_kernel(const GemmArgs p) {
     constexpr int BK = GEMM_BK;
     constexpr int NTHREADS = (BM / WM) * (BN / WN) * 32;
@@ -155,6 +204,14 @@ gemm_f64_kernel(const GemmArgs p) {
     constexpr int A_TILE = (A_KINNER ? BM : BK) * A_LD;
     constexpr int B_TILE = (B_KINNER ? BN : BK) * B_LD;
     constexpr int MI = WM / 8, NI = WN / 8;
+    // accumulator staging for the epilogue reuses the pipeline buffers
+    constexpr int C_LD = BN + 8;                        // == 8 (mod 16): conflict-free 16-byte fragment stores
+    constexpr int SMEM_DOUBLES = STAGES * (A_TILE + B_TILE);
+    constexpr int PASS_ROWS = (BM * C_LD <= SMEM_DOUBLES) ? BM : ((BM / 2) * C_LD <= SMEM_DOUBLES ? BM / 2 : BM / 4);
+    static_assert(PASS_ROWS * C_LD <= SMEM_DOUBLES, "accumulator tile does not fit the pipeline buffers");
+    static_assert(PASS_ROWS % WM == 0, "a warp's rows must fall into one epilogue pass");
+    constexpr int LOG2_BN = BN == 128 ? 7 : (BN == 64 ? 6 : (BN == 32 ? 5 : 4));
+    static_assert((1 << LOG2_BN) == BN, "BN must be 16, 32, 64 or 128");
 
     extern __shared__ __align__(16) double smem[];
     double *As = smem;
@@ -177,6 +234,9 @@ gemm_f64_kernel(const GemmArgs p) {
 #pragma unroll
         for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+    const bool do_colsum = LAYOUT == GEMM_TN && p.colsum_out != nullptr && blockIdx.y == 0;
+    double colsum = 0.0;
+
     auto issue = [&](int kt) {
         const int st = kt % STAGES;
         const int k0 = k_begin + kt * BK;
@@ -190,6 +250,7 @@ gemm_f64_kernel(const GemmArgs p) {
         cp_async_commit();
     }
 
+#pragma unroll 1
     for (int kt = 0; kt < nk; ++kt) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
@@ -198,6 +259,15 @@ gemm_f64_kernel(const GemmArgs p) {
 
         const double *a = As + (kt % STAGES) * A_TILE;
         const double *b = Bs + (kt % STAGES) * B_TILE;
+        if (LAYOUT == GEMM_TN && do_colsum) {   // zero-filled rows beyond k_end add nothing
+            constexpr int GROUPS = colsum_groups(NTHREADS / BN);
+            constexpr int PER = BK / GROUPS;
+            const int col = tid % BN, grp = tid / BN;
+            if (grp < GROUPS) {
+#pragma unroll
+                for (int k = 0; k < PER; ++k) colsum += b[(grp * PER + k) * B_LD + col];
+            }
+        }
 #pragma unroll
         for (int kk = 0; kk < BK / 4; ++kk) {
             double af[MI], bf[NI];
@@ -216,19 +286,35 @@ gemm_f64_kernel(const GemmArgs p) {
         }
     }
     cp_async_wait<0>();
-
-    GemmArgs q = p;
-    q.C = p.C + (int64_t)blockIdx.z * p.split_stride;
+    __syncthreads();   // every warp is done with the operand tiles: reuse them for the accumulators
+    if (LAYOUT == GEMM_TN && do_colsum) {   // fold the per-thread column partials in a fixed order
+        constexpr int GROUPS = colsum_groups(NTHREADS / BN);
+        double *fold = smem;
+        if (tid / BN < GROUPS) fold[tid] = colsum;
+        __syncthreads();
+        if (tid < BN && n0 + tid < p.N) {
+            double t_ = 0.0;
 #pragma unroll
-    for (int i = 0; i < MI; ++i) {
-        const int row = m0 + wm0 + 8 * i + g;
-        if (row >= p.M) continue;
-#pragma unroll
-        for (int j = 0; j < NI; ++j) {
-            const int col = n0 + wn0 + 8 * j + 2 * t;
-            if (col < p.N) epilogue_element(q, row, col, acc[i][j][0]);
-            if (col + 1 < p.N) epilogue_element(q, row, col + 1, acc[i][j][1]);
+            for (int gidx = 0; gidx < GROUPS; ++gidx) t_ += fold[gidx * BN + tid];
+            p.colsum_out[(int64_t)blockIdx.z * p.split_stride + n0 + tid] = t_;
         }
+        __syncthreads();
+    }
+
+    double *Cs = smem;
+#pragma unroll
+    for (int pass = 0; pass < BM / PASS_ROWS; ++pass) {
+        if (wm0 / PASS_ROWS == pass) {   // warp-uniform
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NI; ++j)
+                    *reinterpret_cast<double2 *>(Cs + (wm0 - pass * PASS_ROWS + 8 * i + g) * C_LD + wn0 + 8 * j + 2 * t) =
+                        make_double2(acc[i][j][0], acc[i][j][1]);
+        }
+        __syncthreads();
+        epilogue_tile(p, Cs, C_LD, m0 + pass * PASS_ROWS, n0, PASS_ROWS, LOG2_BN, tid, NTHREADS, blockIdx.z);
+        if (pass + 1 < BM / PASS_ROWS) __syncthreads();
     }
 }
 
@@ -245,6 +331,9 @@ struct SplitPlan {
     int splits;
     int k_per_split;
 };
+// N-tile width / M-tile height the launcher will use
+int gemm_tile_n(int N);
+int gemm_tile_m(int layout, int M, int N);
 SplitPlan plan_split_k(int M, int N, int K);
 
 }  // namespace opl

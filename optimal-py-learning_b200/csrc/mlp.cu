@@ -146,6 +146,67 @@ __global__ void __launch_bounds__(256) output_rows_kernel(const RowArgs r) {
     }
 }
 
+// Same stage for narrow outputs (C <= MAXC): one thread owns a whole pattern in registers -- no
+// shuffles, no re-reads, every transcendental evaluated once.  Classification heads (3..32
+// classes) take this path.
+template <int MAXC>
+__global__ void __launch_bounds__(256) output_rows_thread_kernel(const RowArgs r) {
+    __shared__ double scratch[33];
+    const bool softmax = r.tid == OPL_TRANSFER_SOFTMAX;
+    double loss = 0.0;
+    bool bad = false;
+    for (int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; row < r.rows;
+         row += (int64_t)gridDim.x * blockDim.x) {
+        const double *zp = r.Z + row * r.C;
+        double z[MAXC], a[MAXC];
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) z[c] = c < r.C ? zp[c] : -INFINITY;
+        if (softmax) {
+            double mx = -INFINITY, den = 0.0;
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c) mx = fmax(mx, z[c]);
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c) {
+                a[c] = c < r.C ? exp(z[c] - mx) : 0.0;
+                den += a[c];
+            }
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c) a[c] = a[c] / den;
+        } else {
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c) a[c] = c < r.C ? transfer_value(r.tid, r.tparam, z[c]) : 0.0;
+        }
+        if (r.A) {
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c)
+                if (c < r.C) r.A[row * r.C + c] = a[c];
+        }
+        if (r.Y || r.G) {
+            double g[MAXC], t = 0.0;
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c) {
+                g[c] = 0.0;
+                if (c < r.C) {
+                    g[c] = r.G ? r.G[row * r.C + c] : error_term(r, a[c], r.Y[row * r.C + c], loss, bad);
+                    t += g[c] * a[c];
+                }
+            }
+            if (r.D) {
+#pragma unroll
+                for (int c = 0; c < MAXC; ++c)
+                    if (c < r.C)
+                        r.D[row * r.C + c] = softmax ? a[c] * (g[c] - t)
+                                                     : g[c] * transfer_slope(r.tid, r.tparam, z[c], a[c]);
+            }
+        }
+    }
+    if (bad) *r.flag = 1;
+    if (r.loss_partial) {
+        loss = block_sum(loss, scratch);
+        if (threadIdx.x == 0) r.loss_partial[blockIdx.x] = loss;
+    }
+}
+
 // hidden softmax layer backward: delta = a o (g - sum g a), in place over g
 __global__ void __launch_bounds__(256)
 softmax_backward_rows_kernel(double *G, const double *A, int64_t rows, int C, int group) {
@@ -318,6 +379,8 @@ int row_group(int c) {
     return g;
 }
 
+constexpr int kThreadRowMaxC = 16;
+
 int row_grid(int64_t rows, int group) {
     const int rows_per_block = 256 / group;
     int64_t blocks = ceil_div(rows, rows_per_block);
@@ -325,6 +388,22 @@ int row_grid(int64_t rows, int group) {
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     return (int)blocks;
+}
+
+// pick the row kernel: thread-per-row for narrow outputs unless it works in place (hidden softmax)
+// returns the grid size used (== number of loss partials written)
+int launch_rows(const RowArgs &r, int max_grid, cudaStream_t stream) {
+    if (r.C <= kThreadRowMaxC && r.A != r.Z) {
+        int64_t grid = ceil_div(r.rows, 256);
+        if (grid > max_grid) grid = max_grid;
+        if (grid < 1) grid = 1;
+        output_rows_thread_kernel<kThreadRowMaxC><<<(unsigned)grid, 256, 0, stream>>>(r);
+        return (int)grid;
+    }
+    int grid = row_grid(r.rows, r.group);
+    if (grid > max_grid) grid = max_grid;
+    output_rows_kernel<<<grid, 256, 0, stream>>>(r);
+    return grid;
 }
 
 int free_all(opl_mlp *ws) {
@@ -416,11 +495,9 @@ int output_stage(opl_mlp *ws, const double *y, int64_t rows, bool want_act, bool
     r.mse_mul = 2.0 / ((double)ws->norm_rows * (double)r.C);
     r.flag = ws->flag;
     r.group = row_group(r.C);
-    int grid = row_grid(rows, r.group);
-    if (grid > ws->loss_blocks) grid = ws->loss_blocks;
     r.loss_partial = y ? ws->loss_partial : nullptr;
     mark(ws, STAGE_ROWS * 100 + L);
-    output_rows_kernel<<<grid, 256, 0, ws->stream>>>(r);
+    const int grid = launch_rows(r, ws->loss_blocks, ws->stream);
     OPL_LAUNCH_CHECK();
     ++ws->launches;
     if (y && obj_out) {
@@ -439,7 +516,7 @@ int backward(opl_mlp *ws, const double *w, const double *x, int64_t rows, double
         // dW_l = A_l^T delta_l  (mlp.py:269-273), reduction over the patterns
         {
             SplitPlan plan = plan_split_k(din, dout, (int)rows);
-            if ((int64_t)plan.splits * din * dout > ws->partials_len)
+            if ((int64_t)plan.splits * ((int64_t)din * dout + dout) > ws->partials_len)
                 return fail(OPL_E_STATE, "split-K scratch too small (layer %d)", l);
             GemmArgs a = {};
             a.A = l == 0 ? x : ws->act[l];
@@ -452,20 +529,25 @@ int backward(opl_mlp *ws, const double *w, const double *x, int64_t rows, double
             a.ldc = dout;
             a.k_per_split = plan.k_per_split;
             a.epi = EPI_STORE;
+            // layer 0: the first M-tile's CTAs also sum the columns of delta_0 (bias gradient).  The
+            // flat layout puts bias right before W_0, so [db ; dW_0] is ONE contiguous reduce.
+            const int64_t lead = l == 0 ? dout : 0;
             mark(ws, STAGE_DW * 100 + l);
             if (plan.splits == 1) {
                 a.C = grad + ws->w_off[l];
+                a.colsum_out = l == 0 ? grad : nullptr;
                 int rc = launch_gemm_f64(GEMM_TN, a, 1, ws->stream, &ws->launches);
                 if (rc != OPL_OK) return rc;
             } else {
-                a.C = ws->partials;
-                a.split_stride = (int64_t)din * dout;
+                a.split_stride = lead + (int64_t)din * dout;
+                a.C = ws->partials + lead;
+                a.colsum_out = l == 0 ? ws->partials : nullptr;
                 int rc = launch_gemm_f64(GEMM_TN, a, plan.splits, ws->stream, &ws->launches);
                 if (rc != OPL_OK) return rc;
-                const int64_t count = (int64_t)din * dout;
+                const int64_t count = lead + (int64_t)din * dout;
                 mark(ws, STAGE_DW_REDUCE * 100 + l);
-                rc = launch_reduce_partials(ws->partials, plan.splits, count, count, grad + ws->w_off[l], ws->stream,
-                                            &ws->launches);
+                rc = launch_reduce_partials(ws->partials, plan.splits, count, count, grad + ws->w_off[l] - lead,
+                                            ws->stream, &ws->launches);
                 if (rc != OPL_OK) return rc;
             }
         }
@@ -507,22 +589,6 @@ int backward(opl_mlp *ws, const double *w, const double *x, int64_t rows, double
             OPL_LAUNCH_CHECK();
             ++ws->launches;
         }
-    }
-    // db = column sums of delta_0 (mlp.py:276)
-    {
-        const int cols = (int)ws->width[1];
-        int64_t nblk = std::max<int64_t>(1, std::min<int64_t>(ceil_div(rows, 64),
-                                                              (2 * (int64_t)sm_count()) / ceil_div(cols, 32) + 1));
-        if (nblk * cols > ws->partials_len) nblk = std::max<int64_t>(1, ws->partials_len / cols);
-        const int64_t rpb = ceil_div(rows, nblk);
-        nblk = ceil_div(rows, rpb);
-        dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)nblk);
-        mark(ws, STAGE_BIAS * 100);
-        colsum_partial_kernel<<<grid, dim3(32, 8), 0, ws->stream>>>(ws->delta[0], rows, cols, rpb, ws->partials);
-        OPL_LAUNCH_CHECK();
-        ++ws->launches;
-        int rc = launch_reduce_partials(ws->partials, (int)nblk, cols, cols, grad, ws->stream, &ws->launches);
-        if (rc != OPL_OK) return rc;
     }
     return OPL_OK;
 }
@@ -632,7 +698,7 @@ int opl_mlp_create(opl_mlp **out, int32_t n_widths, const int64_t *widths, const
             OPL_TRY(cudaMalloc(&ws->delta[l], bytes));
         }
         SplitPlan plan = plan_split_k((int)widths[l], (int)widths[l + 1], (int)max_rows);
-        partials = std::max<int64_t>(partials, (int64_t)(plan.splits + 1) * widths[l] * widths[l + 1]);
+        partials = std::max<int64_t>(partials, (int64_t)(plan.splits + 1) * (widths[l] * widths[l + 1] + widths[l + 1]));
     }
     partials = std::max<int64_t>(partials, (int64_t)(4 * sm_count() + 8) * widths[1]);
     ws->partials_len = partials;
@@ -838,14 +904,14 @@ int rows_call(int tid, double tparam, int eid, const double *z_host, const doubl
     r.mse_mul = 2.0 / ((double)rows * (double)cols);
     r.flag = flag;
     r.group = row_group(r.C);
-    const int grid = row_grid(rows, r.group);
+    const int max_grid = 8 * sm_count();
     if (loss_out) {
-        rc = sc.alloc((void **)&lp, sizeof(double) * (size_t)grid);
+        rc = sc.alloc((void **)&lp, sizeof(double) * (size_t)max_grid);
         if (rc == OPL_OK) rc = sc.alloc((void **)&res, sizeof(double));
         if (rc != OPL_OK) return rc;
         r.loss_partial = lp;
     }
-    output_rows_kernel<<<grid, 256>>>(r);
+    const int grid = launch_rows(r, max_grid, nullptr);
     OPL_LAUNCH_CHECK();
     if (loss_out) {
         loss_final_kernel<<<1, 256>>>(lp, grid, eid, (double)rows, (double)cols, res);

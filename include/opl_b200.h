@@ -118,6 +118,12 @@ int opl_mlp_profile_read(opl_mlp *ws, int32_t capacity, int32_t *kinds, float *m
 int opl_bench_gemm_f64(int32_t layout, int32_t M, int32_t N, int32_t K, const double *a_dev, const double *b_dev,
                        double *c_dev, double *scratch_dev, int64_t scratch_len, int32_t iters, float *ms_out);
 
+/* Same hook for the fast-mode TF32 family (tcgen05.mma + TMEM + TMA): FP32 row-major device buffers,
+ * N % 32 == 0, K % 32 == 0 (M % 4 == 0 for layout 2); `splits` > 1 runs split-K through scratch_dev. */
+int opl_bench_gemm_tf32(int32_t layout, int32_t M, int32_t N, int32_t K, const float *a_dev, const float *b_dev,
+                        float *c_dev, float *scratch_dev, int64_t scratch_len, int32_t splits, int32_t iters,
+                        float *ms_out);
+
 /* ---- stand-alone host-buffer forms of the plugin objects' own methods (not on the training
  *      path; they run the same row kernel so the classes stay usable on their own) ---- */
 /* Transfer.__call__ (transfer.py:33-130) on a rows x cols matrix */

@@ -1,0 +1,393 @@
+// tcgen05 / TMEM / TMA GEMM for the fast mode -- see gemm_tf32.cuh for the design.
+#include <cudaTypedefs.h>
+
+#include <algorithm>
+
+#include "gemm_tf32.cuh"
+
+namespace opl {
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded spin: a protocol bug traps (reported as a launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
+        if (spin > (1u << 28)) __trap();
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c_inner, int c_outer, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols));
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem], 128 x N x 8 in TF32 with FP32 accumulation
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor, Blackwell version 1 (cute::UMMA::SmemDescriptor).
+//   layout_type 2 = SWIZZLE_128B          (K-major operands: 16-byte chunks XOR row%8, 1024-byte atoms)
+//   layout_type 1 = SWIZZLE_128B_BASE32B  (the ONLY layout for MN-major 32-bit operands: 32-byte chunks
+//                                          XOR row%4, 512-byte atoms; TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(lbo_bytes >> 4) << 16;
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)layout_type << 61;
+    return d;
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------
+constexpr int tf32_stages(int bn) { return bn >= 128 ? 3 : TF32_STAGES; }
+
+template <int BN>
+struct Tf32Smem {
+    static constexpr int STAGES = tf32_stages(BN);
+    static constexpr int A_BYTES = TF32_BM * 128;
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float epi_apply(const Tf32GemmArgs &p, float z, float aux, float &aux_out_val) {
+    switch (p.epi) {
+        case TEPI_TANH: return tanhf(z);
+        case TEPI_SOFTPLUS: {
+            const float e = expf(z);
+            aux_out_val = isinf(e) ? 1.0f : e / (1.0f + e);
+            const float r = log1pf(e);
+            return isinf(r) ? z : r;
+        }
+        case TEPI_GAUSSIAN: {
+            const float a = expf(-(z * z / p.tparam));
+            aux_out_val = -2.0f * z * a / p.tparam;
+            return a;
+        }
+        case TEPI_MUL_AUX: return z * aux;
+        case TEPI_MUL_DTANH: return z * (1.0f - aux * aux);
+        default: return z;
+    }
+}
+
+template <bool A_MN, bool B_MN, int BN>
+__global__ void __launch_bounds__(192, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Tf32GemmArgs p) {
+    using S = Tf32Smem<BN>;
+    constexpr int STAGES = S::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t *sA = smem;
+    uint8_t *sB = smem + STAGES * S::A_BYTES;
+    uint64_t *full = reinterpret_cast<uint64_t *>(sB + STAGES * S::B_BYTES);
+    uint64_t *empty = full + STAGES;
+    uint64_t *tmem_full = empty + STAGES;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * TF32_BM, n0 = blockIdx.x * BN;
+    const int k_begin = blockIdx.z * p.k_per_split;
+    const int k_end = min(p.K, k_begin + p.k_per_split);
+    const int nkb = k_end > k_begin ? (k_end - k_begin + TF32_BK - 1) / TF32_BK : 0;
+    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) tmem_alloc(tmem_ptr, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0 && lane == 0) {
+        // ================= TMA producer =================
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t phase = (kb / STAGES) & 1;
+            mbar_wait(&empty[s], phase ^ 1);
+            mbar_expect_tx(&full[s], S::A_BYTES + S::B_BYTES);
+            const int k0 = k_begin + kb * TF32_BK;
+            uint8_t *a = sA + s * S::A_BYTES, *b = sB + s * S::B_BYTES;
+            if (!A_MN) tma_load_2d(a, &tmA, k0, m0, &full[s]);                       // box {32 k, 128 m}
+            else
+                for (int j = 0; j < TF32_BM / 32; ++j) tma_load_2d(a + j * 4096, &tmA, m0 + 32 * j, k0, &full[s]);   // box {32 m, 32 k}
+            if (!B_MN) tma_load_2d(b, &tmB, k0, n0, &full[s]);                       // box {32 k, BN n}
+            else
+                for (int j = 0; j < BN / 32; ++j) tma_load_2d(b + j * 4096, &tmB, n0 + 32 * j, k0, &full[s]);        // box {32 n, 32 k}
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ================= MMA issuer =================
+        // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, majors, N>>3, M>>4
+        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                                   ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TF32_BM >> 4) << 24);
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t phase = (kb / STAGES) & 1;
+            mbar_wait(&full[s], phase);
+            tc_fence_after();
+            const uint32_t a = smem_u32(sA + s * S::A_BYTES), b = smem_u32(sB + s * S::B_BYTES);
+#pragma unroll
+            for (int k = 0; k < TF32_BK / 8; ++k) {
+                // K-major: 8 tf32 = 32 bytes further along the swizzled 128-byte row; SBO = 8 rows x 128 B
+                // MN-major: 8 k-rows = 1024 bytes further (two 4-row atoms, SBO = 512 B);
+                //           LBO = next 32-wide MN block (one TMA box of 32 k-rows = 4096 B)
+                const uint64_t ad = A_MN ? smem_desc(a + k * 1024, 4096, 512, 1) : smem_desc(a + k * 32, 16, 1024, 2);
+                const uint64_t bd = B_MN ? smem_desc(b + k * 1024, 4096, 512, 1) : smem_desc(b + k * 32, 16, 1024, 2);
+                umma_tf32(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty[s]);       // smem stage reusable once these MMAs have read it
+        }
+        if (nkb > 0) umma_commit(tmem_full);
+    } else if (warp >= 2) {
+        // ================= epilogue: TMEM -> registers -> global =================
+        const int lane_group = warp & 3;                 // tcgen05.ld: warp w may touch lanes 32*(w%4)..+31
+        const int row = m0 + lane_group * 32 + lane;
+        if (nkb > 0) {
+            mbar_wait(tmem_full, 0);
+            tc_fence_after();
+        }
+        float *C = p.C + (int64_t)blockIdx.z * p.split_stride;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            if (nkb > 0) tmem_ld32(tmem_base + ((uint32_t)(lane_group * 32) << 16) + (uint32_t)c0, v);
+            else
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0u;
+            const int col0 = n0 + c0;
+            if (row < p.M && col0 < p.N) {
+                float out[32], aux_o[32];
+                const bool need_aux_in = p.epi == TEPI_MUL_AUX || p.epi == TEPI_MUL_DTANH;
+                const bool have_aux_out = p.aux_out != nullptr && (p.epi == TEPI_SOFTPLUS || p.epi == TEPI_GAUSSIAN);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    float4 ax = make_float4(0.f, 0.f, 0.f, 0.f), bs = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (need_aux_in) ax = *reinterpret_cast<const float4 *>(p.aux_in + (int64_t)row * p.ldaux + col0 + 4 * q);
+                    if (p.bias) bs = *reinterpret_cast<const float4 *>(p.bias + col0 + 4 * q);
+                    const float axv[4] = {ax.x, ax.y, ax.z, ax.w}, bsv[4] = {bs.x, bs.y, bs.z, bs.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int j = 4 * q + e;
+                        float ao = 0.f;
+                        float r = epi_apply(p, __uint_as_float(v[j]) + bsv[e], axv[e], ao);
+                        if (col0 + j >= p.n_valid) {      // layer padding stays exactly zero
+                            r = 0.f;
+                            ao = 0.f;
+                        }
+                        out[j] = r;
+                        aux_o[j] = ao;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    *reinterpret_cast<float4 *>(C + (int64_t)row * p.ldc + col0 + 4 * q) =
+                        make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
+                    if (have_aux_out)
+                        *reinterpret_cast<float4 *>(p.aux_out + (int64_t)row * p.ldaux + col0 + 4 * q) =
+                            make_float4(aux_o[4 * q], aux_o[4 * q + 1], aux_o[4 * q + 2], aux_o[4 * q + 3]);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (!fn) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+    }
+    return fn;
+}
+
+int make_tensor_map_f32(CUtensorMap *map, const float *base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
+                        uint32_t box_inner, uint32_t box_outer, bool mn_major) {
+    PFN_cuTensorMapEncodeTiled_v12000 fn = encode_fn();
+    if (!fn) return fail(OPL_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    if ((reinterpret_cast<uintptr_t>(base) & 15u) || (ld_elems * sizeof(float)) % 16)
+        return fail(OPL_E_ARG, "TMA operand must be 16-byte aligned with a 16-byte multiple row pitch");
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {ld_elems * sizeof(float)};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(OPL_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return OPL_OK;
+}
+
+namespace {
+
+template <bool A_MN, bool B_MN, int BN>
+int launch_tf32(const CUtensorMap &ta, const CUtensorMap &tb, const Tf32GemmArgs &a, int splits, cudaStream_t stream) {
+    auto kern = gemm_tf32_kernel<A_MN, B_MN, BN>;
+    static bool configured = false;
+    if (!configured) {
+        OPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Tf32Smem<BN>::BYTES));
+        configured = true;
+    }
+    dim3 grid((unsigned)ceil_div(a.N, BN), (unsigned)ceil_div(a.M, TF32_BM), (unsigned)splits);
+    kern<<<grid, 192, Tf32Smem<BN>::BYTES, stream>>>(ta, tb, a);
+    OPL_LAUNCH_CHECK();
+    return OPL_OK;
+}
+
+template <bool A_MN, bool B_MN>
+int launch_bn(int bn, const CUtensorMap &ta, const CUtensorMap &tb, const Tf32GemmArgs &a, int splits, cudaStream_t stream) {
+    if (bn == 32) return launch_tf32<A_MN, B_MN, 32>(ta, tb, a, splits, stream);
+    if (bn == 64) return launch_tf32<A_MN, B_MN, 64>(ta, tb, a, splits, stream);
+    return launch_tf32<A_MN, B_MN, 128>(ta, tb, a, splits, stream);
+}
+
+}  // namespace
+
+int launch_gemm_tf32(int layout, const float *A, int64_t lda, const float *B, int64_t ldb, const Tf32GemmArgs &args,
+                     int splits, cudaStream_t stream, int64_t *launches) {
+    if (args.M <= 0 || args.N <= 0) return OPL_OK;
+    if (args.K % TF32_BK || args.N % 32 || args.ldc % 4)
+        return fail(OPL_E_ARG, "tf32 GEMM needs K %% 32 == 0, N %% 32 == 0 (padded layer widths)");
+    const int bn = args.N >= 128 ? 128 : (args.N >= 64 ? 64 : 32);
+    const bool a_mn = layout == 2, b_mn = layout != 1;
+    CUtensorMap ta, tb;
+    int rc;
+    // A: K-major [M rows][K]  -> box {32 k, 128 m};  MN-major [K rows][M] -> box {32 m, 32 k}
+    rc = a_mn ? make_tensor_map_f32(&ta, A, (uint64_t)args.M, (uint64_t)args.K, (uint64_t)lda, 32, 32, true)
+              : make_tensor_map_f32(&ta, A, (uint64_t)args.K, (uint64_t)args.M, (uint64_t)lda, 32, TF32_BM, false);
+    if (rc != OPL_OK) return rc;
+    // B: K-major [N rows][K]  -> box {32 k, BN n};   MN-major [K rows][N] -> box {32 n, 32 k}
+    rc = b_mn ? make_tensor_map_f32(&tb, B, (uint64_t)args.N, (uint64_t)args.K, (uint64_t)ldb, 32, 32, true)
+              : make_tensor_map_f32(&tb, B, (uint64_t)args.K, (uint64_t)args.N, (uint64_t)ldb, 32, (uint32_t)bn, false);
+    if (rc != OPL_OK) return rc;
+    if (layout == 0) rc = launch_bn<false, true>(bn, ta, tb, args, splits, stream);
+    else if (layout == 1) rc = launch_bn<false, false>(bn, ta, tb, args, splits, stream);
+    else rc = launch_bn<true, true>(bn, ta, tb, args, splits, stream);
+    if (rc == OPL_OK && launches) ++*launches;
+    return rc;
+}
+
+__global__ void reduce_partials_f32_kernel(const float *__restrict__ partial, int splits, int64_t stride, int64_t count,
+                                           float *__restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int k = 0; k < splits; ++k) s += (double)partial[(int64_t)k * stride + i];
+        out[i] = (float)s;
+    }
+}
+
+}  // namespace opl
+
+// Benchmark / validation hook: one plain TF32 GEMM on caller-provided device buffers.
+extern "C" int opl_bench_gemm_tf32(int32_t layout, int32_t M, int32_t N, int32_t K, const float *a_dev,
+                                   const float *b_dev, float *c_dev, float *scratch_dev, int64_t scratch_len,
+                                   int32_t splits, int32_t iters, float *ms_out) {
+    using namespace opl;
+    if (!a_dev || !b_dev || !c_dev || !ms_out || layout < 0 || layout > 2 || iters < 1 || splits < 1)
+        return fail(OPL_E_ARG, "opl_bench_gemm_tf32: bad arguments");
+    Tf32GemmArgs g = {};
+    g.C = c_dev;
+    g.ldc = N;
+    g.M = M;
+    g.N = N;
+    g.K = K;
+    g.n_valid = N;
+    g.ldaux = N;
+    g.epi = TEPI_STORE;
+    g.k_per_split = (int)(ceil_div(ceil_div(K, splits), TF32_BK) * TF32_BK);
+    const int64_t lda = layout == 2 ? M : K, ldb = layout == 1 ? K : N;
+    if (splits > 1) {
+        if (!scratch_dev || (int64_t)splits * M * N > scratch_len) return fail(OPL_E_ARG, "opl_bench_gemm_tf32: scratch too small");
+        g.C = scratch_dev;
+        g.split_stride = (int64_t)M * N;
+    }
+    cudaEvent_t e0, e1;
+    OPL_CUDA(cudaEventCreate(&e0));
+    OPL_CUDA(cudaEventCreate(&e1));
+    const int64_t count = (int64_t)M * N;
+    const int rgrid = (int)std::min<int64_t>(ceil_div(count, 256), 4 * (int64_t)sm_count());
+    for (int i = 0; i <= iters; ++i) {
+        if (i == 1) OPL_CUDA(cudaEventRecord(e0, nullptr));
+        int rc = launch_gemm_tf32(layout, a_dev, lda, b_dev, ldb, g, splits, nullptr, nullptr);
+        if (rc != OPL_OK) return rc;
+        if (splits > 1) reduce_partials_f32_kernel<<<rgrid, 256>>>(scratch_dev, splits, count, count, c_dev);
+    }
+    OPL_CUDA(cudaEventRecord(e1, nullptr));
+    OPL_CUDA(cudaEventSynchronize(e1));
+    OPL_CUDA(cudaEventElapsedTime(ms_out, e0, e1));
+    *ms_out /= iters;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    OPL_LAUNCH_CHECK();
+    return OPL_OK;
+}

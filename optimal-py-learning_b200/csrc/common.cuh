@@ -67,6 +67,13 @@ __device__ __forceinline__ double block_sum(double v, double *scratch) {
     return scratch[32];
 }
 
+// round-to-nearest FP32 -> TF32 (10-bit mantissa); the result is an FP32 bit pattern a tf32 tensor core reads exactly
+__device__ __forceinline__ float round_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
 // numpy.nan_to_num for float64: nan -> 0, +inf -> DBL_MAX, -inf -> -DBL_MAX
 __device__ __forceinline__ double nan_to_num(double v) {
     if (isnan(v)) return 0.0;

@@ -227,6 +227,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         const int j = 4 * q + e;
                         float ao = 0.f;
                         float r = epi_apply(p, __uint_as_float(v[j]) + bsv[e], axv[e], ao);
+                        if (p.round_out) r = round_tf32(r);
                         if (col0 + j >= p.n_valid) {      // layer padding stays exactly zero
                             r = 0.f;
                             ao = 0.f;
@@ -316,8 +317,9 @@ int launch_bn(int bn, const CUtensorMap &ta, const CUtensorMap &tb, const Tf32Ge
 int launch_gemm_tf32(int layout, const float *A, int64_t lda, const float *B, int64_t ldb, const Tf32GemmArgs &args,
                      int splits, cudaStream_t stream, int64_t *launches) {
     if (args.M <= 0 || args.N <= 0) return OPL_OK;
-    if (args.K % TF32_BK || args.N % 32 || args.ldc % 4)
-        return fail(OPL_E_ARG, "tf32 GEMM needs K %% 32 == 0, N %% 32 == 0 (padded layer widths)");
+    // K may be ragged only for the TN layout (K = patterns): TMA zero-fills rows beyond the tensor
+    if ((layout != 2 && args.K % TF32_BK) || args.k_per_split % TF32_BK || args.N % 32 || args.ldc % 4)
+        return fail(OPL_E_ARG, "tf32 GEMM needs N %% 32 == 0 and K %% 32 == 0 (padded layer widths)");
     const int bn = args.N >= 128 ? 128 : (args.N >= 64 ? 64 : 32);
     const bool a_mn = layout == 2, b_mn = layout != 1;
     CUtensorMap ta, tb;

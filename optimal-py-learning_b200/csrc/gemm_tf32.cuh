@@ -43,6 +43,7 @@ struct Tf32GemmArgs {
     int64_t ldaux;
     int epi;
     float tparam;
+    int round_out;           // store C rounded to TF32 (it is the operand of a later GEMM)
 };
 
 constexpr int TF32_BM = 128;

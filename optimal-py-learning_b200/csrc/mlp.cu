@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "gemm_f64.cuh"
+#include "gemm_tf32.cuh"
 
 namespace opl {
 
@@ -56,13 +57,17 @@ __device__ __forceinline__ double transfer_slope(int tid, double tparam, double 
     }
 }
 
-struct RowArgs {
-    const double *Z;   // rows x C pre-activations
-    const double *Y;   // rows x C targets, or null (activate only)
-    const double *G;   // rows x C explicit upstream gradient instead of an error function, or null
-    double *A;         // rows x C activations out, or null (may alias Z)
-    double *D;         // rows x C delta out, or null
+// T = storage type of the activation-side matrices: double (parity mode) or float (fast mode; values that
+// feed a TF32 GEMM are stored pre-rounded to TF32 so the tensor core's truncation is exact).
+template <typename T>
+struct RowArgsT {
+    const T *Z;        // rows x C pre-activations, row stride ld
+    const double *Y;   // rows x C targets (dense, stride C), or null (activate only)
+    const T *G;        // explicit upstream gradient instead of an error function, or null (stride ld)
+    T *A;              // activations out, or null (may alias Z) (stride ld)
+    T *D;              // delta out, or null (stride ld)
     int64_t rows;
+    int64_t ld;
     int C;
     int tid;           // output transfer
     double tparam;
@@ -73,9 +78,14 @@ struct RowArgs {
     int *flag;         // set to 1 on log(negative)
     int group;
 };
+using RowArgs = RowArgsT<double>;
+
+__device__ __forceinline__ void store_operand(double *p, double v) { *p = v; }
+__device__ __forceinline__ void store_operand(float *p, double v) { *p = round_tf32((float)v); }
 
 // error term for one output element: returns the upstream gradient, adds to `loss`
-__device__ __forceinline__ double error_term(const RowArgs &r, double a, double y, double &loss, bool &bad) {
+template <typename T>
+__device__ __forceinline__ double error_term(const RowArgsT<T> &r, double a, double y, double &loss, bool &bad) {
     if (r.eid == OPL_ERROR_MSE) {   // error.py:58-64
         double d = a - y;
         loss += d * d;
@@ -87,7 +97,8 @@ __device__ __forceinline__ double error_term(const RowArgs &r, double a, double 
     return nan_to_num(y / a) / r.ce_div;
 }
 
-__global__ void __launch_bounds__(256) output_rows_kernel(const RowArgs r) {
+template <typename T>
+__global__ void __launch_bounds__(256) output_rows_kernel(const RowArgsT<T> r) {
     __shared__ double scratch[33];
     const int group = r.group;
     const int gl = threadIdx.x & (group - 1);
@@ -100,29 +111,29 @@ __global__ void __launch_bounds__(256) output_rows_kernel(const RowArgs r) {
     for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
         const int64_t row = blk * rows_per_block + slot;
         const bool live = row < r.rows;
-        const double *z = r.Z + (live ? row : 0) * (int64_t)r.C;
+        const T *z = r.Z + (live ? row : 0) * r.ld;
         const double *y = r.Y ? r.Y + (live ? row : 0) * (int64_t)r.C : nullptr;
         double mx = -INFINITY, den = 1.0;
         if (softmax) {   // calculate.py:152-153
             if (live)
-                for (int c = gl; c < r.C; c += group) mx = fmax(mx, z[c]);
+                for (int c = gl; c < r.C; c += group) mx = fmax(mx, (double)z[c]);
             mx = group_max(mx, group);
             double s = 0.0;
             if (live)
-                for (int c = gl; c < r.C; c += group) s += exp(z[c] - mx);
+                for (int c = gl; c < r.C; c += group) s += exp((double)z[c] - mx);
             den = group_sum(s, group);
         }
         double t = 0.0;
         if (live) {
             for (int c = gl; c < r.C; c += group) {
-                const double zc = z[c];
+                const double zc = (double)z[c];
                 const double a = softmax ? exp(zc - mx) / den : transfer_value(r.tid, r.tparam, zc);
                 if (y || r.G) {
-                    const double g = r.G ? r.G[row * r.C + c] : error_term(r, a, y[c], loss, bad);
+                    const double g = r.G ? (double)r.G[row * r.ld + c] : error_term(r, a, y[c], loss, bad);
                     if (softmax) t += g * a;
-                    else if (r.D) r.D[row * r.C + c] = g * transfer_slope(r.tid, r.tparam, zc, a);
+                    else if (r.D) store_operand(&r.D[row * r.ld + c], g * transfer_slope(r.tid, r.tparam, zc, a));
                 }
-                if (r.A && !(softmax && r.D && r.A == r.Z)) r.A[row * r.C + c] = a;
+                if (r.A && !(softmax && r.D && r.A == r.Z)) store_operand(&r.A[row * r.ld + c], a);
             }
         }
         if (softmax && r.D && (y || r.G)) {   // delta_k = a_k (g_k - sum_j g_j a_j): dsoftmax contracted (mlp.py:295)
@@ -131,10 +142,10 @@ __global__ void __launch_bounds__(256) output_rows_kernel(const RowArgs r) {
                 double dummy = 0.0;
                 bool dummy_bad = false;
                 for (int c = gl; c < r.C; c += group) {
-                    const double a = exp(z[c] - mx) / den;
-                    const double g = r.G ? r.G[row * r.C + c] : error_term(r, a, y[c], dummy, dummy_bad);
-                    r.D[row * r.C + c] = a * (g - t);
-                    if (r.A && r.A == r.Z) r.A[row * r.C + c] = a;
+                    const double a = exp((double)z[c] - mx) / den;
+                    const double g = r.G ? (double)r.G[row * r.ld + c] : error_term(r, a, y[c], dummy, dummy_bad);
+                    store_operand(&r.D[row * r.ld + c], a * (g - t));
+                    if (r.A && r.A == r.Z) store_operand(&r.A[row * r.ld + c], a);
                 }
             }
         }
@@ -149,18 +160,18 @@ __global__ void __launch_bounds__(256) output_rows_kernel(const RowArgs r) {
 // Same stage for narrow outputs (C <= MAXC): one thread owns a whole pattern in registers -- no
 // shuffles, no re-reads, every transcendental evaluated once.  Classification heads (3..32
 // classes) take this path.
-template <int MAXC>
-__global__ void __launch_bounds__(256) output_rows_thread_kernel(const RowArgs r) {
+template <int MAXC, typename T>
+__global__ void __launch_bounds__(256) output_rows_thread_kernel(const RowArgsT<T> r) {
     __shared__ double scratch[33];
     const bool softmax = r.tid == OPL_TRANSFER_SOFTMAX;
     double loss = 0.0;
     bool bad = false;
     for (int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; row < r.rows;
          row += (int64_t)gridDim.x * blockDim.x) {
-        const double *zp = r.Z + row * r.C;
+        const T *zp = r.Z + row * r.ld;
         double z[MAXC], a[MAXC];
 #pragma unroll
-        for (int c = 0; c < MAXC; ++c) z[c] = c < r.C ? zp[c] : -INFINITY;
+        for (int c = 0; c < MAXC; ++c) z[c] = c < r.C ? (double)zp[c] : -INFINITY;
         if (softmax) {
             double mx = -INFINITY, den = 0.0;
 #pragma unroll
@@ -179,7 +190,7 @@ __global__ void __launch_bounds__(256) output_rows_thread_kernel(const RowArgs r
         if (r.A) {
 #pragma unroll
             for (int c = 0; c < MAXC; ++c)
-                if (c < r.C) r.A[row * r.C + c] = a[c];
+                if (c < r.C) store_operand(&r.A[row * r.ld + c], a[c]);
         }
         if (r.Y || r.G) {
             double g[MAXC], t = 0.0;
@@ -187,7 +198,7 @@ __global__ void __launch_bounds__(256) output_rows_thread_kernel(const RowArgs r
             for (int c = 0; c < MAXC; ++c) {
                 g[c] = 0.0;
                 if (c < r.C) {
-                    g[c] = r.G ? r.G[row * r.C + c] : error_term(r, a[c], r.Y[row * r.C + c], loss, bad);
+                    g[c] = r.G ? (double)r.G[row * r.ld + c] : error_term(r, a[c], r.Y[row * r.C + c], loss, bad);
                     t += g[c] * a[c];
                 }
             }
@@ -195,8 +206,8 @@ __global__ void __launch_bounds__(256) output_rows_thread_kernel(const RowArgs r
 #pragma unroll
                 for (int c = 0; c < MAXC; ++c)
                     if (c < r.C)
-                        r.D[row * r.C + c] = softmax ? a[c] * (g[c] - t)
-                                                     : g[c] * transfer_slope(r.tid, r.tparam, z[c], a[c]);
+                        store_operand(&r.D[row * r.ld + c], softmax ? a[c] * (g[c] - t)
+                                                                     : g[c] * transfer_slope(r.tid, r.tparam, z[c], a[c]));
             }
         }
     }
@@ -208,8 +219,9 @@ __global__ void __launch_bounds__(256) output_rows_thread_kernel(const RowArgs r
 }
 
 // hidden softmax layer backward: delta = a o (g - sum g a), in place over g
+template <typename T>
 __global__ void __launch_bounds__(256)
-softmax_backward_rows_kernel(double *G, const double *A, int64_t rows, int C, int group) {
+softmax_backward_rows_kernel(T *G, const T *A, int64_t rows, int64_t ld, int C, int group) {
     const int gl = threadIdx.x & (group - 1);
     const int rows_per_block = blockDim.x / group;
     const int slot = threadIdx.x / group;
@@ -219,10 +231,11 @@ softmax_backward_rows_kernel(double *G, const double *A, int64_t rows, int C, in
         const bool live = row < rows;
         double t = 0.0;
         if (live)
-            for (int c = gl; c < C; c += group) t += G[row * C + c] * A[row * C + c];
+            for (int c = gl; c < C; c += group) t += (double)G[row * ld + c] * (double)A[row * ld + c];
         t = group_sum(t, group);
         if (live)
-            for (int c = gl; c < C; c += group) G[row * C + c] = A[row * C + c] * (G[row * C + c] - t);
+            for (int c = gl; c < C; c += group)
+                store_operand(&G[row * ld + c], (double)A[row * ld + c] * ((double)G[row * ld + c] - t));
     }
 }
 
@@ -314,10 +327,13 @@ __global__ void softmax_jacobian_kernel(const double *__restrict__ y, int64_t ro
 
 using namespace opl;
 
+struct FastState;   // fast-mode (TF32) buffers, mlp_fast.inl
+
 // ---------------------------------------------------------------------------------------
 // workspace
 // ---------------------------------------------------------------------------------------
 struct opl_mlp {
+    FastState *fast = nullptr;
     int layers = 0;                    // weight matrices
     std::vector<int64_t> width;        // layers + 1
     std::vector<int> transfer;
@@ -392,21 +408,26 @@ int row_grid(int64_t rows, int group) {
 
 // pick the row kernel: thread-per-row for narrow outputs unless it works in place (hidden softmax)
 // returns the grid size used (== number of loss partials written)
-int launch_rows(const RowArgs &r, int max_grid, cudaStream_t stream) {
+template <typename T>
+int launch_rows(const RowArgsT<T> &r, int max_grid, cudaStream_t stream) {
     if (r.C <= kThreadRowMaxC && r.A != r.Z) {
         int64_t grid = ceil_div(r.rows, 256);
         if (grid > max_grid) grid = max_grid;
         if (grid < 1) grid = 1;
-        output_rows_thread_kernel<kThreadRowMaxC><<<(unsigned)grid, 256, 0, stream>>>(r);
+        output_rows_thread_kernel<kThreadRowMaxC, T><<<(unsigned)grid, 256, 0, stream>>>(r);
         return (int)grid;
     }
     int grid = row_grid(r.rows, r.group);
     if (grid > max_grid) grid = max_grid;
-    output_rows_kernel<<<grid, 256, 0, stream>>>(r);
+    output_rows_kernel<T><<<grid, 256, 0, stream>>>(r);
     return grid;
 }
 
+void fast_free(FastState *f);
+
 int free_all(opl_mlp *ws) {
+    fast_free(ws->fast);
+    ws->fast = nullptr;
     cudaFree(ws->x_own);
     cudaFree(ws->y_own);
     cudaFree(ws->x_scratch);
@@ -469,8 +490,9 @@ int forward(opl_mlp *ws, const double *w, const double *x, int64_t rows, bool ke
             r.C = a.N;
             r.tid = OPL_TRANSFER_SOFTMAX;
             r.flag = ws->flag;
+            r.ld = r.C;
             r.group = row_group(r.C);
-            output_rows_kernel<<<row_grid(rows, r.group), 256, 0, ws->stream>>>(r);
+            output_rows_kernel<double><<<row_grid(rows, r.group), 256, 0, ws->stream>>>(r);
             OPL_LAUNCH_CHECK();
             ++ws->launches;
         }
@@ -488,6 +510,7 @@ int output_stage(opl_mlp *ws, const double *y, int64_t rows, bool want_act, bool
     r.D = want_delta ? ws->delta[L - 1] : nullptr;
     r.rows = rows;
     r.C = (int)ws->width[L];
+    r.ld = r.C;
     r.tid = ws->transfer[L - 1];
     r.tparam = ws->tparam[L - 1];
     r.eid = ws->error_id;
@@ -584,14 +607,20 @@ int backward(opl_mlp *ws, const double *w, const double *x, int64_t rows, double
         if (ws->transfer[l - 1] == OPL_TRANSFER_SOFTMAX) {
             mark(ws, STAGE_ROWS * 100 + l - 1);
             const int group = row_group(din);
-            softmax_backward_rows_kernel<<<row_grid(rows, group), 256, 0, ws->stream>>>(ws->delta[l - 1], ws->act[l],
-                                                                                       rows, din, group);
+            softmax_backward_rows_kernel<double><<<row_grid(rows, group), 256, 0, ws->stream>>>(
+                ws->delta[l - 1], ws->act[l], rows, din, din, group);
             OPL_LAUNCH_CHECK();
             ++ws->launches;
         }
     }
     return OPL_OK;
 }
+
+}  // namespace
+
+#include "mlp_fast.inl"
+
+namespace {
 
 int evaluate(opl_mlp *ws, const double *x_dev, double alpha, const double *dir_dev, bool want_grad,
              double *grad_out_dev) {
@@ -602,7 +631,13 @@ int evaluate(opl_mlp *ws, const double *x_dev, double alpha, const double *dir_d
     trial_point_kernel<<<tgrid, 256, 0, ws->stream>>>(n, x_dev, alpha, dir_dev, ws->w_trial, ws->flag);
     OPL_LAUNCH_CHECK();
     ++ws->launches;
-    int rc = forward(ws, ws->w_trial, ws->x, ws->rows, want_grad);
+    int rc;
+    if (ws->precision == OPL_PRECISION_TF32) {
+        rc = fast_evaluate(ws, want_grad, grad_out_dev);
+        mark(ws, STAGE_END * 100);
+        return rc;
+    }
+    rc = forward(ws, ws->w_trial, ws->x, ws->rows, want_grad);
     if (rc != OPL_OK) return rc;
     rc = output_stage(ws, ws->y, ws->rows, false, want_grad, grad_out_dev + n);
     if (rc != OPL_OK) return rc;
@@ -643,8 +678,8 @@ int opl_mlp_create(opl_mlp **out, int32_t n_widths, const int64_t *widths, const
     if (!out || !widths || !transfer_ids || n_widths < 2) return fail(OPL_E_ARG, "opl_mlp_create: bad arguments");
     if (error_id != OPL_ERROR_MSE && error_id != OPL_ERROR_CROSS_ENTROPY)
         return fail(OPL_E_ARG, "opl_mlp_create: unknown error id %d", error_id);
-    if (precision != OPL_PRECISION_F64)
-        return fail(OPL_E_ARG, "opl_mlp_create: precision %d not available in this build", precision);
+    if (precision != OPL_PRECISION_F64 && precision != OPL_PRECISION_TF32)
+        return fail(OPL_E_ARG, "opl_mlp_create: unknown precision %d", precision);
     if (max_rows < 1) return fail(OPL_E_ARG, "opl_mlp_create: max_rows must be >= 1");
     for (int i = 0; i < n_widths; ++i)
         if (widths[i] < 1 || widths[i] > (1 << 24)) return fail(OPL_E_ARG, "opl_mlp_create: bad width");
@@ -687,7 +722,7 @@ int opl_mlp_create(opl_mlp **out, int32_t n_widths, const int64_t *widths, const
             return fail(OPL_E_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
         }                             \
     } while (0)
-    for (int l = 0; l < L; ++l) {
+    for (int l = 0; l < L && precision == OPL_PRECISION_F64; ++l) {
         const size_t bytes = sizeof(double) * (size_t)max_rows * (size_t)widths[l + 1];
         OPL_TRY(cudaMalloc(&ws->act[l + 1], bytes));
         const int t = ws->transfer[l];
@@ -715,6 +750,14 @@ int opl_mlp_create(opl_mlp **out, int32_t n_widths, const int64_t *widths, const
     OPL_TRY(cudaMemset(ws->flag, 0, sizeof(int)));
     OPL_TRY(cudaMallocHost(&ws->pinned, sizeof(double) * 8));
 #undef OPL_TRY
+    if (precision == OPL_PRECISION_TF32) {
+        int rc = fast_create(ws);
+        if (rc != OPL_OK) {
+            free_all(ws);
+            delete ws;
+            return rc;
+        }
+    }
     *out = ws;
     return OPL_OK;
 }
@@ -768,6 +811,7 @@ int opl_mlp_set_data_host(opl_mlp *ws, const double *x, const double *y, int64_t
     ws->y = ws->y_own;
     ws->rows = rows;
     ws->norm_rows = norm_rows > 0 ? norm_rows : rows;
+    if (ws->precision == OPL_PRECISION_TF32) return fast_set_x(ws);
     return OPL_OK;
 }
 
@@ -778,6 +822,7 @@ int opl_mlp_set_data_device(opl_mlp *ws, const double *x_dev, const double *y_de
     ws->y = y_dev;
     ws->rows = rows;
     ws->norm_rows = norm_rows > 0 ? norm_rows : rows;
+    if (ws->precision == OPL_PRECISION_TF32) return fast_set_x(ws);
     return OPL_OK;
 }
 
@@ -824,6 +869,7 @@ int opl_mlp_obj_jac_host(opl_mlp *ws, const double *params, double *obj_out, dou
 int opl_mlp_activate_device(opl_mlp *ws, const double *params_dev, const double *x_dev, int64_t rows, double *out_dev) {
     if (!ws || !params_dev || !x_dev || !out_dev) return fail(OPL_E_ARG, "opl_mlp_activate_device: null pointer");
     if (rows < 1 || rows > ws->max_rows) return fail(OPL_E_ARG, "opl_mlp_activate_device: rows out of range");
+    if (ws->precision == OPL_PRECISION_TF32) return fast_activate(ws, params_dev, x_dev, rows, out_dev);
     int rc = forward(ws, params_dev, x_dev, rows, false);
     if (rc != OPL_OK) return rc;
     rc = output_stage(ws, nullptr, rows, true, false, nullptr);
@@ -841,9 +887,13 @@ int opl_mlp_activate_host(opl_mlp *ws, const double *params, const double *x, in
     if (!ws->x_scratch) OPL_CUDA(cudaMalloc(&ws->x_scratch, sizeof(double) * (size_t)ws->max_rows * (size_t)d0));
     OPL_CUDA(cudaMemcpyAsync(ws->w_trial, params, sizeof(double) * (size_t)ws->n, cudaMemcpyHostToDevice, ws->stream));
     OPL_CUDA(cudaMemcpyAsync(ws->x_scratch, x, sizeof(double) * (size_t)rows * (size_t)d0, cudaMemcpyHostToDevice, ws->stream));
-    int rc = forward(ws, ws->w_trial, ws->x_scratch, rows, false);
-    if (rc != OPL_OK) return rc;
-    rc = output_stage(ws, nullptr, rows, true, false, nullptr);
+    int rc;
+    if (ws->precision == OPL_PRECISION_TF32) {
+        rc = fast_activate(ws, ws->w_trial, ws->x_scratch, rows, ws->out_act);
+    } else {
+        rc = forward(ws, ws->w_trial, ws->x_scratch, rows, false);
+        if (rc == OPL_OK) rc = output_stage(ws, nullptr, rows, true, false, nullptr);
+    }
     if (rc != OPL_OK) return rc;
     OPL_CUDA(cudaMemcpyAsync(out, ws->out_act, sizeof(double) * (size_t)rows * (size_t)dl, cudaMemcpyDeviceToHost, ws->stream));
     OPL_CUDA(cudaStreamSynchronize(ws->stream));
@@ -897,6 +947,7 @@ int rows_call(int tid, double tparam, int eid, const double *z_host, const doubl
     r.D = d;
     r.rows = rows;
     r.C = (int)cols;
+    r.ld = cols;
     r.tid = tid;
     r.tparam = tparam;
     r.eid = eid;

@@ -15,6 +15,7 @@ come back per evaluation.
 import ctypes
 import functools
 import operator
+import os
 
 import numpy
 import torch
@@ -50,13 +51,13 @@ def _unflatten_weights(flat_weights, shape):
 class _Workspace(object):
     """One opl_mlp handle plus the identity of the data currently resident in it."""
 
-    def __init__(self, shape, transfers, error_id, max_rows):
+    def __init__(self, shape, transfers, error_id, max_rows, precision=0):
         widths = (ctypes.c_int64 * len(shape))(*[int(w) for w in shape])
         tids = (ctypes.c_int32 * len(transfers))(*[t for t, _ in transfers])
         tparams = (ctypes.c_double * len(transfers))(*[p for _, p in transfers])
         out = ctypes.c_void_p()
         nat.check(nat.lib.opl_mlp_create(ctypes.byref(out), len(shape), widths, tids, tparams, error_id,
-                                         int(max_rows), 0, dev.stream_ptr()))
+                                         int(max_rows), int(precision), dev.stream_ptr()))
         self.pointer = out
         self.max_rows = int(max_rows)
         self.resident = None      # fingerprint of the (X, Y) resident on the device
@@ -92,10 +93,21 @@ class MLP(Model):
             (default: BFGS up to 500 weights, else L-BFGS; bias excluded from the count).
         error_func: ErrorFunc (default MeanSquaredError).
         jacobian_norm_break: Training ends when the gradient norm falls below this value.
+        precision: the one knob this build adds.  'f64' (default): FP64 DMMA kernels, objective and
+            gradient match the reference to 1e-10.  'tf32': tcgen05 TF32 tensor-core GEMMs with FP32
+            accumulation (1e-3).  Defaults to the OPL_PRECISION environment variable.
     """
 
-    def __init__(self, shape, transfers=None, optimizer=None, error_func=None, jacobian_norm_break=1e-10):
+    PRECISIONS = {'f64': 0, 'tf32': 1}
+
+    def __init__(self, shape, transfers=None, optimizer=None, error_func=None, jacobian_norm_break=1e-10,
+                 precision=None):
         super(MLP, self).__init__()
+        if precision is None:
+            precision = os.environ.get('OPL_PRECISION', 'f64')
+        if precision not in self.PRECISIONS:
+            raise ValueError("precision must be 'f64' or 'tf32', got %r" % (precision,))
+        self._precision = precision
         hidden = len(shape) - 2
         if transfers is None:
             transfers = [ReluTransfer() for _ in range(hidden)] + [LinearTransfer()]
@@ -146,7 +158,8 @@ class MLP(Model):
     def _workspace_for(self, rows):
         ws = self._workspace
         if ws is None or ws.max_rows < rows:
-            ws = _Workspace(self._shape, self._lowered_transfers, self._lowered_error, rows)
+            ws = _Workspace(self._shape, self._lowered_transfers, self._lowered_error, rows,
+                            self.PRECISIONS[self._precision])
             self._workspace = ws
         return ws
 

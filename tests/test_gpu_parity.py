@@ -532,3 +532,69 @@ def test_mlp_training_reduces_error(L):
         before = L.validation.get_error(model, xor_x, xor_y)
         model.train(xor_x, xor_y, iterations=20)
         assert L.validation.get_error(model, xor_x, xor_y) < before
+
+
+# ----------------------------------------------------------------------------------------
+# fast mode: tcgen05 TF32 tensor cores + TMA, FP32 accumulate -- gate 1e-3 relative (north_star)
+# ----------------------------------------------------------------------------------------
+FAST_TOL = 1e-3        # BASELINE-sized layers: TF32 operand rounding (2^-11) averages out over the contraction
+FAST_TOL_TINY = 5e-3   # toy golden cases (contraction lengths 1..10): no averaging, bound = a few operand roundings
+
+
+def _fast_model(L, shape, transfers, eid):
+    return L.MLP(shape, transfers=make_transfers(L, transfers), error_func=make_error(L, eid),
+                 optimizer=L.optimize.SteepestDescent(), precision='tf32')
+
+
+def test_fast_mode_golden_cases(L, golden_meta, golden_objgrad):
+    g = golden_objgrad
+    for entry in golden_meta["objgrad"]:
+        if entry["name"] in ("overflow", "underflow_some_rows", "big_softplus_lin"):
+            continue   # FP32 range: the +-1e308 / 4000-scaled edge cases belong to the FP64 parity mode
+        k = entry["key"]
+        shape, transfers, eid = specs(entry)
+        model = _fast_model(L, shape, transfers, eid)
+        obj, grad = model._get_obj_jac(g[k + "_w"].copy(), g[k + "_x"], g[k + "_y"])
+        tol = FAST_TOL if min(shape) >= 32 else FAST_TOL_TINY
+        assert rel_err(obj, g[k + "_obj"]) <= tol, (entry["name"], rel_err(obj, g[k + "_obj"]))
+        assert rel_err(grad, g[k + "_grad"]) <= tol, (entry["name"], rel_err(grad, g[k + "_grad"]))
+        assert rel_err(model._get_obj(g[k + "_w"].copy(), g[k + "_x"], g[k + "_y"]), g[k + "_obj"]) <= tol
+        assert rel_err(model.activate(g[k + "_x"]), g[k + "_out"]) <= tol, entry["name"]
+
+
+@pytest.mark.parametrize("shape,transfers,eid,rows", [
+    ((784, 256, 10), [(2, 0), (4, 0)], 1, 4000),
+    ((785, 255, 11), [(2, 0), (4, 0)], 1, 1531),
+    ((512, 128, 128, 10), [(2, 0), (2, 0), (4, 0)], 1, 2048),
+    ((256, 192, 160, 10), [(1, 0), (3, 1.5), (0, 0)], 0, 1000),
+    ((40, 70, 33, 65), [(4, 0), (2, 0), (2, 0)], 0, 517),
+])
+def test_fast_mode_against_oracle_at_size(L, shape, transfers, eid, rows):
+    rng = numpy.random.default_rng(hash(shape) % 1000 + 1)
+    gen = mo.random_classification if eid == 1 else mo.random_regression
+    x, y = gen(rows, shape[0], shape[-1], rng)
+    w = mo.random_params(shape, rng)
+    want_obj, want_grad = mo.objective_gradient(w, shape, transfers, eid, x, y, literal_softmax=False)
+    model = _fast_model(L, shape, transfers, eid)
+    obj, grad = model._get_obj_jac(w.copy(), x, y)
+    print("fast mode", shape, "obj rel", rel_err(obj, want_obj), "grad rel", rel_err(grad, want_grad))
+    assert rel_err(obj, want_obj) <= FAST_TOL
+    assert rel_err(grad, want_grad) <= FAST_TOL, rel_err(grad, want_grad)
+    obj2, grad2 = model._get_obj_jac(w.copy(), x, y)
+    assert obj2 == obj and numpy.array_equal(grad2, grad)      # deterministic
+
+
+def test_fast_mode_trains(L, golden_traces):
+    import random
+    t = golden_traces
+    random.seed(1)
+    numpy.random.seed(1)
+    model = L.MLP((4, 8, 3), transfers=L.SoftmaxTransfer(), error_func=L.CrossEntropyError(),
+                  optimizer=L.optimize.LBFGS(), precision='tf32')
+    model.logging = False
+    before = L.validation.get_error(model, t["iris_x"], t["iris_y"])
+    model.train(t["iris_x"], t["iris_y"], iterations=40)
+    assert L.validation.get_error(model, t["iris_x"], t["iris_y"]) < 0.5 * before
+    assert L.validation.get_accuracy(model, t["iris_test_x"], t["iris_test_y"]) >= 0.85
+    with pytest.raises(ValueError):
+        L.MLP((2, 2, 2), precision='fp8')

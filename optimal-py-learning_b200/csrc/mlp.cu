@@ -164,51 +164,44 @@ template <int MAXC, typename T>
 __global__ void __launch_bounds__(256) output_rows_thread_kernel(const RowArgsT<T> r) {
     __shared__ double scratch[33];
     const bool softmax = r.tid == OPL_TRANSFER_SOFTMAX;
+    const int C = r.C;
     double loss = 0.0;
     bool bad = false;
     for (int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; row < r.rows;
          row += (int64_t)gridDim.x * blockDim.x) {
         const T *zp = r.Z + row * r.ld;
-        double z[MAXC], a[MAXC];
-#pragma unroll
-        for (int c = 0; c < MAXC; ++c) z[c] = c < r.C ? (double)zp[c] : -INFINITY;
+        // Rolled loops on purpose (the unrolled version inlined 16 copies of exp/log/div and stalled on
+        // instruction fetch); the per-pattern values live in a small thread-local array.
+        double a[MAXC], g[MAXC];
+        double mx = -INFINITY, den = 0.0, t = 0.0;
         if (softmax) {
-            double mx = -INFINITY, den = 0.0;
-#pragma unroll
-            for (int c = 0; c < MAXC; ++c) mx = fmax(mx, z[c]);
-#pragma unroll
-            for (int c = 0; c < MAXC; ++c) {
-                a[c] = c < r.C ? exp(z[c] - mx) : 0.0;
+#pragma unroll 1
+            for (int c = 0; c < C; ++c) {
+                a[c] = (double)zp[c];
+                mx = fmax(mx, a[c]);
+            }
+#pragma unroll 1
+            for (int c = 0; c < C; ++c) {
+                a[c] = exp(a[c] - mx);
                 den += a[c];
             }
-#pragma unroll
-            for (int c = 0; c < MAXC; ++c) a[c] = a[c] / den;
-        } else {
-#pragma unroll
-            for (int c = 0; c < MAXC; ++c) a[c] = c < r.C ? transfer_value(r.tid, r.tparam, z[c]) : 0.0;
         }
-        if (r.A) {
-#pragma unroll
-            for (int c = 0; c < MAXC; ++c)
-                if (c < r.C) store_operand(&r.A[row * r.ld + c], a[c]);
+#pragma unroll 1
+        for (int c = 0; c < C; ++c) {
+            const double zc = (double)zp[c];
+            const double ac = softmax ? a[c] / den : transfer_value(r.tid, r.tparam, zc);
+            a[c] = ac;
+            if (r.A) store_operand(&r.A[row * r.ld + c], ac);
+            if (r.Y || r.G) {
+                const double gc = r.G ? (double)r.G[row * r.ld + c] : error_term(r, ac, r.Y[row * C + c], loss, bad);
+                g[c] = gc;
+                if (softmax) t += gc * ac;
+                else if (r.D) store_operand(&r.D[row * r.ld + c], gc * transfer_slope(r.tid, r.tparam, zc, ac));
+            }
         }
-        if (r.Y || r.G) {
-            double g[MAXC], t = 0.0;
-#pragma unroll
-            for (int c = 0; c < MAXC; ++c) {
-                g[c] = 0.0;
-                if (c < r.C) {
-                    g[c] = r.G ? (double)r.G[row * r.ld + c] : error_term(r, a[c], r.Y[row * r.C + c], loss, bad);
-                    t += g[c] * a[c];
-                }
-            }
-            if (r.D) {
-#pragma unroll
-                for (int c = 0; c < MAXC; ++c)
-                    if (c < r.C)
-                        store_operand(&r.D[row * r.ld + c], softmax ? a[c] * (g[c] - t)
-                                                                     : g[c] * transfer_slope(r.tid, r.tparam, z[c], a[c]));
-            }
+        if (softmax && r.D && (r.Y || r.G)) {
+#pragma unroll 1
+            for (int c = 0; c < C; ++c) store_operand(&r.D[row * r.ld + c], a[c] * (g[c] - t));
         }
     }
     if (bad) *r.flag = 1;
@@ -236,6 +229,51 @@ softmax_backward_rows_kernel(T *G, const T *A, int64_t rows, int64_t ld, int C, 
         if (live)
             for (int c = gl; c < C; c += group)
                 store_operand(&G[row * ld + c], (double)A[row * ld + c] * ((double)G[row * ld + c] - t));
+    }
+}
+
+// delta_prev[r][j] = (sum_c delta[r][c] * W[j][c]) * slope[r][j] for a NARROW next layer (C <= 16): the
+// "GEMM" has K = C, so it is pure streaming over the rows x H slope / output matrices.  One CTA takes a
+// block of rows; W (H x C) and the block's delta rows sit in shared memory; thread j walks the rows, so
+// global traffic is perfectly coalesced along j with 8 independent loads in flight per thread.
+// mode: 0 out = s, 1 out = s * aux (D = f'), 2 out = s * (1 - aux^2) (tanh from the activation)
+template <int MAXC>
+__global__ void __launch_bounds__(256) narrow_backprop_kernel(const double *__restrict__ delta, const double *__restrict__ W,
+                                                              const double *aux, double *out, int64_t rows, int H, int C,
+                                                              int rows_per_block, int mode) {
+    extern __shared__ double sm[];
+    double *Ws = sm;                       // H x (C|1): odd stride => conflict-free across j
+    const int cp = C | 1;
+    double *Ds = sm + (size_t)H * cp;      // rows_per_block x C
+    for (int i = threadIdx.x; i < H * C; i += blockDim.x) Ws[(i / C) * cp + (i % C)] = W[i];
+    // persistent CTAs over small row blocks: W is staged once per CTA and the tail is a few rows, not a wave
+    const int64_t nblocks = (rows + rows_per_block - 1) / rows_per_block;
+    for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        const int64_t r0 = blk * rows_per_block;
+        const int nr = (int)min((int64_t)rows_per_block, rows - r0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nr * C; i += blockDim.x) Ds[i] = delta[r0 * C + i];
+        __syncthreads();
+        for (int j = threadIdx.x; j < H; j += blockDim.x) {
+            double w[MAXC];
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c) w[c] = c < C ? Ws[j * cp + c] : 0.0;
+            for (int rb = 0; rb < nr; rb += 8) {
+                double x[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) x[u] = (mode != 0 && rb + u < nr) ? aux[(r0 + rb + u) * H + j] : 1.0;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (rb + u < nr) {
+                        double s_ = 0.0;
+#pragma unroll
+                        for (int c = 0; c < MAXC; ++c)
+                            if (c < C) s_ += Ds[(rb + u) * C + c] * w[c];
+                        out[(r0 + rb + u) * H + j] = mode == 2 ? s_ * (1.0 - x[u] * x[u]) : s_ * x[u];
+                    }
+                }
+            }
+        }
     }
 }
 
@@ -411,10 +449,10 @@ int row_grid(int64_t rows, int group) {
 template <typename T>
 int launch_rows(const RowArgsT<T> &r, int max_grid, cudaStream_t stream) {
     if (r.C <= kThreadRowMaxC && r.A != r.Z) {
-        int64_t grid = ceil_div(r.rows, 256);
+        int64_t grid = ceil_div(r.rows, 128);
         if (grid > max_grid) grid = max_grid;
         if (grid < 1) grid = 1;
-        output_rows_thread_kernel<kThreadRowMaxC, T><<<(unsigned)grid, 256, 0, stream>>>(r);
+        output_rows_thread_kernel<kThreadRowMaxC, T><<<(unsigned)grid, 128, 0, stream>>>(r);
         return (int)grid;
     }
     int grid = row_grid(r.rows, r.group);
@@ -576,6 +614,22 @@ int backward(opl_mlp *ws, const double *w, const double *x, int64_t rows, double
         }
         if (l == 0) break;
         // delta_{l-1} = (delta_l W_l^T) o f'_{l-1}   (mlp.py:254-260)
+        if (dout <= 16 && ws->transfer[l - 1] != OPL_TRANSFER_SOFTMAX &&
+            sizeof(double) * ((size_t)din * (dout | 1) + (size_t)64 * dout) <= 48 * 1024) {
+            // narrow next layer: K = dout <= 16 makes this a streaming pass, not a GEMM
+            const int t = ws->transfer[l - 1];
+            const int mode = (t == OPL_TRANSFER_SOFTPLUS || t == OPL_TRANSFER_GAUSSIAN) ? 1 : (t == OPL_TRANSFER_TANH ? 2 : 0);
+            const double *aux = mode == 1 ? ws->deriv[l - 1] : (mode == 2 ? ws->act[l] : nullptr);
+            const int rpb = 16;
+            const size_t smem = sizeof(double) * ((size_t)din * (dout | 1) + (size_t)rpb * dout);
+            const int64_t grid = std::min<int64_t>(ceil_div(rows, rpb), 6 * (int64_t)sm_count());
+            mark(ws, STAGE_DA * 100 + l);
+            narrow_backprop_kernel<16><<<(unsigned)grid, 256, smem, ws->stream>>>(
+                ws->delta[l], w + ws->w_off[l], aux, ws->delta[l - 1], rows, din, dout, rpb, mode);
+            OPL_LAUNCH_CHECK();
+            ++ws->launches;
+            continue;
+        }
         GemmArgs a = {};
         a.A = ws->delta[l];
         a.lda = dout;

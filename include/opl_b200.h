@@ -41,6 +41,8 @@ extern "C" {
 #define OPL_TRANSFER_SOFTPLUS 2   /* the reference's "ReluTransfer" is softplus */
 #define OPL_TRANSFER_GAUSSIAN 3   /* param = variance */
 #define OPL_TRANSFER_SOFTMAX  4
+#define OPL_TRANSFER_LOGIT    5   /* output layers only: calculate.logit / dlogit (calculate.py:65-88),
+                                     the equation of LogisticRegressionModel (regression.py:255-290) */
 
 /* error ids: error.py:46-116 */
 #define OPL_ERROR_MSE            0
@@ -102,6 +104,12 @@ int opl_mlp_probe_scalars(opl_mlp *ws, const double *grad_dev, const double *dir
 /* activate on device buffers: x_dev rows x d0 -> out_dev rows x d_L */
 int opl_mlp_activate_device(opl_mlp *ws, const double *params_dev, const double *x_dev, int64_t rows,
                             double *out_dev);
+/* DropoutMLP (mlp.py:330-445): 0/1 vectors of active neurons for one train_step, concatenated as
+ * [input mask (d0) ; hidden mask 1 (d1) ; ... ; hidden mask L-1 (d_{L-1})] (no mask on the output
+ * layer).  NULL clears them.  The input mask is folded into W0's rows (and dW0's), the hidden masks
+ * multiply the transfer outputs in the forward epilogue; derivatives are NOT masked (mlp.py:438-445).
+ * Parity mode only. */
+int opl_mlp_set_masks_host(opl_mlp *ws, const double *masks, int64_t len);
 /* number of kernels this workspace has launched since creation (bench.py gpu_launches) */
 int64_t opl_mlp_launch_count(const opl_mlp *ws);
 /* Per-launch device timing for the roofline report: while enabled, a CUDA event is recorded on
@@ -218,6 +226,12 @@ int opl_vec_axpy_device(int64_t n, const double *x, double a, const double *d, d
                         const double *p, double *out, void *cuda_stream);
 /* out = a * x */
 int opl_vec_scale_device(int64_t n, double a, const double *x, double *out, void *cuda_stream);
+/* Weight penalties of RegressionModel (error.py:122-193, regression.py:158-180):
+ *   kind 1: L1Penalty  value = lambda * sum|w|,     grad += lambda * sign(w)
+ *   kind 2: L2Penalty  value = lambda * ||w||_2,    grad += lambda * w / ||w||_2
+ * grad_inout may be NULL (objective only).  host_out[0] = penalty value; synchronises. */
+int opl_vec_penalty_device(int64_t n, const double *w, int32_t kind, double lambda, double *grad_inout,
+                           double *host_out, void *cuda_stream);
 /* host_out[0] = x . y   (deterministic two-stage reduction; synchronises) */
 int opl_vec_dot_device(int64_t n, const double *x, const double *y, double *host_out, void *cuda_stream);
 

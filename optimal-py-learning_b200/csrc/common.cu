@@ -71,6 +71,33 @@ __global__ void dot_final_kernel(int nparts, const double *__restrict__ partial,
     if (threadIdx.x == 0) out[0] = s;
 }
 
+// stage 1 of the penalty norms: sum|w| (kind 1) or sum w^2 (kind 2)
+__global__ void penalty_partial_kernel(int64_t n, const double *__restrict__ w, int kind, double *__restrict__ partial) {
+    __shared__ double scratch[33];
+    double s = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        s += kind == 1 ? fabs(w[i]) : w[i] * w[i];
+    s = block_sum(s, scratch);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+// every block folds the partials identically, then adds its slice of the penalty gradient
+__global__ void penalty_apply_kernel(int64_t n, const double *__restrict__ w, int kind, double lambda, int nparts,
+                                     const double *__restrict__ partial, double *grad, double *value_out) {
+    __shared__ double scratch[33];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nparts; i += blockDim.x) s += partial[i];
+    s = block_sum(s, scratch);
+    const double norm = kind == 1 ? s : sqrt(s);
+    if (blockIdx.x == 0 && threadIdx.x == 0) value_out[0] = lambda * norm;
+    if (!grad) return;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double wi = w[i];
+        const double d = kind == 1 ? (wi > 0.0 ? 1.0 : (wi < 0.0 ? -1.0 : 0.0)) : wi / norm;   // numpy.sign / w / ||w||
+        grad[i] += lambda * d;
+    }
+}
+
 static int vec_grid(int64_t n, int threads) {
     int64_t g = ceil_div(n, threads);
     int64_t cap = 4 * (int64_t)sm_count();
@@ -111,6 +138,23 @@ int opl_vec_scale_device(int64_t n, double a, const double *x, double *out, void
     if (n < 0 || (n > 0 && (!x || !out))) return fail(OPL_E_ARG, "opl_vec_scale_device: null pointer");
     if (n == 0) return OPL_OK;
     scale_kernel<<<vec_grid(n, 256), 256, 0, (cudaStream_t)cuda_stream>>>(n, a, x, out);
+    OPL_LAUNCH_CHECK();
+    return OPL_OK;
+}
+
+int opl_vec_penalty_device(int64_t n, const double *w, int32_t kind, double lambda, double *grad_inout,
+                           double *host_out, void *cuda_stream) {
+    if (n < 1 || !w || !host_out || (kind != 1 && kind != 2)) return fail(OPL_E_ARG, "opl_vec_penalty_device: bad arguments");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int blocks = vec_grid(n, 256);
+    double *scratch = nullptr;
+    OPL_CUDA(cudaMallocAsync(&scratch, sizeof(double) * (blocks + 1), st));
+    penalty_partial_kernel<<<blocks, 256, 0, st>>>(n, w, kind, scratch);
+    penalty_apply_kernel<<<blocks, 256, 0, st>>>(n, w, kind, lambda, blocks, scratch, grad_inout, scratch + blocks);
+    cudaError_t e = cudaMemcpyAsync(host_out, scratch + blocks, sizeof(double), cudaMemcpyDeviceToHost, st);
+    cudaFreeAsync(scratch, st);
+    if (e != cudaSuccess) return fail(OPL_E_CUDA, "penalty readback: %s", cudaGetErrorString(e));
+    OPL_CUDA(cudaStreamSynchronize(st));
     OPL_LAUNCH_CHECK();
     return OPL_OK;
 }

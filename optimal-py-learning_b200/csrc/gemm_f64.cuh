@@ -45,6 +45,9 @@ struct GemmArgs {
     // TN only: CTAs of the first M-tile also accumulate the column sums of their B tiles
     // (db = 1^T delta_0, mlp.py:276) into colsum_out[split * split_stride + col]
     double *colsum_out;
+    // forward only: DropoutTransfer (mlp.py:429-445) multiplies the transfer OUTPUT by a 0/1 vector of
+    // active neurons; the derivative is evaluated on that masked output (matters for tanh / gaussian)
+    const double *colmask;
 };
 
 constexpr int GEMM_BK = 16;
@@ -137,11 +140,13 @@ static __device__ __noinline__ void epilogue_tile(const GemmArgs &p, const doubl
     for (int base = 0; base < total; base += 4 * nthreads) {                    \
         double zz[4], xx[4];                                                    \
         int64_t cc[4], xc[4];                                                   \
+        int cg[4];                                                              \
         bool ok[4];                                                             \
         _Pragma("unroll") for (int u = 0; u < 4; ++u) {                         \
             const int idx = base + u * nthreads + tid;                          \
             const int r = idx >> log2_cols, c = idx & (cols - 1);               \
             ok[u] = idx < total && c < cmax;                                    \
+            cg[u] = col0 + c;                                                   \
             cc[u] = (int64_t)(row0 + r) * p.ldc + col0 + c;                     \
             xc[u] = (int64_t)(row0 + r) * p.ldaux + col0 + c;                   \
             zz[u] = ok[u] ? Cs[r * c_ld + c] : 0.0;                             \
@@ -153,29 +158,36 @@ static __device__ __noinline__ void epilogue_tile(const GemmArgs &p, const doubl
             if (ok[u]) {                                                        \
                 const double z = zz[u], x = xx[u];                              \
                 const int64_t ci = cc[u], xi = xc[u];                           \
-                (void)x; (void)xi;                                              \
+                const int gc = cg[u];                                           \
+                (void)x; (void)xi; (void)gc;                                    \
                 BODY                                                            \
             }                                                                   \
         }                                                                       \
     }
     switch (p.epi) {
         case EPI_STORE:
-            OPL_EPI_LOOP(, C[ci] = z;)
+            if (p.colmask) { OPL_EPI_LOOP(, C[ci] = z * p.colmask[gc];) }
+            else { OPL_EPI_LOOP(, C[ci] = z;) }
             break;
         case EPI_TANH:
-            OPL_EPI_LOOP(, C[ci] = tanh(z);)
+            if (p.colmask) { OPL_EPI_LOOP(, C[ci] = tanh(z) * p.colmask[gc];) }
+            else { OPL_EPI_LOOP(, C[ci] = tanh(z);) }
             break;
         case EPI_SOFTPLUS: {   // calculate.py:128-141
             double *__restrict__ aux = p.aux_out;
             // one exp serves both: sigmoid(z) = e/(1+e) (== 1/(1+exp(-z)) to rounding; 1 once e overflows)
+            const double *cm = p.colmask;
             OPL_EPI_LOOP(, const double e = exp(z); const double d_ = 1.0 + e; double r_ = log(d_);
-                         if (isinf(r_)) r_ = z; C[ci] = r_; if (aux) aux[xi] = isinf(e) ? 1.0 : e / d_;)
+                         if (isinf(r_)) r_ = z; if (cm) r_ *= cm[gc]; C[ci] = r_;
+                         if (aux) aux[xi] = isinf(e) ? 1.0 : e / d_;)
             break;
         }
         case EPI_GAUSSIAN: {   // calculate.py:101-106
             double *__restrict__ aux = p.aux_out;
             const double v = p.tparam;
-            OPL_EPI_LOOP(, const double a = exp(-(z * z / v)); C[ci] = a; if (aux) aux[xi] = -2.0 * z * a / v;)
+            const double *cm = p.colmask;
+            OPL_EPI_LOOP(, double a = exp(-(z * z / v)); if (cm) a *= cm[gc]; C[ci] = a;
+                         if (aux) aux[xi] = -2.0 * z * a / v;)
             break;
         }
         case EPI_MUL_AUX: {

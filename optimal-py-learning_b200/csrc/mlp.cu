@@ -45,6 +45,7 @@ __device__ __forceinline__ double transfer_value(int tid, double tparam, double 
             return isinf(r) ? z : r;
         }
         case OPL_TRANSFER_GAUSSIAN: return exp(-(z * z / tparam));
+        case OPL_TRANSFER_LOGIT: return 1.0 / (1.0 + exp(-z));   // calculate.py:65-67
         default: return z;
     }
 }
@@ -53,6 +54,10 @@ __device__ __forceinline__ double transfer_slope(int tid, double tparam, double 
         case OPL_TRANSFER_TANH: return 1.0 - a * a;
         case OPL_TRANSFER_SOFTPLUS: return 1.0 / (1.0 + exp(-z));
         case OPL_TRANSFER_GAUSSIAN: return -2.0 * z * a / tparam;
+        case OPL_TRANSFER_LOGIT: {   // calculate.dlogit (calculate.py:70-88): e^z/(e^z+1)^2, and 1 where e^z overflows
+            const double e = exp(z);
+            return isinf(e) ? 1.0 : e / ((e + 1.0) * (e + 1.0));
+        }
         default: return 1.0;
     }
 }
@@ -307,6 +312,13 @@ __global__ void colsum_partial_kernel(const double *__restrict__ D, int64_t rows
     }
 }
 
+// rows of a (rows x cols) matrix times a per-row 0/1 factor: the input dropout mask folded into W0 / dW0
+__global__ void scale_rows_kernel(double *M, int64_t rows, int64_t cols, const double *__restrict__ factor) {
+    const int64_t total = rows * cols;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        M[i] *= factor[i / cols];
+}
+
 // trial point w = x + fl(alpha*dir) (or a copy), and per-evaluation flag reset
 __global__ void trial_point_kernel(int64_t n, const double *__restrict__ x, double alpha,
                                    const double *__restrict__ dir, double *__restrict__ w, int *flag) {
@@ -400,6 +412,8 @@ struct opl_mlp {
     double *scal = nullptr;         // device: 4 doubles
     int *flag = nullptr;
     double *pinned = nullptr;       // host pinned: 4 doubles + flag
+    double *masks = nullptr;        // DropoutMLP: [d0 ; d1 ; ... ; d_{L-1}] 0/1 vectors, or null
+    std::vector<int64_t> mask_off;  // offset of layer l's mask (l = 0 input, l >= 1 hidden outputs)
     int64_t launches = 0;
     // optional per-launch timing (CUDA events on the launch stream): kind = stage*100 + layer
     bool profiling = false;
@@ -481,6 +495,7 @@ int free_all(opl_mlp *ws) {
     cudaFree(ws->probe_partial);
     cudaFree(ws->scal);
     cudaFree(ws->flag);
+    cudaFree(ws->masks);
     cudaFreeHost(ws->pinned);
     for (cudaEvent_t e : ws->ev_pool) cudaEventDestroy(e);
     return OPL_OK;
@@ -496,7 +511,7 @@ int epilogue_for(int transfer) {
 }
 
 // forward through all layers; leaves Z_L in act[layers]
-int forward(opl_mlp *ws, const double *w, const double *x, int64_t rows, bool keep_deriv) {
+int forward(opl_mlp *ws, const double *w, const double *x, int64_t rows, bool keep_deriv, bool masked = false) {
     const double *in = x;
     for (int l = 0; l < ws->layers; ++l) {
         GemmArgs a = {};
@@ -516,6 +531,7 @@ int forward(opl_mlp *ws, const double *w, const double *x, int64_t rows, bool ke
         const bool last = l == ws->layers - 1;
         a.epi = last ? EPI_STORE : epilogue_for(ws->transfer[l]);
         a.aux_out = (!last && keep_deriv) ? ws->deriv[l] : nullptr;
+        a.colmask = (!last && ws->masks && masked) ? ws->masks + ws->mask_off[l + 1] : nullptr;
         mark(ws, STAGE_FWD * 100 + l);
         int rc = launch_gemm_f64(GEMM_NN, a, 1, ws->stream, &ws->launches);
         if (rc != OPL_OK) return rc;
@@ -691,11 +707,23 @@ int evaluate(opl_mlp *ws, const double *x_dev, double alpha, const double *dir_d
         mark(ws, STAGE_END * 100);
         return rc;
     }
-    rc = forward(ws, ws->w_trial, ws->x, ws->rows, want_grad);
+    const int64_t w0_count = ws->width[0] * ws->width[1];
+    const int mgrid = (int)std::min<int64_t>(ceil_div(w0_count, 256), 4 * (int64_t)sm_count());
+    if (ws->masks) {   // (X o m) W0 == X (diag(m) W0) exactly for a 0/1 mask
+        scale_rows_kernel<<<mgrid, 256, 0, ws->stream>>>(ws->w_trial + ws->w_off[0], ws->width[0], ws->width[1], ws->masks);
+        OPL_LAUNCH_CHECK();
+        ++ws->launches;
+    }
+    rc = forward(ws, ws->w_trial, ws->x, ws->rows, want_grad, true);
     if (rc != OPL_OK) return rc;
     rc = output_stage(ws, ws->y, ws->rows, false, want_grad, grad_out_dev + n);
     if (rc != OPL_OK) return rc;
     if (want_grad) rc = backward(ws, ws->w_trial, ws->x, ws->rows, grad_out_dev);
+    if (rc == OPL_OK && want_grad && ws->masks) {   // dW0 = (X o m)^T delta_0 = diag(m) X^T delta_0
+        scale_rows_kernel<<<mgrid, 256, 0, ws->stream>>>(grad_out_dev + ws->w_off[0], ws->width[0], ws->width[1], ws->masks);
+        OPL_LAUNCH_CHECK();
+        ++ws->launches;
+    }
     mark(ws, STAGE_END * 100);
     return rc;
 }
@@ -738,8 +766,9 @@ int opl_mlp_create(opl_mlp **out, int32_t n_widths, const int64_t *widths, const
     for (int i = 0; i < n_widths; ++i)
         if (widths[i] < 1 || widths[i] > (1 << 24)) return fail(OPL_E_ARG, "opl_mlp_create: bad width");
     for (int i = 0; i < n_widths - 1; ++i)
-        if (transfer_ids[i] < 0 || transfer_ids[i] > OPL_TRANSFER_SOFTMAX)
-            return fail(OPL_E_ARG, "opl_mlp_create: unknown transfer id %d", transfer_ids[i]);
+        if (transfer_ids[i] < 0 || transfer_ids[i] > OPL_TRANSFER_LOGIT ||
+            (transfer_ids[i] == OPL_TRANSFER_LOGIT && i != n_widths - 2))
+            return fail(OPL_E_ARG, "opl_mlp_create: unknown transfer id %d (logit is an output transfer)", transfer_ids[i]);
     if (max_rows > 0x7fffffff) return fail(OPL_E_ARG, "opl_mlp_create: max_rows too large");
     if (opl_device_count() < 1) return fail(OPL_E_CUDA, "no CUDA device: opl_b200 has no CPU fallback");
 
@@ -761,6 +790,11 @@ int opl_mlp_create(opl_mlp **out, int32_t n_widths, const int64_t *widths, const
         at += widths[l] * widths[l + 1];
     }
     ws->n = at;
+    ws->mask_off.resize(ws->layers);
+    for (int l = 0, m = 0; l < ws->layers; ++l) {
+        ws->mask_off[l] = m;
+        m += (int)widths[l];
+    }
 
     const int L = ws->layers;
     ws->act.assign(L + 1, nullptr);
@@ -826,6 +860,26 @@ int opl_mlp_destroy(opl_mlp *ws) {
 
 int64_t opl_mlp_param_count(const opl_mlp *ws) { return ws ? ws->n : -1; }
 int64_t opl_mlp_launch_count(const opl_mlp *ws) { return ws ? ws->launches : -1; }
+
+int opl_mlp_set_masks_host(opl_mlp *ws, const double *masks, int64_t len) {
+    if (!ws) return fail(OPL_E_ARG, "opl_mlp_set_masks_host: null");
+    if (!masks) {
+        OPL_CUDA(cudaStreamSynchronize(ws->stream));
+        cudaFree(ws->masks);
+        ws->masks = nullptr;
+        return OPL_OK;
+    }
+    if (ws->precision != OPL_PRECISION_F64) return fail(OPL_E_ARG, "dropout masks are supported in the FP64 parity mode only");
+    int64_t want = 0;
+    for (int l = 0; l < ws->layers; ++l) want += ws->width[l];
+    if (len != want) return fail(OPL_E_ARG, "opl_mlp_set_masks_host: expected %lld mask entries, got %lld", (long long)want, (long long)len);
+    for (int l = 0; l + 1 < ws->layers; ++l)
+        if (ws->transfer[l] == OPL_TRANSFER_SOFTMAX) return fail(OPL_E_ARG, "dropout on a hidden softmax layer is not supported");
+    if (!ws->masks) OPL_CUDA(cudaMalloc(&ws->masks, sizeof(double) * (size_t)want));
+    OPL_CUDA(cudaMemcpyAsync(ws->masks, masks, sizeof(double) * (size_t)want, cudaMemcpyHostToDevice, ws->stream));
+    OPL_CUDA(cudaStreamSynchronize(ws->stream));
+    return OPL_OK;
+}
 
 int opl_mlp_profile(opl_mlp *ws, int32_t enable) {
     if (!ws) return fail(OPL_E_ARG, "opl_mlp_profile: null");
@@ -1037,14 +1091,14 @@ extern "C" {
 
 int opl_transfer_apply_host(int32_t transfer_id, double param, const double *x, int64_t rows, int64_t cols,
                             double *out) {
-    if (!x || !out || transfer_id < 0 || transfer_id > OPL_TRANSFER_SOFTMAX)
+    if (!x || !out || transfer_id < 0 || transfer_id > OPL_TRANSFER_LOGIT)
         return fail(OPL_E_ARG, "opl_transfer_apply_host: bad arguments");
     return rows_call(transfer_id, param, OPL_ERROR_MSE, x, nullptr, nullptr, rows, cols, out, nullptr, nullptr);
 }
 
 int opl_transfer_backprop_host(int32_t transfer_id, double param, const double *x, const double *upstream,
                                int64_t rows, int64_t cols, double *out) {
-    if (!x || !upstream || !out || transfer_id < 0 || transfer_id > OPL_TRANSFER_SOFTMAX)
+    if (!x || !upstream || !out || transfer_id < 0 || transfer_id > OPL_TRANSFER_LOGIT)
         return fail(OPL_E_ARG, "opl_transfer_backprop_host: bad arguments");
     return rows_call(transfer_id, param, OPL_ERROR_MSE, x, nullptr, upstream, rows, cols, nullptr, out, nullptr);
 }

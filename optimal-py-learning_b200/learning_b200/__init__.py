@@ -9,12 +9,14 @@ from . import _native  # noqa: F401  (loads / builds libopl_b200.so or raises Im
 
 from .transfer import (Transfer, LinearTransfer, TanhTransfer, ReluTransfer, GaussianTransfer,
                        SoftmaxTransfer)
-from .error import ErrorFunc, MeanSquaredError, CrossEntropyError
+from .error import ErrorFunc, MeanSquaredError, CrossEntropyError, L1Penalty, L2Penalty
 from .base import Model
 from . import optimize
 from . import validation
-from .architecture.mlp import MLP
+from .architecture.mlp import MLP, DropoutMLP
+from .architecture.regression import LinearRegressionModel, LogisticRegressionModel
 
 __all__ = ['Transfer', 'LinearTransfer', 'TanhTransfer', 'ReluTransfer', 'GaussianTransfer',
-           'SoftmaxTransfer', 'ErrorFunc', 'MeanSquaredError', 'CrossEntropyError', 'Model', 'MLP',
+           'SoftmaxTransfer', 'ErrorFunc', 'MeanSquaredError', 'CrossEntropyError', 'L1Penalty', 'L2Penalty', 'Model',
+           'MLP', 'DropoutMLP', 'LinearRegressionModel', 'LogisticRegressionModel',
            'optimize', 'validation']

@@ -75,3 +75,16 @@ def error_value(kernel_id, tensor_a, tensor_b):
 
 def error_value_derivative(kernel_id, tensor_a, tensor_b):
     return _error(kernel_id, tensor_a, tensor_b, True)
+
+
+def penalty(kind, weight, weight_tensor, want_derivative):
+    """(penalty value, gradient or None) of an L1 / L2 weight penalty, computed on the device."""
+    import torch
+    from . import _device as dev
+    w = dev.to_device(numpy.asarray(weight_tensor, dtype=numpy.float64).ravel())
+    grad = torch.zeros_like(w) if want_derivative else None
+    value = ctypes.c_double(0.0)
+    nat.check(nat.lib.opl_vec_penalty_device(w.numel(), dev.ptr(w), int(kind), float(weight), dev.ptr(grad),
+                                             ctypes.byref(value), dev.stream_ptr()))
+    out = dev.to_host(grad).reshape(numpy.shape(weight_tensor)) if want_derivative else None
+    return value.value, out

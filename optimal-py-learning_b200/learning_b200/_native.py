@@ -36,6 +36,7 @@ SIGNATURES = {
     "opl_mlp_probe_scalars": (ctypes.c_int, [vp, vp, vp, i32, c_double_p]),
     "opl_mlp_activate_device": (ctypes.c_int, [vp, vp, vp, i64, vp]),
     "opl_mlp_launch_count": (i64, [vp]),
+    "opl_mlp_set_masks_host": (ctypes.c_int, [vp, vp, i64]),
     "opl_mlp_profile": (ctypes.c_int, [vp, i32]),
     "opl_mlp_profile_read": (ctypes.c_int, [vp, i32, c_int32_p, ctypes.POINTER(ctypes.c_float), c_int32_p]),
     "opl_bench_gemm_f64": (ctypes.c_int, [i32, i32, i32, i32, vp, vp, vp, vp, i64, i32, ctypes.POINTER(ctypes.c_float)]),
@@ -63,6 +64,7 @@ SIGNATURES = {
     "opl_lbfgs_launch_count": (i64, [vp]),
     "opl_vec_axpy_device": (ctypes.c_int, [i64, vp, f64, vp, f64, vp, vp, vp]),
     "opl_vec_scale_device": (ctypes.c_int, [i64, f64, vp, vp, vp]),
+    "opl_vec_penalty_device": (ctypes.c_int, [i64, vp, i32, f64, vp, c_double_p, vp]),
     "opl_vec_dot_device": (ctypes.c_int, [i64, vp, vp, c_double_p, vp]),
 }
 

@@ -1,2 +1,3 @@
 """Model architectures on the B200 hot path."""
-from .mlp import MLP
+from .mlp import MLP, DropoutMLP
+from .regression import LinearRegressionModel, LogisticRegressionModel

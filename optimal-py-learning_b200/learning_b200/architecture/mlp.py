@@ -16,6 +16,7 @@ import ctypes
 import functools
 import operator
 import os
+import random
 
 import numpy
 import torch
@@ -82,77 +83,28 @@ def _fingerprint(x, y):
             x.shape, y.shape, sample(x), sample(y))
 
 
-class MLP(Model):
-    """MultiLayer Perceptron.
+class _KernelModel(Model):
+    """Device plumbing shared by the models whose objective is the MLP kernel schedule (MLP,
+    DropoutMLP, Linear/LogisticRegressionModel): workspace lifetime, dataset residency, row
+    sharding over torch.distributed ranks and the fused evaluation probe.
 
-    Args:
-        shape: Number of inputs, followed by number of outputs of each layer.
-        transfers: Optional list of transfer layers, or a single Transfer for the output layer.
-            Defaults to softplus ("ReLU") hidden layers followed by a linear output.
-        optimizer: Optimizer used to optimize the weight matrices
-            (default: BFGS up to 500 weights, else L-BFGS; bias excluded from the count).
-        error_func: ErrorFunc (default MeanSquaredError).
-        jacobian_norm_break: Training ends when the gradient norm falls below this value.
-        precision: the one knob this build adds.  'f64' (default): FP64 DMMA kernels, objective and
-            gradient match the reference to 1e-10.  'tf32': tcgen05 TF32 tensor-core GEMMs with FP32
-            accumulation (1e-3).  Defaults to the OPL_PRECISION environment variable.
+    Subclasses provide ``_shape``, ``_lowered_transfers``, ``_lowered_error`` and ``_precision``.
     """
 
     PRECISIONS = {'f64': 0, 'tf32': 1}
 
-    def __init__(self, shape, transfers=None, optimizer=None, error_func=None, jacobian_norm_break=1e-10,
-                 precision=None):
-        super(MLP, self).__init__()
+    def _init_kernel_state(self, precision=None):
         if precision is None:
             precision = os.environ.get('OPL_PRECISION', 'f64')
         if precision not in self.PRECISIONS:
             raise ValueError("precision must be 'f64' or 'tf32', got %r" % (precision,))
         self._precision = precision
-        hidden = len(shape) - 2
-        if transfers is None:
-            transfers = [ReluTransfer() for _ in range(hidden)] + [LinearTransfer()]
-        elif isinstance(transfers, Transfer):
-            transfers = [ReluTransfer() for _ in range(hidden)] + [transfers]
-        if len(transfers) != len(shape) - 1:
-            raise ValueError('Must have exactly 1 transfer between each pair of layers, and after the output')
-        self._shape = shape
-
-        # draw order matters for seeded reproducibility (mlp.py:79-82): bias first, then matrices
-        self._bias_vec = self._random_weight_matrix(shape[1])
-        self._weight_matrices = []
-        self._setup_weight_matrices()
-        self._transfers = transfers
-        self._lowered_transfers = [transfer_mod.lower(t) for t in transfers]
-
-        if optimizer is None:
-            optimizer = make_optimizer(sum(functools.reduce(operator.mul, m.shape)
-                                           for m in self._weight_matrices))
-        self._optimizer = optimizer
-        if error_func is None:
-            error_func = MeanSquaredError()
-        self._error_func = error_func
-        self._lowered_error = error_mod.lower(error_func)
-        self._jacobian_norm_break = jacobian_norm_break
-
         self._workspace = None
         self._last_grad_norm = None
         self.obj_jac_evaluations = 0     # probe counter (bench / diagnostics)
-        self.reset()
 
-    # ------------------------------------------------------------------ weights
-    def _setup_weight_matrices(self):
-        self._weight_matrices = [self._random_weight_matrix((rows, cols))
-                                 for rows, cols in zip(self._shape[:-1], self._shape[1:])]
-
-    def _random_weight_matrix(self, shape):
-        return (2 * numpy.random.random(shape) - 1) * INITIAL_WEIGHTS_RANGE
-
-    def reset(self):
-        """New random weights (matrices first, then bias: mlp.py:125-130) and a reset optimizer."""
-        super(MLP, self).reset()
-        self._setup_weight_matrices()
-        self._bias_vec = self._random_weight_matrix(self._shape[1])
-        self._optimizer.reset()
+    def _param_count(self):
+        return self._shape[1] + sum(a * b for a, b in zip(self._shape[:-1], self._shape[1:]))
 
     # ------------------------------------------------------------------ device workspace
     def _workspace_for(self, rows):
@@ -231,9 +183,8 @@ class MLP(Model):
         if outs != self._shape[-1]:
             raise ValueError('target attributes == %s, expected %s' % (outs, self._shape[-1]))
 
-    # ------------------------------------------------------------------ forward
-    def activate(self, input_tensor):
-        """Model outputs for one pattern (1-D) or a matrix of patterns (mlp.py:134-163)."""
+    def _forward_host(self, flat_params, input_tensor):
+        """Batched forward of host patterns with host parameters (one H2D + kernels + one D2H)."""
         if not isinstance(input_tensor, numpy.ndarray):
             input_tensor = numpy.array(input_tensor)
         if input_tensor.shape[-1] != self._shape[0]:
@@ -244,12 +195,129 @@ class MLP(Model):
         if x2.ndim != 2:
             raise ValueError('activate expects a vector or a matrix')
         ws = self._workspace_for(x2.shape[0])
-        params = _flatten(self._bias_vec, self._weight_matrices)
+        params = numpy.ascontiguousarray(flat_params, dtype=numpy.float64)
         out = numpy.empty((x2.shape[0], self._shape[-1]))
         nat.check(nat.lib.opl_mlp_activate_host(ws.pointer, params.ctypes.data_as(ctypes.c_void_p),
                                                 x2.ctypes.data_as(ctypes.c_void_p), x2.shape[0],
                                                 out.ctypes.data_as(ctypes.c_void_p)))
         return out[0] if vector else out
+
+    def _probe(self, ws, x_dev, alpha, direction, want_grad):
+        """Evaluate at x + alpha*direction on the device.  Returns (obj, slope, grad tensor | None)."""
+        n = x_dev.numel()
+        out = torch.empty(n + 1, dtype=torch.float64, device=x_dev.device)
+        nat.check(nat.lib.opl_mlp_eval_device(ws.pointer, dev.ptr(x_dev), float(alpha), dev.ptr(direction),
+                                              1 if want_grad else 0, dev.ptr(out)))
+        if getattr(ws, 'sharded', False):
+            # batch-sharded ranks hold partial sums of [gradient ; objective]: one NCCL all-reduce
+            torch.distributed.all_reduce(out if want_grad else out[n:])
+        scalars = (ctypes.c_double * 3)()
+        nat.check(nat.lib.opl_mlp_probe_scalars(ws.pointer, dev.ptr(out), dev.ptr(direction),
+                                                1 if want_grad else 0, scalars))
+        self.obj_jac_evaluations += 1
+        self._last_grad_norm = float(numpy.sqrt(scalars[2])) if want_grad else None
+        return scalars[0], scalars[1], (out[:n] if want_grad else None)
+
+    def _objective(self, parameter_vec, input_matrix, target_matrix, want_grad):
+        """Shared body of _get_obj / _get_obj_jac: NumPy in -> host-buffer C-ABI call, device in -> device call."""
+        ws = self._make_resident(input_matrix, target_matrix)
+        if dev.is_device_vector(parameter_vec):
+            obj, _, grad = self._probe(ws, parameter_vec, 0.0, None, want_grad)
+            return obj, grad
+        params = numpy.ascontiguousarray(parameter_vec, dtype=numpy.float64)
+        if params.shape != (self._param_count(),):
+            raise ValueError('parameter_vec has shape %s, expected (%d,)' % (params.shape, self._param_count()))
+        self._adopt(params)
+        if getattr(ws, 'sharded', False):
+            obj, _, grad = self._probe(ws, dev.to_device(params), 0.0, None, want_grad)
+            return obj, (dev.to_host(grad) if want_grad else None)
+        obj = ctypes.c_double(0.0)
+        if not want_grad:
+            nat.check(nat.lib.opl_mlp_obj_host(ws.pointer, params.ctypes.data_as(ctypes.c_void_p), ctypes.byref(obj)))
+            return obj.value, None
+        grad = numpy.empty_like(params)
+        nat.check(nat.lib.opl_mlp_obj_jac_host(ws.pointer, params.ctypes.data_as(ctypes.c_void_p),
+                                               ctypes.byref(obj), grad.ctypes.data_as(ctypes.c_void_p)))
+        self.obj_jac_evaluations += 1
+        return obj.value, grad
+
+    def _adopt(self, params):
+        raise NotImplementedError()
+
+    # ------------------------------------------------------------------ pickling (base.py:350-373)
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state['_workspace'] = None       # device buffers are rebuilt on demand
+        return state
+
+
+class MLP(_KernelModel):
+    """MultiLayer Perceptron.
+
+    Args:
+        shape: Number of inputs, followed by number of outputs of each layer.
+        transfers: Optional list of transfer layers, or a single Transfer for the output layer.
+            Defaults to softplus ("ReLU") hidden layers followed by a linear output.
+        optimizer: Optimizer used to optimize the weight matrices
+            (default: BFGS up to 500 weights, else L-BFGS; bias excluded from the count).
+        error_func: ErrorFunc (default MeanSquaredError).
+        jacobian_norm_break: Training ends when the gradient norm falls below this value.
+        precision: the one knob this build adds.  'f64' (default): FP64 DMMA kernels, objective and
+            gradient match the reference to 1e-10.  'tf32': tcgen05 TF32 tensor-core GEMMs with FP32
+            accumulation (1e-3).  Defaults to the OPL_PRECISION environment variable.
+    """
+
+    def __init__(self, shape, transfers=None, optimizer=None, error_func=None, jacobian_norm_break=1e-10,
+                 precision=None):
+        super(MLP, self).__init__()
+        self._init_kernel_state(precision)
+        hidden = len(shape) - 2
+        if transfers is None:
+            transfers = [ReluTransfer() for _ in range(hidden)] + [LinearTransfer()]
+        elif isinstance(transfers, Transfer):
+            transfers = [ReluTransfer() for _ in range(hidden)] + [transfers]
+        if len(transfers) != len(shape) - 1:
+            raise ValueError('Must have exactly 1 transfer between each pair of layers, and after the output')
+        self._shape = shape
+
+        # draw order matters for seeded reproducibility (mlp.py:79-82): bias first, then matrices
+        self._bias_vec = self._random_weight_matrix(shape[1])
+        self._weight_matrices = []
+        self._setup_weight_matrices()
+        self._transfers = transfers
+        self._lowered_transfers = [transfer_mod.lower(t) for t in transfers]
+
+        if optimizer is None:
+            optimizer = make_optimizer(sum(functools.reduce(operator.mul, m.shape)
+                                           for m in self._weight_matrices))
+        self._optimizer = optimizer
+        if error_func is None:
+            error_func = MeanSquaredError()
+        self._error_func = error_func
+        self._lowered_error = error_mod.lower(error_func)
+        self._jacobian_norm_break = jacobian_norm_break
+
+        self.reset()
+
+    # ------------------------------------------------------------------ weights
+    def _setup_weight_matrices(self):
+        self._weight_matrices = [self._random_weight_matrix((rows, cols))
+                                 for rows, cols in zip(self._shape[:-1], self._shape[1:])]
+
+    def _random_weight_matrix(self, shape):
+        return (2 * numpy.random.random(shape) - 1) * INITIAL_WEIGHTS_RANGE
+
+    def reset(self):
+        """New random weights (matrices first, then bias: mlp.py:125-130) and a reset optimizer."""
+        super(MLP, self).reset()
+        self._setup_weight_matrices()
+        self._bias_vec = self._random_weight_matrix(self._shape[1])
+        self._optimizer.reset()
+
+    # ------------------------------------------------------------------ forward
+    def activate(self, input_tensor):
+        """Model outputs for one pattern (1-D) or a matrix of patterns (mlp.py:134-163)."""
+        return self._forward_host(_flatten(self._bias_vec, self._weight_matrices), input_tensor)
 
     # ------------------------------------------------------------------ training
     def _pre_train(self, input_matrix, target_matrix):
@@ -281,65 +349,73 @@ class MLP(Model):
         self._optimizer.reset()
 
     # ------------------------------------------------------------------ objective / gradient
-    def _probe(self, ws, x_dev, alpha, direction, want_grad):
-        """Evaluate at x + alpha*direction on the device.  Returns (obj, slope, grad tensor | None)."""
-        n = x_dev.numel()
-        out = torch.empty(n + 1, dtype=torch.float64, device=x_dev.device)
-        nat.check(nat.lib.opl_mlp_eval_device(ws.pointer, dev.ptr(x_dev), float(alpha), dev.ptr(direction),
-                                              1 if want_grad else 0, dev.ptr(out)))
-        if getattr(ws, 'sharded', False):
-            # batch-sharded ranks hold partial sums of [gradient ; objective]: one NCCL all-reduce
-            torch.distributed.all_reduce(out if want_grad else out[n:])
-        scalars = (ctypes.c_double * 3)()
-        nat.check(nat.lib.opl_mlp_probe_scalars(ws.pointer, dev.ptr(out), dev.ptr(direction),
-                                                1 if want_grad else 0, scalars))
-        self.obj_jac_evaluations += 1
-        self._last_grad_norm = float(numpy.sqrt(scalars[2])) if want_grad else None
-        return scalars[0], scalars[1], (out[:n] if want_grad else None)
-
     def _get_obj(self, parameter_vec, input_matrix, target_matrix):
-        """Objective at ``parameter_vec`` (mlp.py:195-199).  NumPy in -> host-buffer C-ABI call;
-        device tensor in -> device call."""
-        ws = self._make_resident(input_matrix, target_matrix)
-        if dev.is_device_vector(parameter_vec):
-            return self._probe(ws, parameter_vec, 0.0, None, False)[0]
-        params = numpy.ascontiguousarray(parameter_vec, dtype=numpy.float64)
-        self._adopt(params)
-        if getattr(ws, 'sharded', False):
-            return self._probe(ws, dev.to_device(params), 0.0, None, False)[0]
-        obj = ctypes.c_double(0.0)
-        nat.check(nat.lib.opl_mlp_obj_host(ws.pointer, params.ctypes.data_as(ctypes.c_void_p), ctypes.byref(obj)))
-        return obj.value
+        """Objective at ``parameter_vec`` (mlp.py:195-199)."""
+        return self._objective(parameter_vec, input_matrix, target_matrix, False)[0]
 
     def _get_obj_jac(self, parameter_vec, input_matrix, target_matrix):
         """(objective, flat gradient) at ``parameter_vec`` (mlp.py:202-208)."""
-        ws = self._make_resident(input_matrix, target_matrix)
-        if dev.is_device_vector(parameter_vec):
-            obj, _, grad = self._probe(ws, parameter_vec, 0.0, None, True)
-            return obj, grad
-        params = numpy.ascontiguousarray(parameter_vec, dtype=numpy.float64)
-        if params.shape != (self._param_count(),):
-            raise ValueError('parameter_vec has shape %s, expected (%d,)' % (params.shape, self._param_count()))
-        self._adopt(params)
-        if getattr(ws, 'sharded', False):
-            obj, _, grad = self._probe(ws, dev.to_device(params), 0.0, None, True)
-            return obj, dev.to_host(grad)
-        obj = ctypes.c_double(0.0)
-        grad = numpy.empty_like(params)
-        nat.check(nat.lib.opl_mlp_obj_jac_host(ws.pointer, params.ctypes.data_as(ctypes.c_void_p),
-                                               ctypes.byref(obj), grad.ctypes.data_as(ctypes.c_void_p)))
-        self.obj_jac_evaluations += 1
-        return obj.value, grad
+        return self._objective(parameter_vec, input_matrix, target_matrix, True)
 
     def _adopt(self, params):
         """The reference leaves the model weights at the last evaluated point (mlp.py:197,204)."""
         self._bias_vec, self._weight_matrices = _unflatten_weights(params, self._shape)
 
-    def _param_count(self):
-        return self._shape[1] + sum(a * b for a, b in zip(self._shape[:-1], self._shape[1:]))
 
-    # ------------------------------------------------------------------ pickling (base.py:350-373)
-    def __getstate__(self):
-        state = dict(self.__dict__)
-        state['_workspace'] = None       # device buffers are rebuilt on demand
-        return state
+def _get_active_neurons(active_probability, num_neurons):
+    """0/1 vector of active neurons, at least one active (mlp.py:448-462); draws from ``random``."""
+    if active_probability <= 0.0 or active_probability > 1.0:
+        raise ValueError('0 < active_probability <= 1')
+    active = [1.0 if random.uniform(0, 1) < active_probability else 0.0 for _ in range(num_neurons)]
+    if 1.0 not in active:
+        active[random.randint(0, len(active) - 1)] = 1.0
+    return numpy.array(active)
+
+
+class DropoutMLP(MLP):
+    """MLP trained with dropout (mlp.py:330-427).
+
+    Every train_step draws a fresh 0/1 mask for the inputs and for each hidden layer (same
+    ``random`` call order as the reference).  On the device the input mask is folded into the rows
+    of W0 / dW0 and the hidden masks multiply the transfer outputs in the forward GEMM epilogue;
+    derivatives are evaluated on the masked outputs but not masked themselves (mlp.py:438-445).
+    After training, the first ``activate`` scales every weight matrix by the hidden keep
+    probability (mlp.py:374-384).
+    """
+
+    def __init__(self, shape, transfers=None, optimizer=None, error_func=None, input_active_probability=0.8,
+                 hidden_active_probability=0.5):
+        if optimizer is None:
+            from ..optimize import SteepestDescent   # BFGS cannot track a problem that changes every step
+            optimizer = SteepestDescent()
+        super(DropoutMLP, self).__init__(shape, transfers, optimizer, error_func)
+        self._inp_act_prob = input_active_probability
+        self._hid_act_prob = hidden_active_probability
+        self._during_training = False
+        self._did_post_training = True
+
+    def activate(self, input_tensor):
+        if (not self._during_training) and (not self._did_post_training):
+            self._post_training()
+            self._did_post_training = True
+        return super(DropoutMLP, self).activate(input_tensor)
+
+    def _post_training(self):
+        for i, _ in enumerate(self._weight_matrices):
+            self._weight_matrices[i] = self._weight_matrices[i] * self._hid_act_prob
+
+    def train_step(self, input_matrix, target_matrix):
+        self._during_training = True
+        self._did_post_training = False
+        masks = [_get_active_neurons(self._inp_act_prob, self._shape[0])]
+        for num_neurons in self._shape[1:-1]:
+            masks.append(_get_active_neurons(self._hid_act_prob, num_neurons))
+        flat = numpy.ascontiguousarray(numpy.hstack(masks), dtype=numpy.float64)
+        ws = self._make_resident(input_matrix, target_matrix)
+        nat.check(nat.lib.opl_mlp_set_masks_host(ws.pointer, flat.ctypes.data_as(ctypes.c_void_p), flat.size))
+        try:
+            error = super(DropoutMLP, self).train_step(input_matrix, target_matrix)
+        finally:
+            nat.check(nat.lib.opl_mlp_set_masks_host(ws.pointer, None, 0))
+            self._during_training = False
+        return error

@@ -306,6 +306,90 @@ def gen_traces(L, store, meta):
                                    steps=steps, optimizer=optname, reference_evals=nevals))
 
 
+# ----------------------------------------------------------------------------
+# E. SURVEY section 8(f) widening: DropoutMLP, Linear / Logistic regression (+ L1 / L2 penalties)
+#    No separate oracle restatement: the golden vectors ARE the reference's outputs.
+# ----------------------------------------------------------------------------
+def gen_widening(L, store, meta):
+    from learning.architecture import mlp as rmlp
+    from learning.architecture import regression as rreg
+    rng = numpy.random.default_rng(4000)
+    meta["dropout"] = []
+    for k, (shape, hidden_t, out_t, eid, rows, steps) in enumerate([
+            ((5, 7, 3), "softplus", "softmax", mo.CROSS_ENTROPY, 40, 8),
+            ((6, 8, 5, 2), "tanh", "linear", mo.MSE, 30, 8),
+            ((4, 9, 2), "gaussian", "linear", mo.MSE, 25, 6)]):
+        gen = mo.random_classification if eid == mo.CROSS_ENTROPY else mo.random_regression
+        x, y = gen(rows, shape[0], shape[-1], rng)
+        tmap = {"softplus": L.ReluTransfer, "tanh": L.TanhTransfer, "gaussian": L.GaussianTransfer,
+                "linear": L.LinearTransfer, "softmax": L.SoftmaxTransfer}
+        transfers = [tmap[hidden_t]() for _ in shape[1:-1]] + [tmap[out_t]()]
+        random.seed(50 + k)
+        numpy.random.seed(50 + k)
+        model = rmlp.DropoutMLP(shape, transfers=transfers, error_func=_ref_error(L, eid),
+                                input_active_probability=0.8, hidden_active_probability=0.6)
+        model.logging = False
+        weights, errors = [], []
+        with numpy.errstate(all='ignore'):
+            for _ in range(steps):
+                errors.append(float(model.train_step(x, y)))
+                weights.append(rmlp._flatten(model._bias_vec, model._weight_matrices).copy())
+            out = model.activate(x)          # first activate after training: post-training weight scaling
+        key = "do%d" % k
+        store[key + "_x"], store[key + "_y"] = x, y
+        store[key + "_weights"], store[key + "_errors"], store[key + "_out"] = numpy.array(weights), numpy.array(errors), out
+        meta["dropout"].append(dict(key=key, shape=list(shape), hidden=hidden_t, out=out_t, error=int(eid), seed=50 + k,
+                                    steps=steps))
+        print("dropout %s steps=%d final err=%.6g" % (shape, steps, errors[-1]))
+
+    meta["regression"] = []
+    for k, (kind, attrs, outs, eid, pen, rows) in enumerate([
+            ("linear", 5, 2, mo.MSE, None, 40), ("linear", 7, 3, mo.MSE, ("l1", 0.05), 33),
+            ("linear", 4, 1, mo.MSE, ("l2", 0.3), 21), ("logistic", 6, 3, mo.MSE, None, 50),
+            ("logistic", 5, 2, mo.CROSS_ENTROPY, ("l2", 0.01), 45), ("logistic", 3, 4, mo.MSE, ("l1", 0.02), 28)]):
+        x, y = mo.random_regression(rows, attrs, outs, rng)
+        if kind == "logistic":
+            y = (y + 1.0) / 2.0
+        penalty = None if pen is None else (L.L1Penalty if pen[0] == "l1" else L.L2Penalty)(penalty_weight=pen[1])
+        cls = rreg.LinearRegressionModel if kind == "linear" else rreg.LogisticRegressionModel
+        random.seed(70 + k)
+        numpy.random.seed(70 + k)
+        model = cls(attrs, outs, error_func=_ref_error(L, eid), penalty_func=penalty)
+        model.logging = False
+        w = (2.0 * rng.random((attrs + 1) * outs) - 1.0) * 0.7
+        with numpy.errstate(all='ignore'):
+            obj = float(model._get_obj(w.copy(), x, y))
+            obj2, jac = model._get_obj_jac(w.copy(), x, y)
+            model._weight_matrix = w.copy().reshape(attrs + 1, outs)
+            out = model.activate(x)
+            # short training trace from the seeded initial weights
+            random.seed(70 + k)
+            numpy.random.seed(70 + k)
+            model = cls(attrs, outs, error_func=_ref_error(L, eid), penalty_func=penalty)
+            model.logging = False
+            w0 = model._weight_matrix.ravel().copy()
+            weights, errors = [], []
+            for _ in range(10):
+                errors.append(float(model.train_step(x, y)))
+                weights.append(model._weight_matrix.ravel().copy())
+        assert abs(obj - float(obj2)) <= 1e-15 * max(1, abs(obj))
+        key = "rg%d" % k
+        store[key + "_x"], store[key + "_y"], store[key + "_w"] = x, y, w
+        store[key + "_obj"], store[key + "_jac"], store[key + "_out"] = numpy.array(obj), jac, out
+        store[key + "_w0"], store[key + "_weights"], store[key + "_errors"] = w0, numpy.array(weights), numpy.array(errors)
+        meta["regression"].append(dict(key=key, kind=kind, attrs=attrs, outs=outs, error=int(eid),
+                                       penalty=list(pen) if pen else None, seed=70 + k))
+        print("regression %-8s pen=%s obj=%.8g |jac|=%.4g trained err=%.6g" % (kind, pen, obj, numpy.linalg.norm(jac), errors[-1]))
+
+    # penalty known answers
+    w = rng.standard_normal(9)
+    store["pen_w"] = w
+    store["pen_l1"] = numpy.array([L.L1Penalty(0.3)(w)])
+    store["pen_l1_d"] = L.L1Penalty(0.3).derivative(w)
+    store["pen_l2"] = numpy.array([L.L2Penalty(0.7)(w)])
+    store["pen_l2_d"] = L.L2Penalty(0.7).derivative(w)
+
+
 def main():
     logging.disable(logging.WARNING)
     L = _load_reference()
@@ -325,6 +409,10 @@ def main():
     store = {}
     gen_traces(L, store, meta)
     numpy.savez_compressed(os.path.join(GOLDEN, "traces.npz"), **store)
+
+    store = {}
+    gen_widening(L, store, meta)
+    numpy.savez_compressed(os.path.join(GOLDEN, "widening.npz"), **store)
 
     with io.open(os.path.join(GOLDEN, "meta.json"), "w") as fh:
         json.dump(meta, fh, indent=1, sort_keys=True)

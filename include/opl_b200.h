@@ -132,6 +132,11 @@ int opl_bench_gemm_tf32(int32_t layout, int32_t M, int32_t N, int32_t K, const f
                         float *c_dev, float *scratch_dev, int64_t scratch_len, int32_t splits, int32_t iters,
                         float *ms_out);
 
+/* Validation hook for the FP64-on-INT8 (Ozaki) GEMM: C[M,N] = A[M,K].B[K,N], row-major FP64 device buffers.
+ * slice_ms_out = time of the two slicing passes, gemm_ms_out = tcgen05 INT8 GEMM (+ FP64 fold of K splits). */
+int opl_bench_gemm_ozaki(int32_t M, int32_t N, int32_t K, const double *a_dev, const double *b_dev, double *c_dev,
+                         int32_t iters, float *slice_ms_out, float *gemm_ms_out);
+
 /* ---- stand-alone host-buffer forms of the plugin objects' own methods (not on the training
  *      path; they run the same row kernel so the classes stay usable on their own) ---- */
 /* Transfer.__call__ (transfer.py:33-130) on a rows x cols matrix */

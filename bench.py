@@ -357,12 +357,12 @@ def run_gpu(args):
     if profile and stage_ms:
         flops_eval = algorithmic_flops(SHAPE, ROWS)
         names = {1: "forward GEMM", 2: "row kernel", 3: "dW GEMM", 4: "dW reduce", 5: "dA GEMM", 6: "bias colsum",
-                 7: "loss", 0: "trial point"}
+                 7: "loss", 8: "digits", 0: "trial point"}
         per_kind = {k: sum(v) / args.steps for k, v in stage_ms.items()}
         total = sum(per_kind.values())
         line["stage_ms"] = {"%s L%d" % (names.get(k // 100, "?"), k % 100): round(v, 4) for k, v in sorted(per_kind.items())}
         # dominant kernel: the FP64 DMMA GEMM (forward layer 0 + dW layer 0 are ~98% of the flops)
-        gemm_ms = sum(v for k, v in per_kind.items() if k // 100 in (1, 3, 5))
+        gemm_ms = sum(v for k, v in per_kind.items() if k // 100 in (1, 3, 5, 8))   # digit extraction counts as GEMM time
         fwd0 = per_kind.get(100, None)
         fp64_peak = fp64_gemm_peak(torch)
         gemm_flops = flops_eval

@@ -49,8 +49,13 @@ extern "C" {
 #define OPL_ERROR_CROSS_ENTROPY  1
 
 /* arithmetic modes */
-#define OPL_PRECISION_F64   0   /* parity mode: FP64 DMMA, matches NumPy float64 to 1e-10  */
+#define OPL_PRECISION_F64   0   /* parity mode: FP64 in / out, matches NumPy float64 to 1e-10 */
 #define OPL_PRECISION_TF32  1   /* fast mode: tcgen05 TF32, FP32 accumulate (1e-3)         */
+
+/* which kernels run the large layer GEMMs of the parity mode (both are FP64-accurate; small layers always use DMMA) */
+#define OPL_ENGINE_DMMA     0   /* mma.sync.m8n8k4.f64                                               */
+#define OPL_ENGINE_INT8     1   /* Ozaki splitting: 21 exact INT8 products on tcgen05.mma.kind::i8, FP64 recombination
+                                   (default; environment OPL_F64_ENGINE=dmma selects the other one)  */
 
 const char *opl_last_error(void);
 int opl_version(void);
@@ -71,6 +76,8 @@ int opl_mlp_create(opl_mlp **out, int32_t n_widths, const int64_t *widths,
                    int32_t error_id, int64_t max_rows, int32_t precision, void *cuda_stream);
 int opl_mlp_destroy(opl_mlp *ws);
 int64_t opl_mlp_param_count(const opl_mlp *ws);
+/* select OPL_ENGINE_* for the parity mode's large GEMMs (takes effect at the next evaluation) */
+int opl_mlp_set_engine(opl_mlp *ws, int32_t engine);
 
 /* Make `rows` patterns resident (copied into the workspace).  `norm_rows` is the N of the
  * reference's 1/N (cross entropy, error.py:115-116) and 1/(N*C) (MSE, error.py:62) scales:
@@ -132,10 +139,12 @@ int opl_bench_gemm_tf32(int32_t layout, int32_t M, int32_t N, int32_t K, const f
                         float *c_dev, float *scratch_dev, int64_t scratch_len, int32_t splits, int32_t iters,
                         float *ms_out);
 
-/* Validation hook for the FP64-on-INT8 (Ozaki) GEMM: C[M,N] = A[M,K].B[K,N], row-major FP64 device buffers.
- * slice_ms_out = time of the two slicing passes, gemm_ms_out = tcgen05 INT8 GEMM (+ FP64 fold of K splits). */
+/* Validation hook for the FP64-on-INT8 (Ozaki) GEMM: C[M,N] = epi(A[M,K].B[K,N]), row-major FP64 device buffers.
+ * variant: 0 = A read from shared memory by every MMA, 1 = A staged into TMEM by tcgen05.cp, 2 = by loader warps;
+ * epi: 0 store, 1 tanh, 2 softplus, 3 gaussian (as the layer GEMMs fuse them).
+ * slice_ms_out = time of the two digit-extraction passes, gemm_ms_out = tcgen05 INT8 GEMM (+ FP64 fold of K splits). */
 int opl_bench_gemm_ozaki(int32_t M, int32_t N, int32_t K, const double *a_dev, const double *b_dev, double *c_dev,
-                         int32_t iters, float *slice_ms_out, float *gemm_ms_out);
+                         int32_t variant, int32_t epi, int32_t iters, float *slice_ms_out, float *gemm_ms_out);
 
 /* ---- stand-alone host-buffer forms of the plugin objects' own methods (not on the training
  *      path; they run the same row kernel so the classes stay usable on their own) ---- */

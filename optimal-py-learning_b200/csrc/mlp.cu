@@ -19,6 +19,7 @@
 
 #include "gemm_f64.cuh"
 #include "gemm_tf32.cuh"
+#include "ozaki.cuh"
 
 namespace opl {
 
@@ -378,12 +379,15 @@ __global__ void softmax_jacobian_kernel(const double *__restrict__ y, int64_t ro
 using namespace opl;
 
 struct FastState;   // fast-mode (TF32) buffers, mlp_fast.inl
+struct Int8State;   // parity-mode GEMMs on the INT8 tensor cores, mlp_int8.inl
 
 // ---------------------------------------------------------------------------------------
 // workspace
 // ---------------------------------------------------------------------------------------
 struct opl_mlp {
     FastState *fast = nullptr;
+    Int8State *int8 = nullptr;
+    int gemm_engine = OPL_ENGINE_INT8;   // which kernels run the large FP64 layer GEMMs
     int layers = 0;                    // weight matrices
     std::vector<int64_t> width;        // layers + 1
     std::vector<int> transfer;
@@ -423,7 +427,7 @@ struct opl_mlp {
 };
 
 enum { STAGE_TRIAL = 0, STAGE_FWD = 1, STAGE_ROWS = 2, STAGE_DW = 3, STAGE_DW_REDUCE = 4, STAGE_DA = 5,
-       STAGE_BIAS = 6, STAGE_LOSS = 7, STAGE_END = 9 };
+       STAGE_BIAS = 6, STAGE_LOSS = 7, STAGE_DIGITS = 8, STAGE_END = 9 };
 
 namespace {
 
@@ -476,10 +480,13 @@ int launch_rows(const RowArgsT<T> &r, int max_grid, cudaStream_t stream) {
 }
 
 void fast_free(FastState *f);
+void int8_free(Int8State *s);
 
 int free_all(opl_mlp *ws) {
     fast_free(ws->fast);
     ws->fast = nullptr;
+    int8_free(ws->int8);
+    ws->int8 = nullptr;
     cudaFree(ws->x_own);
     cudaFree(ws->y_own);
     cudaFree(ws->x_scratch);
@@ -510,6 +517,12 @@ int epilogue_for(int transfer) {
     }
 }
 
+}  // namespace
+
+#include "mlp_int8.inl"
+
+namespace {
+
 // forward through all layers; leaves Z_L in act[layers]
 int forward(opl_mlp *ws, const double *w, const double *x, int64_t rows, bool keep_deriv, bool masked = false) {
     const double *in = x;
@@ -532,8 +545,13 @@ int forward(opl_mlp *ws, const double *w, const double *x, int64_t rows, bool ke
         a.epi = last ? EPI_STORE : epilogue_for(ws->transfer[l]);
         a.aux_out = (!last && keep_deriv) ? ws->deriv[l] : nullptr;
         a.colmask = (!last && ws->masks && masked) ? ws->masks + ws->mask_off[l + 1] : nullptr;
-        mark(ws, STAGE_FWD * 100 + l);
-        int rc = launch_gemm_f64(GEMM_NN, a, 1, ws->stream, &ws->launches);
+        int rc;
+        if (int8_fwd_ok(ws, l, in, rows)) {
+            rc = int8_forward_layer(ws, l, w, in, rows, keep_deriv, masked);
+        } else {
+            mark(ws, STAGE_FWD * 100 + l);
+            rc = launch_gemm_f64(GEMM_NN, a, 1, ws->stream, &ws->launches);
+        }
         if (rc != OPL_OK) return rc;
         if (!last && ws->transfer[l] == OPL_TRANSFER_SOFTMAX) {
             mark(ws, STAGE_ROWS * 100 + l);   // hidden softmax: row kernel in place
@@ -591,7 +609,10 @@ int backward(opl_mlp *ws, const double *w, const double *x, int64_t rows, double
     for (int l = ws->layers - 1; l >= 0; --l) {
         const int din = (int)ws->width[l], dout = (int)ws->width[l + 1];
         // dW_l = A_l^T delta_l  (mlp.py:269-273), reduction over the patterns
-        {
+        if (int8_dw_ok(ws, l, l == 0 ? x : ws->act[l], rows)) {
+            int rc = int8_dw_layer(ws, l, l == 0 ? x : ws->act[l], rows, grad);
+            if (rc != OPL_OK) return rc;
+        } else {
             SplitPlan plan = plan_split_k(din, dout, (int)rows);
             if ((int64_t)plan.splits * ((int64_t)din * dout + dout) > ws->partials_len)
                 return fail(OPL_E_STATE, "split-K scratch too small (layer %d)", l);
@@ -824,6 +845,16 @@ int opl_mlp_create(opl_mlp **out, int32_t n_widths, const int64_t *widths, const
         partials = std::max<int64_t>(partials, (int64_t)(plan.splits + 1) * (widths[l] * widths[l + 1] + widths[l + 1]));
     }
     partials = std::max<int64_t>(partials, (int64_t)(4 * sm_count() + 8) * widths[1]);
+    if (precision == OPL_PRECISION_F64) {
+        const char *env = getenv("OPL_F64_ENGINE");
+        if (env && std::string(env) == "dmma") ws->gemm_engine = OPL_ENGINE_DMMA;
+        int rc = int8_create(ws, &partials);
+        if (rc != OPL_OK) {
+            free_all(ws);
+            delete ws;
+            return rc;
+        }
+    }
     ws->partials_len = partials;
     OPL_TRY(cudaMalloc(&ws->partials, sizeof(double) * (size_t)partials));
     OPL_TRY(cudaMalloc(&ws->out_act, sizeof(double) * (size_t)max_rows * (size_t)widths[L]));
@@ -855,6 +886,12 @@ int opl_mlp_destroy(opl_mlp *ws) {
     cudaStreamSynchronize(ws->stream);
     free_all(ws);
     delete ws;
+    return OPL_OK;
+}
+
+int opl_mlp_set_engine(opl_mlp *ws, int32_t engine) {
+    if (!ws || (engine != OPL_ENGINE_DMMA && engine != OPL_ENGINE_INT8)) return fail(OPL_E_ARG, "opl_mlp_set_engine: bad arguments");
+    ws->gemm_engine = engine;
     return OPL_OK;
 }
 
@@ -920,7 +957,7 @@ int opl_mlp_set_data_host(opl_mlp *ws, const double *x, const double *y, int64_t
     ws->rows = rows;
     ws->norm_rows = norm_rows > 0 ? norm_rows : rows;
     if (ws->precision == OPL_PRECISION_TF32) return fast_set_x(ws);
-    return OPL_OK;
+    return int8_set_x(ws);
 }
 
 int opl_mlp_set_data_device(opl_mlp *ws, const double *x_dev, const double *y_dev, int64_t rows, int64_t norm_rows) {
@@ -931,7 +968,7 @@ int opl_mlp_set_data_device(opl_mlp *ws, const double *x_dev, const double *y_de
     ws->rows = rows;
     ws->norm_rows = norm_rows > 0 ? norm_rows : rows;
     if (ws->precision == OPL_PRECISION_TF32) return fast_set_x(ws);
-    return OPL_OK;
+    return int8_set_x(ws);
 }
 
 int opl_mlp_eval_device(opl_mlp *ws, const double *x_dev, double alpha, const double *dir_dev, int32_t want_grad,

@@ -6,20 +6,28 @@
 
 namespace opl {
 
-constexpr int OZ_S = 7;          // 7 slices x 7 bits = 49 bits below each row / column maximum
+constexpr int OZ_S = 6;          // 6 signed radix-256 digits = 48 bits below each row / column scale
 constexpr int OZ_BM = 128;
-constexpr int OZ_BN = 64;        // 7 diagonal accumulators x 64 INT32 columns = 448 of 512 TMEM columns
-constexpr int OZ_MAX_K = 16384;  // 7 * 16384 * 127^2 < 2^31: INT32 accumulation stays exact
+constexpr int OZ_BN = 64;        // 6 diagonal accumulators x 64 INT32 columns = 384 of 512 TMEM columns (+128 for A staging)
+constexpr int OZ_MAX_K = 16384;  // 6 * 16384 * 128^2 < 2^31: INT32 accumulation stays exact
 
 enum OzakiEpilogue { OZ_EPI_STORE = 0, OZ_EPI_TANH = 1, OZ_EPI_SOFTPLUS = 2, OZ_EPI_GAUSSIAN = 3 };
+
+// How the M-side operand reaches the tensor core
+enum OzakiVariant {
+    OZ_A_SMEM = 0,      // tcgen05.mma SS: A and B both read from shared memory by every MMA
+    OZ_A_UTCCP = 1,     // A tile copied smem -> TMEM once (tcgen05.cp), MMAs read A from TMEM
+    OZ_A_WARPS = 2      // A tile moved smem -> registers -> TMEM by four loader warps (tcgen05.st), MMAs read A from TMEM
+};
 
 struct OzakiArgs {
     double *C;
     int64_t ldc;
     int M, N, K;              // K = padded contraction length (multiple of 128)
     int k_per_split;          // multiple of 128, <= OZ_MAX_K
+    int splits;
     int64_t split_stride;
-    const double *scale_a;    // per row of A: power of two >= max|row|
+    const double *scale_a;    // per row of A: power of two, |a| <= 0.498 * scale
     const double *scale_b;    // per column of B
     const double *bias;
     double *aux_out;
@@ -29,24 +37,24 @@ struct OzakiArgs {
     const double *colmask;
 };
 
-// weight of diagonal d = p + q in the recombination: 2^-7(d+2)
-__host__ __device__ inline double oz_weight(int d) {
-    double w = 1.0 / 16384.0;                 // 2^-14
-    for (int i = 0; i < d; ++i) w *= 1.0 / 128.0;
-    return w;
-}
-
 int64_t ozaki_pad(int64_t v);   // round up to a multiple of 128
 
-// slices of a row-major FP64 [rows x cols] matrix, scaled per ROW: INT8 [S][pad(rows)][pad(cols)], scale[rows]
+// digits of a row-major FP64 [rows x cols] matrix, scaled per ROW: INT8 [S][pad(rows)][pad(cols)], scale[rows].
+// Padding must already be zero (ozaki_slice_* never write it); pass zero_fill to have it cleared here.
 int ozaki_slice_rows(const double *src, int64_t rows, int64_t cols, int64_t ld, int8_t *slices, double *scale,
-                     cudaStream_t stream, int64_t *launches);
-// slices of the TRANSPOSE, scaled per COLUMN of src: INT8 [S][pad(cols)][pad(rows)], scale[cols];
+                     bool zero_fill, cudaStream_t stream, int64_t *launches);
+// digits of the TRANSPOSE, scaled per COLUMN of src: INT8 [S][pad(cols)][pad(rows)], scale[cols];
 // scratch: >= min(ceil(rows/256), 4*SMs) * cols doubles
+// Output row of src column c is c + row_off (scale[c + row_off]); m_pad = padded row count of the digit array
+// (0: pad(cols + row_off)).
 int ozaki_slice_cols_transposed(const double *src, int64_t rows, int64_t cols, int64_t ld, int8_t *slices, double *scale,
-                                double *scratch, int64_t scratch_len, cudaStream_t stream, int64_t *launches);
-// C = (A slices) . (B slices)^T with both operands K-major; rows_pad = padded row counts of the slice arrays
+                                double *scratch, int64_t scratch_len, int64_t row_off, int64_t m_pad, bool zero_fill,
+                                cudaStream_t stream, int64_t *launches);
+// row 0 of a transposed digit array [S][m_pad][pad(rows)] := a row of ones (scale[0] = 4): the bias-gradient row
+int ozaki_ones_row(int8_t *slices, double *scale, int64_t rows, int64_t m_pad, cudaStream_t stream, int64_t *launches);
+// FP64 fold of split-K partials is done by the caller (launch_reduce_partials)
+// C = (A digits) . (B digits)^T with both operands K-major; rows_pad = padded row counts of the digit arrays
 int launch_ozaki_gemm(const int8_t *a_slices, int64_t a_rows_pad, const int8_t *b_slices, int64_t b_rows_pad, int64_t k_pad,
-                      const OzakiArgs &args, int splits, cudaStream_t stream, int64_t *launches);
+                      const OzakiArgs &args, int variant, cudaStream_t stream, int64_t *launches);
 
 }  // namespace opl

@@ -91,13 +91,13 @@ class _KernelModel(Model):
     Subclasses provide ``_shape``, ``_lowered_transfers``, ``_lowered_error`` and ``_precision``.
     """
 
-    PRECISIONS = {'f64': 0, 'tf32': 1}
+    PRECISIONS = {'f64': 0, 'f64-dmma': 0, 'tf32': 1}
 
     def _init_kernel_state(self, precision=None):
         if precision is None:
             precision = os.environ.get('OPL_PRECISION', 'f64')
         if precision not in self.PRECISIONS:
-            raise ValueError("precision must be 'f64' or 'tf32', got %r" % (precision,))
+            raise ValueError("precision must be 'f64', 'f64-dmma' or 'tf32', got %r" % (precision,))
         self._precision = precision
         self._workspace = None
         self._last_grad_norm = None
@@ -112,6 +112,8 @@ class _KernelModel(Model):
         if ws is None or ws.max_rows < rows:
             ws = _Workspace(self._shape, self._lowered_transfers, self._lowered_error, rows,
                             self.PRECISIONS[self._precision])
+            if self._precision == 'f64-dmma':
+                nat.check(nat.lib.opl_mlp_set_engine(ws.pointer, 0))
             self._workspace = ws
         return ws
 
@@ -262,8 +264,10 @@ class MLP(_KernelModel):
             (default: BFGS up to 500 weights, else L-BFGS; bias excluded from the count).
         error_func: ErrorFunc (default MeanSquaredError).
         jacobian_norm_break: Training ends when the gradient norm falls below this value.
-        precision: the one knob this build adds.  'f64' (default): FP64 DMMA kernels, objective and
-            gradient match the reference to 1e-10.  'tf32': tcgen05 TF32 tensor-core GEMMs with FP32
+        precision: the one knob this build adds.  'f64' (default): FP64 in, FP64 out, objective and
+            gradient match the reference to 1e-10; the large layer GEMMs run as exact INT8 digit products
+            on the tcgen05 tensor cores (Ozaki splitting), the small ones on FP64 DMMA.  'f64-dmma': every
+            GEMM on FP64 DMMA.  'tf32': tcgen05 TF32 tensor-core GEMMs with FP32
             accumulation (1e-3).  Defaults to the OPL_PRECISION environment variable.
     """
 

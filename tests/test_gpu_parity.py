@@ -27,9 +27,9 @@ def L():
     return learning_b200
 
 
-def _model(L, shape, transfers, eid, optimizer=None):
+def _model(L, shape, transfers, eid, optimizer=None, precision=None):
     return L.MLP(shape, transfers=make_transfers(L, transfers), error_func=make_error(L, eid),
-                 optimizer=optimizer or L.optimize.SteepestDescent())
+                 optimizer=optimizer or L.optimize.SteepestDescent(), precision=precision)
 
 
 # ----------------------------------------------------------------------------------------
@@ -82,17 +82,19 @@ def test_device_api_matches_host_api_and_probe(L, golden_meta, golden_objgrad):
     ((784, 256, 10), [(2, 0), (4, 0)], 1, 3000),           # config-2 layer shapes, split-K, 16-byte path
     ((785, 255, 11), [(2, 0), (4, 0)], 1, 1531),           # odd everything: 8-byte cp.async path, edge tiles
     ((512, 128, 128, 10), [(2, 0), (2, 0), (4, 0)], 1, 2048),   # config-3 shape
-    ((256, 192, 160, 10), [(1, 0), (3, 1.5), (0, 0)], 0, 1000),  # tanh / gaussian / linear + MSE
+    ((256, 192, 160, 10), [(1, 0), (3, 1.5), (0, 0)], 0, 1100),  # tanh / gaussian / linear + MSE
+    ((130, 140, 150, 65), [(4, 0), (2, 0), (2, 0)], 0, 1200),   # hidden softmax, wide output
     ((40, 70, 33, 65), [(4, 0), (2, 0), (2, 0)], 0, 517),   # hidden softmax, wide output
     ((3, 1), [(0, 0)], 0, 5),
 ])
-def test_objgrad_against_oracle_at_size(L, shape, transfers, eid, rows):
+@pytest.mark.parametrize("precision", ["f64", "f64-dmma"])   # INT8 (Ozaki) engine for the large GEMMs / DMMA everywhere
+def test_objgrad_against_oracle_at_size(L, shape, transfers, eid, rows, precision):
     rng = numpy.random.default_rng(hash(shape) % 1000)
     gen = mo.random_classification if eid == 1 else mo.random_regression
     x, y = gen(rows, shape[0], shape[-1], rng)
     w = mo.random_params(shape, rng)
     want_obj, want_grad = mo.objective_gradient(w, shape, transfers, eid, x, y, literal_softmax=rows < 2000)
-    model = _model(L, shape, transfers, eid)
+    model = _model(L, shape, transfers, eid, precision=precision)
     obj, grad = model._get_obj_jac(w.copy(), x, y)
     assert rel_err(obj, want_obj) <= TOL
     assert rel_err(grad, want_grad) <= TOL, rel_err(grad, want_grad)

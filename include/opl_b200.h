@@ -140,11 +140,10 @@ int opl_bench_gemm_tf32(int32_t layout, int32_t M, int32_t N, int32_t K, const f
                         float *ms_out);
 
 /* Validation hook for the FP64-on-INT8 (Ozaki) GEMM: C[M,N] = epi(A[M,K].B[K,N]), row-major FP64 device buffers.
- * variant: 0 = A read from shared memory by every MMA, 1 = A staged into TMEM by tcgen05.cp, 2 = by loader warps;
  * epi: 0 store, 1 tanh, 2 softplus, 3 gaussian (as the layer GEMMs fuse them).
  * slice_ms_out = time of the two digit-extraction passes, gemm_ms_out = tcgen05 INT8 GEMM (+ FP64 fold of K splits). */
 int opl_bench_gemm_ozaki(int32_t M, int32_t N, int32_t K, const double *a_dev, const double *b_dev, double *c_dev,
-                         int32_t variant, int32_t epi, int32_t iters, float *slice_ms_out, float *gemm_ms_out);
+                         int32_t epi, int32_t iters, float *slice_ms_out, float *gemm_ms_out);
 
 /* ---- stand-alone host-buffer forms of the plugin objects' own methods (not on the training
  *      path; they run the same row kernel so the classes stay usable on their own) ---- */

@@ -209,7 +209,7 @@ int int8_forward_layer(opl_mlp *ws, int l, const double *w, const double *in, in
     g.colmask = (!last && ws->masks && masked) ? ws->masks + ws->mask_off[l + 1] : nullptr;
     if (kp > OZ_MAX_K) return fail(OPL_E_STATE, "int8 forward: layer %d is wider than %d inputs", l, OZ_MAX_K);
     mark(ws, STAGE_FWD * 100 + l);
-    return launch_ozaki_gemm(a_dig, a_rows_pad, s->w_dig, np, kp, g, OZ_A_SMEM, ws->stream, &ws->launches);
+    return launch_ozaki_gemm(a_dig, a_rows_pad, s->w_dig, np, kp, g, ws->stream, &ws->launches);
 }
 
 // dW_l = A_l^T delta_l (+ db = 1^T delta_0 for l = 0) into the flat gradient
@@ -252,7 +252,7 @@ int int8_dw_layer(opl_mlp *ws, int l, const double *in, int64_t rows, double *gr
     g.ldaux = dout;
     mark(ws, STAGE_DW * 100 + l);
     // digit arrays are pitched by the PADDED row count of the resident batch
-    rc = launch_ozaki_gemm(a_dig, mp, s->d_dig, np, kp, g, OZ_A_SMEM, ws->stream, &ws->launches);
+    rc = launch_ozaki_gemm(a_dig, mp, s->d_dig, np, kp, g, ws->stream, &ws->launches);
     if (rc != OPL_OK) return rc;
     if (plan.splits > 1) {
         mark(ws, STAGE_DW_REDUCE * 100 + l);

@@ -15,18 +15,19 @@
 // split (`splits`) and folded in FP64 by the caller.
 //
 // Kernel: persistent, one CTA per SM, static tile schedule (n fastest).  Warp roles:
-//   warps 0..7  epilogue.  Drain: TMEM -> FP64 (magic-number int->double, Horner over the 6 diagonals, row scale)
-//               -> padded shared staging tile; the accumulators are then released, so the next tile's MMAs overlap
-//               the finish phase: column scale, bias, transfer function (FP64 exp/log), coalesced 16-byte stores.
-//   (warps 8..11 A loaders, OZ_A_WARPS only)
-//   warp n-2    TMA producer: per 128-wide k-block the 6 B digit tiles (64 x 128 B each, one barrier, double
-//               buffered), then the 6 A digit tiles (128 x 128 B each) through a 3-deep ring
-//   warp n-1    MMA issuer: A_p meets B_0..B_{5-p}; those B tiles are contiguous in shared memory and their
+//   warps 0..3 / 4..7  two epilogue groups taking alternate tiles.  Drain: TMEM -> FP64 registers (magic-number
+//               int->double, Horner over the 6 diagonals, row scale), 64 columns per thread; the accumulators are
+//               released right after, so the next tile's MMAs (and the other group's next drain) overlap this
+//               group's finish phase: column scale, bias, transfer function (FP64 exp/log), and stores that go
+//               through a per-warp shared patch to become 64-byte row segments.
+//   warp 8      TMA producer: per 128-wide k-block the 6 B digit tiles (64 x 128 B each, one barrier, double
+//               buffered) and the 6 A digit tiles (128 x 128 B each, one stage per digit = a whole k-block in flight)
+//   warp 9      MMA issuer: A_p meets B_0..B_{5-p}; those B tiles are contiguous in shared memory and their
 //               accumulators p..5 are contiguous in TMEM, so each A_p needs one tcgen05.mma of N = 64 (6-p)
-//               (two when N > 256) per K = 32 step: 32 MMAs per k-block, not 84.  With N >= 128 the SS form stays
-//               inside the SM's shared-memory bandwidth (OZ_A_SMEM, the default).  OZ_A_UTCCP / OZ_A_WARPS move
-//               the A tile into the spare 128 TMEM columns first (tcgen05.cp / loader warps + tcgen05.st) and
-//               read it from there (TS form); kept for comparison.
+//               (two when N > 256) per K = 32 step: 32 MMAs per k-block, not 84, and with N >= 128 the SS form stays
+//               inside the SM's shared-memory bandwidth.
+// Tried and dropped (profiles/r01_ozaki_gemm_variants_v3.txt): staging A in the spare TMEM columns by tcgen05.cp
+// (no faster than SS once the MMAs were merged: the copy serialises with the MMAs) or by loader warps + tcgen05.st.
 #include <cudaTypedefs.h>
 
 #include <algorithm>
@@ -40,21 +41,15 @@ namespace {
 
 constexpr int OZ_A_BYTES = OZ_BM * 128;        // 16 KB: 128 rows x 128 int8
 constexpr int OZ_B_BYTES = OZ_BN * 128;        //  8 KB
-constexpr int OZ_A_STAGES = 3;
-constexpr int OZ_TSLOTS = 4;                   // A staging slots in TMEM: 32 columns each at columns 384..511
-constexpr int OZ_TSLOT_COL0 = OZ_S * OZ_BN;    // 384
-constexpr int OZ_ZLD = 66;                     // doubles per staged row (padded: conflict-free 16-byte row-per-thread stores)
-constexpr int OZ_Z_BYTES = OZ_BM * OZ_ZLD * 8;
+constexpr int OZ_EPI_WARPS = 16;               // 4 per sub-partition: the FP64 chains of the finish phase need the TLP
+constexpr int OZ_ZC = OZ_BN / 4;               // columns of a tile row one epilogue thread keeps in registers
 constexpr int OZ_OFF_A = 2 * OZ_S * OZ_B_BYTES;                 // 96 KB of B first (1024-aligned tiles)
-constexpr int OZ_OFF_Z = OZ_OFF_A + OZ_A_STAGES * OZ_A_BYTES;
-constexpr int OZ_OFF_BAR = OZ_OFF_Z + OZ_Z_BYTES;
+constexpr int OZ_OFF_PATCH = OZ_OFF_A + OZ_S * OZ_A_BYTES;      // + 96 KB of A: one stage per digit
+constexpr int OZ_OFF_BAR = OZ_OFF_PATCH + OZ_EPI_WARPS * 2048;   // per warp: 32 rows x 8 columns, 16-byte chunks swizzled
 constexpr int OZ_SMEM = OZ_OFF_BAR + 256 + 1024;
-constexpr int OZ_EPI_WARPS = 8;
-constexpr int OZ_LOADER_WARPS = 4;                             // OZ_A_WARPS only
-constexpr int OZ_THREADS_BASE = 32 * (OZ_EPI_WARPS + 2);       // 320
-constexpr int OZ_THREADS_LOADERS = 32 * (OZ_EPI_WARPS + OZ_LOADER_WARPS + 2);   // 448
+constexpr int OZ_THREADS = 32 * (OZ_EPI_WARPS + 2);            // 576
 static_assert(OZ_SMEM <= 232448, "shared memory budget");
-static_assert(OZ_TSLOT_COL0 + OZ_TSLOTS * 32 <= 512, "TMEM budget");
+static_assert(OZ_S * OZ_BN <= 512, "TMEM budget");
 
 __device__ __forceinline__ uint32_t oz_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void oz_mbar_init(uint64_t *bar, uint32_t count) {
@@ -101,33 +96,10 @@ __device__ __forceinline__ void oz_umma_ss(uint32_t tmem_d, uint64_t adesc, uint
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
         : "memory");
 }
-// same with A read from TMEM (lane = row, 8 columns = 32 int8 along k)
-__device__ __forceinline__ void oz_umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
-        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
-        : "memory");
-}
-// shared -> TMEM: 128 lanes x 32 bytes
-__device__ __forceinline__ void oz_utccp(uint32_t tmem_dst, uint64_t sdesc) {
-    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(tmem_dst), "l"(sdesc) : "memory");
-}
 __device__ __forceinline__ void oz_tmem_ld8(uint32_t taddr, int32_t (&v)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "r"(taddr));
-}
-__device__ __forceinline__ void oz_tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
-        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
-        "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]),
-        "r"(v[29]), "r"(v[30]), "r"(v[31])
-        : "memory");
 }
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (see gemm_tf32.cu)
 __device__ __forceinline__ uint64_t oz_desc(uint32_t saddr) {
@@ -150,11 +122,106 @@ __device__ __forceinline__ bool oz_elect_one() {
         : "=r"(pred));
     return pred != 0;
 }
-__device__ __forceinline__ void oz_epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(OZ_EPI_WARPS * 32) : "memory"); }
 
 // exact int32 -> double without the conversion pipe: bits(2^52 + 2^31 + v) - (2^52 + 2^31)
 __device__ __forceinline__ double oz_i2d(int32_t v) {
     return __hiloint2double(0x43300000, (int)((uint32_t)v ^ 0x80000000u)) - 4503601774854144.0;
+}
+
+// ---- branch-free FP64 softplus + logistic for the fused epilogue ----------------------------------------------
+// The library exp / log / division cost ~200 FP64-pipe instructions per element and their rare-path branches keep
+// the 8 columns a thread works on from interleaving; the epilogue of the forward GEMM is FP64-pipe bound, so these
+// are written out: t = exp(-|z|), u = 1 + t, softplus = max(z,0) + log(u), logistic = z >= 0 ? 1/u : t/u
+// (for z < 0 this IS the reference's log(1 + exp(z)); for z >= 0 it is the same value without the overflow detour
+// of calculate.py:128-135).  ~60 FP64 instructions, errors ~1 ulp.
+// W elements advance in lockstep through every step, so W independent FP64 chains are adjacent in program order.
+template <int W>
+__device__ __forceinline__ void oz_rcp_n(const double (&x)[W], double (&y)[W]) {   // x in [1, 4]: approximation + 2 Newton steps
+    double e[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y[i]) : "d"(x[i]));
+#pragma unroll
+    for (int i = 0; i < W; ++i) e[i] = fma(-x[i], y[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < W; ++i) y[i] = fma(y[i], e[i], y[i]);
+#pragma unroll
+    for (int i = 0; i < W; ++i) e[i] = fma(-x[i], y[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < W; ++i) y[i] = fma(y[i], e[i], y[i]);
+}
+template <int W>
+__device__ __forceinline__ void oz_softplus_logistic_n(const double (&z)[W], double (&sp)[W], double (&sg)[W]) {
+    // ---- t = exp(-|z|) (0 below -708): n = rint(a log2 e), r = a - n ln2, Taylor degree 13, exponent insert ----
+    double a[W], t[W], nd[W], r[W], q[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) a[i] = -fabs(z[i]);
+#pragma unroll
+    for (int i = 0; i < W; ++i) t[i] = fma(a[i], 1.4426950408889634, 6755399441055744.0);
+#pragma unroll
+    for (int i = 0; i < W; ++i) nd[i] = t[i] - 6755399441055744.0;
+#pragma unroll
+    for (int i = 0; i < W; ++i) r[i] = fma(nd[i], -6.93147180369123816490e-01, a[i]);
+#pragma unroll
+    for (int i = 0; i < W; ++i) r[i] = fma(nd[i], -1.90821492927058770002e-10, r[i]);
+    // Estrin's scheme: 16 operations at dependency depth 4 instead of Horner's 13 (the finish phase is bound by the
+    // latency of dependent FP64 operations, not by their count)
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        const double x = r[i], x2 = x * x, x4 = x2 * x2, x8 = x4 * x4;
+        const double a0 = fma(x, 1.0, 1.0);                                          // 1/0! + x/1!
+        const double a1 = fma(x, 0.16666666666666666, 0.5);                          // 1/2! + x/3!
+        const double a2 = fma(x, 0.008333333333333333, 0.041666666666666664);        // 1/4! + x/5!
+        const double a3 = fma(x, 0.0001984126984126984, 0.001388888888888889);       // 1/6! + x/7!
+        const double a4 = fma(x, 2.7557319223985893e-06, 2.48015873015873e-05);      // 1/8! + x/9!
+        const double a5 = fma(x, 2.505210838544172e-08, 2.755731922398589e-07);      // 1/10! + x/11!
+        const double a6 = fma(x, 1.6059043836821613e-10, 2.08767569878681e-09);      // 1/12! + x/13!
+        const double b0 = fma(a1, x2, a0), b1 = fma(a3, x2, a2), b2 = fma(a5, x2, a4);
+        const double d0 = fma(b1, x4, b0), d1 = fma(a6, x4, b2);
+        q[i] = fma(d1, x8, d0);
+    }
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        const double scaled = __hiloint2double(__double2hiint(q[i]) + (__double2loint(t[i]) << 20), __double2loint(q[i]));
+        t[i] = a[i] < -708.0 ? 0.0 : scaled;
+    }
+    // ---- u = 1 + t in [1, 2]; 1/u; log(u) with the fdlibm e_log.c kernel ----
+    double u[W], ru[W], m[W], dk[W], f[W], d2[W], rd[W], s_[W], w[W], R[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) u[i] = 1.0 + t[i];
+    oz_rcp_n<W>(u, ru);
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        const bool big = u[i] > 1.4142135623730951;
+        m[i] = big ? u[i] * 0.5 : u[i];
+        dk[i] = big ? 1.0 : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < W; ++i) f[i] = m[i] - 1.0;
+#pragma unroll
+    for (int i = 0; i < W; ++i) d2[i] = 2.0 + f[i];
+    oz_rcp_n<W>(d2, rd);
+#pragma unroll
+    for (int i = 0; i < W; ++i) s_[i] = f[i] * rd[i];
+#pragma unroll
+    for (int i = 0; i < W; ++i) w[i] = s_[i] * s_[i];
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        const double x = w[i], x2 = x * x, x4 = x2 * x2;
+        const double e0 = fma(x, 3.999999999940941908e-01, 6.666666666666735130e-01);
+        const double e1 = fma(x, 2.222219843214978396e-01, 2.857142874366239149e-01);
+        const double e2 = fma(x, 1.531383769920937332e-01, 1.818357216161805012e-01);
+        const double g0 = fma(e1, x2, e0), g1 = fma(1.479819860511658591e-01, x2, e2);
+        R[i] = fma(g1, x4, g0) * x;
+    }
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        const double hfsq = 0.5 * f[i] * f[i];
+        const double l = dk[i] * 6.93147180369123816490e-01 -
+                         ((hfsq - (s_[i] * (hfsq + R[i]) + dk[i] * 1.90821492927058770002e-10)) - f[i]);
+        const double spv = fmax(z[i], 0.0) + l, sgv = z[i] >= 0.0 ? ru[i] : t[i] * ru[i];
+        sp[i] = z[i] != z[i] ? z[i] : spv;
+        sg[i] = z[i] != z[i] ? z[i] : sgv;
+    }
 }
 
 struct OzTile {
@@ -173,44 +240,63 @@ __device__ __forceinline__ OzTile oz_tile(const OzakiArgs &p, int t, int tiles_m
     return r;
 }
 
-template <int VARIANT>
-__global__ void __launch_bounds__(VARIANT == OZ_A_WARPS ? OZ_THREADS_LOADERS : OZ_THREADS_BASE, 1)
+// one 8-column chunk of a warp's 32 rows: registers -> per-warp shared patch -> 64-byte row segments in global memory.
+// Patch row = 64 bytes = four 16-byte chunks, chunk c of row r stored at c ^ ((r >> 1) & 3): conflict-free both ways.
+__device__ __forceinline__ void oz_store_chunk(double *patch, const double (&v)[8], double *base, int64_t ld, int row0, int col0,
+                                               int M, int N, bool vec, int lane) {
+    double2 *pw = reinterpret_cast<double2 *>(patch + lane * 8);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) pw[j ^ ((lane >> 1) & 3)] = make_double2(v[2 * j], v[2 * j + 1]);
+    __syncwarp();
+    const int pc = lane & 3, gcol = col0 + 2 * pc;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int prow = (lane >> 2) + 8 * i, grow = row0 + prow;
+        const double2 q = *reinterpret_cast<const double2 *>(patch + prow * 8 + 2 * (pc ^ ((prow >> 1) & 3)));
+        if (grow < M) {
+            double *dst = base + (int64_t)grow * ld + gcol;
+            if (vec && gcol + 1 < N) {
+                *reinterpret_cast<double2 *>(dst) = q;
+            } else {
+                if (gcol < N) dst[0] = q.x;
+                if (gcol + 1 < N) dst[1] = q.y;
+            }
+        }
+    }
+    __syncwarp();
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(OZ_THREADS, 1)
 ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const OzakiArgs p) {
     extern __shared__ uint8_t oz_smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(oz_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint8_t *sB = smem;                                   // 2 x 6 x 8 KB
-    uint8_t *sA = smem + OZ_OFF_A;                        // OZ_A_STAGES x 16 KB
-    double *sZ = reinterpret_cast<double *>(smem + OZ_OFF_Z);
+    uint8_t *sA = smem + OZ_OFF_A;                        // 6 x 16 KB: one stage per digit
+    double *sPatch = reinterpret_cast<double *>(smem + OZ_OFF_PATCH);
     uint64_t *a_full = reinterpret_cast<uint64_t *>(smem + OZ_OFF_BAR);
-    uint64_t *a_empty = a_full + OZ_A_STAGES;
-    uint64_t *b_full = a_empty + OZ_A_STAGES;
+    uint64_t *a_empty = a_full + OZ_S;
+    uint64_t *b_full = a_empty + OZ_S;
     uint64_t *b_empty = b_full + 2;
-    uint64_t *t_full = b_empty + 2;
-    uint64_t *t_empty = t_full + OZ_TSLOTS;
-    uint64_t *acc_full = t_empty + OZ_TSLOTS;
+    uint64_t *acc_full = b_empty + 2;
     uint64_t *acc_empty = acc_full + 1;
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(acc_empty + 1);
 
-    // warp roles: 0..7 epilogue, (8..15 A loaders), second-to-last TMA producer, last MMA issuer (the arbiter favours
-    // the highest warp id of a sub-partition, and the single issuing thread is the latency-critical one)
+    // warp roles: 0..15 epilogue (warp w: TMEM lane quarter w % 4, column quarter w / 4), 16 TMA producer, 17 MMA issuer (the
+    // arbiter favours the highest warp id of a sub-partition, and the issuing thread is the latency-critical one)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nwarps = (VARIANT == OZ_A_WARPS ? OZ_THREADS_LOADERS : OZ_THREADS_BASE) / 32;
-    const int producer_warp = nwarps - 2, mma_warp = nwarps - 1;
+    constexpr int producer_warp = OZ_EPI_WARPS, mma_warp = OZ_EPI_WARPS + 1;
     const int tiles_m = (p.M + OZ_BM - 1) / OZ_BM, tiles_n = (p.N + OZ_BN - 1) / OZ_BN;
     const int ntiles = tiles_m * tiles_n * p.splits;
 
     if (warp == producer_warp && lane == 0) {
-        for (int s = 0; s < OZ_A_STAGES; ++s) {
+        for (int s = 0; s < OZ_S; ++s) {
             oz_mbar_init(&a_full[s], 1);
-            oz_mbar_init(&a_empty[s], VARIANT == OZ_A_WARPS ? 4 : 1);
+            oz_mbar_init(&a_empty[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
             oz_mbar_init(&b_full[s], 1);
             oz_mbar_init(&b_empty[s], 1);
-        }
-        for (int s = 0; s < OZ_TSLOTS; ++s) {
-            oz_mbar_init(&t_full[s], 4);
-            oz_mbar_init(&t_empty[s], 1);
         }
         oz_mbar_init(acc_full, 1);
         oz_mbar_init(acc_empty, OZ_EPI_WARPS);
@@ -223,8 +309,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     oz_fence_before();
     __syncthreads();
     oz_fence_after();
-    const uint32_t tmem_base = 0;                   // the CTA owns all 512 columns, so the allocation starts at column 0
-    if (*tmem_ptr != 0) __trap();
+    if (*tmem_ptr != 0) __trap();                   // the CTA owns all 512 columns, so the allocation starts at column 0
 
     if (warp == producer_warp) {
         // ============ TMA producer (warp-uniform control flow, one elected lane issues) ============
@@ -242,14 +327,11 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     for (int q = 0; q < OZ_S; ++q) oz_tma_3d(sB + (bs * OZ_S + q) * OZ_B_BYTES, &tmB, k0, tl.n0, q, &b_full[bs]);
                 }
 #pragma unroll
-                for (int pp = 0; pp < OZ_S; ++pp) {
-                    // a_it = 6 kbt + pp: stage and phase are compile-time functions of pp (6 % OZ_A_STAGES == 0)
-                    constexpr int per = OZ_S / OZ_A_STAGES;
-                    const int s = pp % OZ_A_STAGES;
-                    oz_wait(&a_empty[s], ((kbt * per + pp / OZ_A_STAGES) & 1) ^ 1);
+                for (int pp = 0; pp < OZ_S; ++pp) {   // digit pp always travels through stage pp
+                    oz_wait(&a_empty[pp], (kbt & 1) ^ 1);
                     if (leader) {
-                        oz_expect_tx(&a_full[s], OZ_A_BYTES);
-                        oz_tma_3d(sA + s * OZ_A_BYTES, &tmA, k0, tl.m0, pp, &a_full[s]);
+                        oz_expect_tx(&a_full[pp], OZ_A_BYTES);
+                        oz_tma_3d(sA + pp * OZ_A_BYTES, &tmA, k0, tl.m0, pp, &a_full[pp]);
                     }
                 }
             }
@@ -258,19 +340,18 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // ============ MMA issuer (warp-uniform control flow, one elected lane issues) ============
         // The B digit tiles of one k-block are contiguous 8 KB blocks of 64 rows, and the accumulators of diagonals
         // p..5 are contiguous TMEM columns, so A_p . [B_0; ..; B_{5-p}]^T is ONE MMA of N = 64 (6 - p) columns
-        // (cut at N = 256): 8 instructions per K = 32 step instead of 21.  All 512 TMEM columns are ours, so the
-        // allocation starts at column 0 and every TMEM address below is a compile-time constant; shared-memory
-        // descriptors differ only in their low word (start address >> 4), by compile-time offsets.
+        // (cut at N = 256): 8 instructions per K = 32 step instead of 21.  All 512 TMEM columns are ours, so every
+        // TMEM address below is a compile-time constant; shared-memory descriptors differ only in their low word
+        // (start address >> 4), by compile-time offsets.
         // instruction descriptor: D = S32 (2), A = B = signed INT8 (1), both K-major, N>>3, M>>4
         constexpr uint32_t idesc0 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BM >> 4) << 24);
         const bool leader = oz_elect_one();
         const uint32_t desc_hi = (uint32_t)(oz_desc(0) >> 32);
         const uint32_t a_lo0 = (uint32_t)oz_desc(oz_smem_u32(sA)), b_lo0 = (uint32_t)oz_desc(oz_smem_u32(sB));
-        uint32_t kbt = 0, acc_it = 0;               // acc_it counts tiles that use the accumulators
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        uint32_t kbt = 0, local = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++local) {
             const OzTile tl = oz_tile(p, t, tiles_m, tiles_n);
-            if (tl.nkb == 0) continue;              // (the epilogue skips the accumulator handshake as well)
-            oz_wait(acc_empty, (acc_it & 1) ^ 1);
+            oz_wait(acc_empty, (local & 1) ^ 1);     // the previous tile has left TMEM
             oz_fence_after();
             for (int kb = 0; kb < tl.nkb; ++kb, ++kbt) {
                 const uint32_t bs = kbt & 1;
@@ -279,26 +360,10 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 oz_wait(&b_full[bs], (kbt >> 1) & 1);
 #pragma unroll
                 for (int pp = 0; pp < OZ_S; ++pp) {
-                    constexpr int per = OZ_S / OZ_A_STAGES;
-                    const int s = pp % OZ_A_STAGES;
-                    const uint32_t a_par = (kbt * per + pp / OZ_A_STAGES) & 1;
-                    const uint32_t slot = (kbt * OZ_S + pp) % OZ_TSLOTS;      // TMEM staging slot (TS variants)
-                    const uint32_t a_lo = a_lo0 + (uint32_t)((s * OZ_A_BYTES) >> 4);
-                    const uint32_t ta = (uint32_t)OZ_TSLOT_COL0 + slot * 32;
-                    if (VARIANT == OZ_A_WARPS) {
-                        oz_wait(&t_full[slot], ((kbt * OZ_S + pp) / OZ_TSLOTS) & 1);
-                    } else {
-                        oz_wait(&a_full[s], a_par);
-                    }
+                    const uint32_t a_lo = a_lo0 + (uint32_t)((pp * OZ_A_BYTES) >> 4);
+                    oz_wait(&a_full[pp], kbt & 1);
                     oz_fence_after();
                     if (leader) {
-                        if (VARIANT == OZ_A_UTCCP) {
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) oz_utccp(ta + k * 8, oz_desc_join(desc_hi, a_lo + k * 2));
-                            oz_commit(&a_empty[s]);            // smem stage reusable once the copies have read it
-                        }
-                        constexpr int dummy = 0;
-                        (void)dummy;
                         const int nq = OZ_S - pp;              // B digits this A digit meets
 #pragma unroll
                         for (int q0 = 0; q0 < nq; q0 += 4) {   // chunks of <= 4 digits = N <= 256
@@ -309,14 +374,10 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             for (int k = 0; k < 4; ++k) {      // 4 x K32 per 128-byte row, +32 bytes each
                                 const uint32_t acc = (pp == 0 && k == 0) ? first : 1u;
                                 const uint64_t bd = oz_desc_join(desc_hi, b_lo + (uint32_t)((q0 * OZ_B_BYTES + k * 32) >> 4));
-                                if (VARIANT == OZ_A_SMEM)
-                                    oz_umma_ss(d_tmem, oz_desc_join(desc_hi, a_lo + k * 2), bd, idesc, acc);
-                                else
-                                    oz_umma_ts(d_tmem, ta + k * 8, bd, idesc, acc);
+                                oz_umma_ss(d_tmem, oz_desc_join(desc_hi, a_lo + k * 2), bd, idesc, acc);
                             }
                         }
-                        if (VARIANT == OZ_A_SMEM) oz_commit(&a_empty[s]);
-                        if (VARIANT == OZ_A_WARPS) oz_commit(&t_empty[slot]);
+                        oz_commit(&a_empty[pp]);
                         if (pp == OZ_S - 1) oz_commit(&b_empty[bs]);
                     }
                     __syncwarp();
@@ -324,156 +385,82 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             if (leader) oz_commit(acc_full);
             __syncwarp();
-            ++acc_it;
         }
-    } else if (warp < OZ_EPI_WARPS) {
+    } else {
         // ============ epilogue ============
-        const int ew = warp;
+        // Drain: TMEM -> FP64 registers (magic-number int->double, Horner over the 6 diagonals, row scale), 32 columns
+        // per thread; the accumulators are released right after, so the next tile's MMAs overlap the finish phase:
+        // column scale, bias, transfer function, stores.
+        const int half = warp >> 2;                   // columns [16 half, 16 half + 16) of the tile
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
-        const int half = ew >> 2;                     // drain: columns [32*half, 32*half+32)
-        const int lrow = quarter * 32 + lane;         // drain: one accumulator row per thread
-        uint32_t acc_it = 0;
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-            const OzTile tl = oz_tile(p, t, tiles_m, tiles_n);
-            // ---- drain: TMEM -> FP64 -> staging tile ----
-            if (tl.nkb > 0) {
-                oz_wait(acc_full, acc_it & 1);
-                oz_fence_after();
-                ++acc_it;
-            }
-            {
-                const int row = tl.m0 + lrow;
-                const double ea = (row < p.M ? p.scale_a[row] : 0.0) * (1.0 / 65536.0);
-                double *zrow = sZ + lrow * OZ_ZLD + half * 32;
-#pragma unroll 1
-                for (int c0 = 0; c0 < 32; c0 += 8) {
-                    double acc[8];
-                    if (tl.nkb > 0) {
-                        int32_t v[OZ_S][8];
-#pragma unroll
-                        for (int d = 0; d < OZ_S; ++d)
-                            oz_tmem_ld8(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(d * OZ_BN + half * 32 + c0), v[d]);
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            double s = oz_i2d(v[OZ_S - 1][j]);
-#pragma unroll
-                            for (int d = OZ_S - 2; d >= 0; --d) s = fma(s, 1.0 / 256.0, oz_i2d(v[d][j]));
-                            acc[j] = s * ea;
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) acc[j] = 0.0;
-                    }
-#pragma unroll
-                    for (int j = 0; j < 8; j += 2) *reinterpret_cast<double2 *>(zrow + c0 + j) = make_double2(acc[j], acc[j + 1]);
-                }
-            }
-            if (tl.nkb > 0) {
-                oz_fence_before();
-                __syncwarp();
-                if (lane == 0) oz_arrive(acc_empty);          // accumulators free: the next tile's MMAs may start
-            }
-            oz_epi_bar();
-            // ---- finish: warp ew owns staged rows [16 ew, 16 ew + 16), lane owns columns 2 lane, 2 lane + 1 ----
-            {
-                const int col = tl.n0 + 2 * lane;
-                const bool c0ok = col < p.N, c1ok = col + 1 < p.N;
-                const double eb0 = c0ok ? p.scale_b[col] : 0.0, eb1 = c1ok ? p.scale_b[col + 1] : 0.0;
-                const double bi0 = (p.bias && c0ok) ? p.bias[col] : 0.0, bi1 = (p.bias && c1ok) ? p.bias[col + 1] : 0.0;
-                const double mk0 = (p.colmask && c0ok) ? p.colmask[col] : 1.0, mk1 = (p.colmask && c1ok) ? p.colmask[col + 1] : 1.0;
-                double *C = p.C + (int64_t)tl.split * p.split_stride;
-                const bool vec_c = ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && c1ok;
-                const bool vec_x = p.aux_out && ((p.ldaux & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.aux_out) & 15) == 0) && c1ok;
-#pragma unroll 2
-                for (int r = 0; r < 16; ++r) {
-                    const int lr = ew * 16 + r;
-                    const int row = tl.m0 + lr;
-                    if (row >= p.M) break;
-                    const double2 zz = *reinterpret_cast<const double2 *>(sZ + lr * OZ_ZLD + 2 * lane);
-                    const double z0 = zz.x * eb0 + bi0, z1 = zz.y * eb1 + bi1;
-                    double r0, r1, x0 = 0.0, x1 = 0.0;
-                    switch (p.epi) {
-                        case OZ_EPI_SOFTPLUS: {
-                            const double e0 = exp(z0), e1 = exp(z1);
-                            const double d0 = 1.0 + e0, d1 = 1.0 + e1;
-                            r0 = log(d0);
-                            r1 = log(d1);
-                            if (isinf(r0)) r0 = z0;
-                            if (isinf(r1)) r1 = z1;
-                            x0 = isinf(e0) ? 1.0 : e0 / d0;
-                            x1 = isinf(e1) ? 1.0 : e1 / d1;
-                            break;
-                        }
-                        case OZ_EPI_TANH:
-                            r0 = tanh(z0);
-                            r1 = tanh(z1);
-                            break;
-                        case OZ_EPI_GAUSSIAN:
-                            r0 = exp(-(z0 * z0 / p.tparam));
-                            r1 = exp(-(z1 * z1 / p.tparam));
-                            x0 = -2.0 * z0 * r0 / p.tparam;
-                            x1 = -2.0 * z1 * r1 / p.tparam;
-                            break;
-                        default:
-                            r0 = z0;
-                            r1 = z1;
-                    }
-                    r0 *= mk0;
-                    r1 *= mk1;
-                    if (p.epi == OZ_EPI_GAUSSIAN) {   // derivative uses the masked output, as the reference does
-                        x0 = -2.0 * z0 * r0 / p.tparam;
-                        x1 = -2.0 * z1 * r1 / p.tparam;
-                    }
-                    double *cp = C + (int64_t)row * p.ldc + col;
-                    if (vec_c) {
-                        *reinterpret_cast<double2 *>(cp) = make_double2(r0, r1);
-                    } else {
-                        if (c0ok) cp[0] = r0;
-                        if (c1ok) cp[1] = r1;
-                    }
-                    if (p.aux_out && (p.epi == OZ_EPI_SOFTPLUS || p.epi == OZ_EPI_GAUSSIAN)) {
-                        double *xp = p.aux_out + (int64_t)row * p.ldaux + col;
-                        if (vec_x) {
-                            *reinterpret_cast<double2 *>(xp) = make_double2(x0, x1);
-                        } else {
-                            if (c0ok) xp[0] = x0;
-                            if (c1ok) xp[1] = x1;
-                        }
-                    }
-                }
-            }
-            oz_epi_bar();                                     // staging tile free for the next drain
-        }
-    } else if (VARIANT == OZ_A_WARPS) {
-        // ============ A loaders: shared (128B-swizzled rows) -> registers -> TMEM ============
-        const int quarter = warp & 3;
         const int lrow = quarter * 32 + lane;
-        uint32_t a_it = 0;
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        double *patch = sPatch + warp * 256;
+        uint32_t local = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++local) {
             const OzTile tl = oz_tile(p, t, tiles_m, tiles_n);
-            for (int i = 0; i < tl.nkb * OZ_S; ++i, ++a_it) {
-                const uint32_t s = a_it % OZ_A_STAGES, slot = a_it % OZ_TSLOTS;
-                oz_wait(&a_full[s], (a_it / OZ_A_STAGES) & 1);
-                const uint8_t *rowp = sA + s * OZ_A_BYTES + lrow * 128;
-                uint32_t v[32];
+            const int row = tl.m0 + lrow;
+            const double ea = (row < p.M ? p.scale_a[row] : 0.0) * (1.0 / 65536.0);
+            double z[OZ_ZC];
+            oz_wait(acc_full, local & 1);
+            oz_fence_after();
+#pragma unroll
+            for (int c0 = 0; c0 < OZ_ZC; c0 += 8) {
+                int32_t v[OZ_S][8];
+#pragma unroll
+                for (int d = 0; d < OZ_S; ++d)
+                    oz_tmem_ld8(((uint32_t)(quarter * 32) << 16) + (uint32_t)(d * OZ_BN + half * OZ_ZC + c0), v[d]);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const uint4 q = *reinterpret_cast<const uint4 *>(rowp + ((j ^ (lrow & 7)) << 4));
-                    v[4 * j + 0] = q.x;
-                    v[4 * j + 1] = q.y;
-                    v[4 * j + 2] = q.z;
-                    v[4 * j + 3] = q.w;
+                    double s = oz_i2d(v[OZ_S - 1][j]);
+#pragma unroll
+                    for (int d = OZ_S - 2; d >= 0; --d) s = fma(s, 1.0 / 256.0, oz_i2d(v[d][j]));
+                    z[c0 + j] = s * ea;
                 }
-                __syncwarp();
-                if (lane == 0) oz_arrive(&a_empty[s]);        // this warp's 32 rows are in registers
-                oz_wait(&t_empty[slot], ((a_it / OZ_TSLOTS) & 1) ^ 1);
-                oz_fence_after();
-                oz_tmem_st32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(OZ_TSLOT_COL0 + slot * 32), v);
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                oz_fence_before();
-                __syncwarp();
-                if (lane == 0) oz_arrive(&t_full[slot]);
+            }
+            oz_fence_before();
+            __syncwarp();
+            if (lane == 0) oz_arrive(acc_empty);              // accumulators free again
+            // ---- finish: 2 chunks of 8 columns ----
+            double *C = p.C + (int64_t)tl.split * p.split_stride;
+            const bool vec_c = ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+            const bool want_x = p.aux_out && (EPI == OZ_EPI_SOFTPLUS || EPI == OZ_EPI_GAUSSIAN);
+            const bool vec_x = want_x && ((p.ldaux & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.aux_out) & 15) == 0);
+            const int row0 = tl.m0 + quarter * 32;
+#pragma unroll
+            for (int ch = 0; ch < OZ_ZC / 8; ++ch) {
+                const int col0 = tl.n0 + half * OZ_ZC + ch * 8;
+                double r[8], x[8], zz[8], mk[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int col = col0 + j;
+                    const bool ok = col < p.N;
+                    const double eb = ok ? __ldg(p.scale_b + col) : 0.0;
+                    const double bi = (p.bias && ok) ? __ldg(p.bias + col) : 0.0;
+                    mk[j] = (p.colmask && ok) ? __ldg(p.colmask + col) : 1.0;
+                    zz[j] = z[ch * 8 + j] * eb + bi;
+                    x[j] = 0.0;
+                }
+                // the transfer function of all 8 columns in ONE basic block, so the FP64 chains interleave
+                if (EPI == OZ_EPI_SOFTPLUS) {
+                    oz_softplus_logistic_n<8>(zz, r, x);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) r[j] *= mk[j];
+                } else if (EPI == OZ_EPI_TANH) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) r[j] = tanh(zz[j]) * mk[j];
+                } else if (EPI == OZ_EPI_GAUSSIAN) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        r[j] = exp(-(zz[j] * zz[j] / p.tparam)) * mk[j];
+                        x[j] = -2.0 * zz[j] * r[j] / p.tparam;   // derivative uses the masked output, as the reference does
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) r[j] = zz[j] * mk[j];
+                }
+                oz_store_chunk(patch, r, C, p.ldc, row0, col0, p.M, p.N, vec_c, lane);
+                if (want_x) oz_store_chunk(patch, x, p.aux_out, p.ldaux, row0, col0, p.M, p.N, vec_x, lane);
             }
         }
     }
@@ -481,7 +468,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     __syncthreads();
     if (warp == mma_warp) {
         oz_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(0u), "r"(512u));
     }
 }
 
@@ -722,35 +709,31 @@ int ozaki_slice_cols_transposed(const double *src, int64_t rows, int64_t cols, i
 }
 
 int launch_ozaki_gemm(const int8_t *a_slices, int64_t a_rows_pad, const int8_t *b_slices, int64_t b_rows_pad, int64_t k_pad,
-                      const OzakiArgs &args, int variant, cudaStream_t stream, int64_t *launches) {
+                      const OzakiArgs &args, cudaStream_t stream, int64_t *launches) {
     if (args.M <= 0 || args.N <= 0) return OPL_OK;
-    if (args.k_per_split % 128 || args.k_per_split > OZ_MAX_K || args.splits < 1)
-        return fail(OPL_E_ARG, "ozaki GEMM: k_per_split must be a multiple of 128 and <= %d", OZ_MAX_K);
+    if (args.k_per_split % 128 || args.k_per_split > OZ_MAX_K || args.splits < 1 ||
+        (int64_t)args.k_per_split * (args.splits - 1) >= args.K)
+        return fail(OPL_E_ARG, "ozaki GEMM: k_per_split must be a multiple of 128, <= %d, and every split non-empty", OZ_MAX_K);
     CUtensorMap ta, tb;
     int rc = oz_tensor_map(&ta, a_slices, a_rows_pad, k_pad, OZ_BM);
     if (rc == OPL_OK) rc = oz_tensor_map(&tb, b_slices, b_rows_pad, k_pad, OZ_BN);
     if (rc != OPL_OK) return rc;
     static bool configured = false;
     if (!configured) {
-        OPL_CUDA(cudaFuncSetAttribute(ozaki_gemm_kernel<OZ_A_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
-        OPL_CUDA(cudaFuncSetAttribute(ozaki_gemm_kernel<OZ_A_UTCCP>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
-        OPL_CUDA(cudaFuncSetAttribute(ozaki_gemm_kernel<OZ_A_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
+        OPL_CUDA(cudaFuncSetAttribute(ozaki_gemm_kernel<OZ_EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
+        OPL_CUDA(cudaFuncSetAttribute(ozaki_gemm_kernel<OZ_EPI_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
+        OPL_CUDA(cudaFuncSetAttribute(ozaki_gemm_kernel<OZ_EPI_SOFTPLUS>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
+        OPL_CUDA(cudaFuncSetAttribute(ozaki_gemm_kernel<OZ_EPI_GAUSSIAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
         configured = true;
     }
     const int64_t tiles = ceil_div(args.M, OZ_BM) * ceil_div(args.N, OZ_BN) * args.splits;
     const unsigned grid = (unsigned)std::min<int64_t>(tiles, sm_count());
-    switch (variant) {
-        case OZ_A_SMEM:
-            ozaki_gemm_kernel<OZ_A_SMEM><<<grid, OZ_THREADS_BASE, OZ_SMEM, stream>>>(ta, tb, args);
-            break;
-        case OZ_A_UTCCP:
-            ozaki_gemm_kernel<OZ_A_UTCCP><<<grid, OZ_THREADS_BASE, OZ_SMEM, stream>>>(ta, tb, args);
-            break;
-        case OZ_A_WARPS:
-            ozaki_gemm_kernel<OZ_A_WARPS><<<grid, OZ_THREADS_LOADERS, OZ_SMEM, stream>>>(ta, tb, args);
-            break;
-        default:
-            return fail(OPL_E_ARG, "ozaki GEMM: unknown variant %d", variant);
+    switch (args.epi) {
+        case OZ_EPI_STORE: ozaki_gemm_kernel<OZ_EPI_STORE><<<grid, OZ_THREADS, OZ_SMEM, stream>>>(ta, tb, args); break;
+        case OZ_EPI_TANH: ozaki_gemm_kernel<OZ_EPI_TANH><<<grid, OZ_THREADS, OZ_SMEM, stream>>>(ta, tb, args); break;
+        case OZ_EPI_SOFTPLUS: ozaki_gemm_kernel<OZ_EPI_SOFTPLUS><<<grid, OZ_THREADS, OZ_SMEM, stream>>>(ta, tb, args); break;
+        case OZ_EPI_GAUSSIAN: ozaki_gemm_kernel<OZ_EPI_GAUSSIAN><<<grid, OZ_THREADS, OZ_SMEM, stream>>>(ta, tb, args); break;
+        default: return fail(OPL_E_ARG, "ozaki GEMM: unknown epilogue %d", args.epi);
     }
     OPL_LAUNCH_CHECK();
     if (launches) ++*launches;
@@ -770,7 +753,7 @@ __global__ void oz_fold_kernel(const double *__restrict__ partial, int splits, i
 // Validation / benchmark hook: C[M,N] = epi(A[M,K] . B[K,N]) (row-major FP64 device buffers) through the Ozaki path
 // (digit extraction timed in `slice_ms_out`, the INT8 GEMM + fold in `gemm_ms_out`).
 extern "C" int opl_bench_gemm_ozaki(int32_t M, int32_t N, int32_t K, const double *a_dev, const double *b_dev, double *c_dev,
-                                    int32_t variant, int32_t epi, int32_t iters, float *slice_ms_out, float *gemm_ms_out) {
+                                    int32_t epi, int32_t iters, float *slice_ms_out, float *gemm_ms_out) {
     using namespace opl;
     if (!a_dev || !b_dev || !c_dev || !slice_ms_out || !gemm_ms_out || iters < 1 || M < 1 || N < 1 || K < 1)
         return fail(OPL_E_ARG, "opl_bench_gemm_ozaki: bad arguments");
@@ -819,7 +802,7 @@ extern "C" int opl_bench_gemm_ozaki(int32_t M, int32_t N, int32_t K, const doubl
         g.scale_b = eb;
         g.epi = epi;
         g.tparam = 1.0;
-        if (rc == OPL_OK) rc = launch_ozaki_gemm(sa, mp, sb, np, kp, g, variant, nullptr, nullptr);
+        if (rc == OPL_OK) rc = launch_ozaki_gemm(sa, mp, sb, np, kp, g, nullptr, nullptr);
         if (rc == OPL_OK && splits > 1)
             oz_fold_kernel<<<oz_grid1((int64_t)M * N, 256), 256>>>(partial, splits, (int64_t)M * N, (int64_t)M * N, c_dev);
         cudaEventRecord(e2, nullptr);

@@ -8,17 +8,10 @@ namespace opl {
 
 constexpr int OZ_S = 6;          // 6 signed radix-256 digits = 48 bits below each row / column scale
 constexpr int OZ_BM = 128;
-constexpr int OZ_BN = 64;        // 6 diagonal accumulators x 64 INT32 columns = 384 of 512 TMEM columns (+128 for A staging)
+constexpr int OZ_BN = 64;        // 6 diagonal accumulators x 64 INT32 columns = 384 of 512 TMEM columns
 constexpr int OZ_MAX_K = 16384;  // 6 * 16384 * 128^2 < 2^31: INT32 accumulation stays exact
 
 enum OzakiEpilogue { OZ_EPI_STORE = 0, OZ_EPI_TANH = 1, OZ_EPI_SOFTPLUS = 2, OZ_EPI_GAUSSIAN = 3 };
-
-// How the M-side operand reaches the tensor core
-enum OzakiVariant {
-    OZ_A_SMEM = 0,      // tcgen05.mma SS: A and B both read from shared memory by every MMA
-    OZ_A_UTCCP = 1,     // A tile copied smem -> TMEM once (tcgen05.cp), MMAs read A from TMEM
-    OZ_A_WARPS = 2      // A tile moved smem -> registers -> TMEM by four loader warps (tcgen05.st), MMAs read A from TMEM
-};
 
 struct OzakiArgs {
     double *C;
@@ -55,6 +48,6 @@ int ozaki_ones_row(int8_t *slices, double *scale, int64_t rows, int64_t m_pad, c
 // FP64 fold of split-K partials is done by the caller (launch_reduce_partials)
 // C = (A digits) . (B digits)^T with both operands K-major; rows_pad = padded row counts of the digit arrays
 int launch_ozaki_gemm(const int8_t *a_slices, int64_t a_rows_pad, const int8_t *b_slices, int64_t b_rows_pad, int64_t k_pad,
-                      const OzakiArgs &args, int variant, cudaStream_t stream, int64_t *launches);
+                      const OzakiArgs &args, cudaStream_t stream, int64_t *launches);
 
 }  // namespace opl

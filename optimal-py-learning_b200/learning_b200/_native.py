@@ -42,7 +42,7 @@ SIGNATURES = {
     "opl_mlp_profile_read": (ctypes.c_int, [vp, i32, c_int32_p, ctypes.POINTER(ctypes.c_float), c_int32_p]),
     "opl_bench_gemm_f64": (ctypes.c_int, [i32, i32, i32, i32, vp, vp, vp, vp, i64, i32, ctypes.POINTER(ctypes.c_float)]),
     "opl_bench_gemm_tf32": (ctypes.c_int, [i32, i32, i32, i32, vp, vp, vp, vp, i64, i32, i32, ctypes.POINTER(ctypes.c_float)]),
-    "opl_bench_gemm_ozaki": (ctypes.c_int, [i32, i32, i32, vp, vp, vp, i32, i32, i32, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
+    "opl_bench_gemm_ozaki": (ctypes.c_int, [i32, i32, i32, vp, vp, vp, i32, i32, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float)]),
     "opl_transfer_apply_host": (ctypes.c_int, [i32, f64, vp, i64, i64, vp]),
     "opl_transfer_backprop_host": (ctypes.c_int, [i32, f64, vp, vp, i64, i64, vp]),
     "opl_error_host": (ctypes.c_int, [i32, vp, vp, i64, i64, c_double_p, vp]),

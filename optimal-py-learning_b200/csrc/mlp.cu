@@ -244,9 +244,11 @@ softmax_backward_rows_kernel(T *G, const T *A, int64_t rows, int64_t ld, int C, 
 // global traffic is perfectly coalesced along j with 8 independent loads in flight per thread.
 // mode: 0 out = s, 1 out = s * aux (D = f'), 2 out = s * (1 - aux^2) (tanh from the activation)
 template <int MAXC>
+// colmax (optional): max |out[:, j]| per column, gathered with atomicMax on the bit patterns (non-negative doubles order
+// like unsigned integers; a non-finite entry stores the NaN pattern, which is larger than every finite one).
 __global__ void __launch_bounds__(256) narrow_backprop_kernel(const double *__restrict__ delta, const double *__restrict__ W,
                                                               const double *aux, double *out, int64_t rows, int H, int C,
-                                                              int rows_per_block, int mode) {
+                                                              int rows_per_block, int mode, double *colmax) {
     extern __shared__ double sm[];
     double *Ws = sm;                       // H x (C|1): odd stride => conflict-free across j
     const int cp = C | 1;
@@ -262,6 +264,8 @@ __global__ void __launch_bounds__(256) narrow_backprop_kernel(const double *__re
         __syncthreads();
         for (int j = threadIdx.x; j < H; j += blockDim.x) {
             double w[MAXC];
+            double cmax = 0.0;
+            bool bad = false;
 #pragma unroll
             for (int c = 0; c < MAXC; ++c) w[c] = c < C ? Ws[j * cp + c] : 0.0;
             for (int rb = 0; rb < nr; rb += 8) {
@@ -275,10 +279,17 @@ __global__ void __launch_bounds__(256) narrow_backprop_kernel(const double *__re
 #pragma unroll
                         for (int c = 0; c < MAXC; ++c)
                             if (c < C) s_ += Ds[(rb + u) * C + c] * w[c];
-                        out[(r0 + rb + u) * H + j] = mode == 2 ? s_ * (1.0 - x[u] * x[u]) : s_ * x[u];
+                        const double o = mode == 2 ? s_ * (1.0 - x[u] * x[u]) : s_ * x[u];
+                        out[(r0 + rb + u) * H + j] = o;
+                        const double ao = fabs(o);
+                        bad |= !(ao <= 1.7976931348623157e308);
+                        cmax = fmax(cmax, ao);
                     }
                 }
             }
+            if (colmax)
+                atomicMax(reinterpret_cast<unsigned long long *>(colmax) + j,
+                          bad ? 0x7ff8000000000000ULL : (unsigned long long)__double_as_longlong(cmax));
         }
     }
 }
@@ -660,9 +671,10 @@ int backward(opl_mlp *ws, const double *w, const double *x, int64_t rows, double
             const int rpb = 16;
             const size_t smem = sizeof(double) * ((size_t)din * (dout | 1) + (size_t)rpb * dout);
             const int64_t grid = std::min<int64_t>(ceil_div(rows, rpb), 6 * (int64_t)sm_count());
+            double *dmax = int8_arm_delta_max(ws, l - 1, rows);
             mark(ws, STAGE_DA * 100 + l);
             narrow_backprop_kernel<16><<<(unsigned)grid, 256, smem, ws->stream>>>(
-                ws->delta[l], w + ws->w_off[l], aux, ws->delta[l - 1], rows, din, dout, rpb, mode);
+                ws->delta[l], w + ws->w_off[l], aux, ws->delta[l - 1], rows, din, dout, rpb, mode, dmax);
             OPL_LAUNCH_CHECK();
             ++ws->launches;
             continue;

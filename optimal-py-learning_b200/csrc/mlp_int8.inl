@@ -30,6 +30,8 @@ struct Int8State {
     int8_t *d_dig = nullptr;           // delta_l^T: [S][pad(dout)][rows_pad]
     double *d_scale = nullptr;
     double *colmax = nullptr;          // column-max scratch
+    double *dmax = nullptr;            // max |delta_l[:, j]| gathered by the kernel that writes delta_l (atomicMax), or unused
+    int dmax_layer = -1;               // layer whose delta the maxima in dmax belong to (-1: none)
     int64_t colmax_len = 0;
 };
 // Padding: the digit kernels write zeros along the CONTRACTION index themselves (pad columns of a row-digit array,
@@ -60,6 +62,7 @@ void int8_free(Int8State *s) {
     cudaFree(s->d_dig);
     cudaFree(s->d_scale);
     cudaFree(s->colmax);
+    cudaFree(s->dmax);
     delete s;
 }
 
@@ -129,6 +132,7 @@ int int8_create(opl_mlp *ws, int64_t *partials_needed) {
     }
     s->colmax_len = 4 * (int64_t)sm_count() * std::max<int64_t>(std::max(d_cols, at_rows), ozaki_pad(ws->width[0] + 1));
     OPL_CUDA(cudaMalloc(&s->colmax, sizeof(double) * (size_t)s->colmax_len));
+    OPL_CUDA(cudaMalloc(&s->dmax, sizeof(double) * (size_t)d_cols));
     return OPL_OK;
 }
 
@@ -143,7 +147,7 @@ int int8_set_x(opl_mlp *ws) {
     mark(ws, STAGE_DIGITS * 100);
     int rc = ozaki_slice_rows(ws->x, rows, d0, d0, s->x_dig, s->x_scale, false, ws->stream, &ws->launches);
     if (rc != OPL_OK) return rc;
-    rc = ozaki_slice_cols_transposed(ws->x, rows, d0, d0, s->xt_dig, s->xt_scale, s->colmax, s->colmax_len, 1, mp, false,
+    rc = ozaki_slice_cols_transposed(ws->x, rows, d0, d0, s->xt_dig, s->xt_scale, s->colmax, s->colmax_len, 1, mp, nullptr,
                                      ws->stream, &ws->launches);
     if (rc != OPL_OK) return rc;
     rc = ozaki_ones_row(s->xt_dig, s->xt_scale, rows, mp, ws->stream, &ws->launches);
@@ -165,6 +169,17 @@ bool int8_dw_ok(const opl_mlp *ws, int l, const double *in, int64_t rows) {
     return l > 0 || (in == ws->int8->x_for && rows == ws->int8->x_rows);
 }
 
+// The kernel about to write delta_l may gather max |delta_l[:, j]| on the fly: returns the (zeroed) buffer, or null when
+// layer l's weight gradient does not run on the INT8 engine.
+double *int8_arm_delta_max(opl_mlp *ws, int l, int64_t rows) {
+    if (!int8_use(ws, rows) || !ws->int8->dw[l]) return nullptr;
+    Int8State *s = ws->int8;
+    if (l == 0 && (s->x_for == nullptr || rows != s->x_rows)) return nullptr;
+    if (cudaMemsetAsync(s->dmax, 0, sizeof(double) * (size_t)ws->width[l + 1], ws->stream) != cudaSuccess) return nullptr;
+    s->dmax_layer = l;
+    return s->dmax;
+}
+
 // act[l+1] = f_l(in . W_l (+ b)), deriv[l] = f_l'  -- the forward GEMM of layer l
 int int8_forward_layer(opl_mlp *ws, int l, const double *w, const double *in, int64_t rows, bool keep_deriv, bool masked) {
     Int8State *s = ws->int8;
@@ -174,7 +189,7 @@ int int8_forward_layer(opl_mlp *ws, int l, const double *w, const double *in, in
     // B operand: W_l (din x dout row-major) -> digits of its transpose, one scale per output unit
     mark(ws, STAGE_DIGITS * 100 + l);
     int rc = ozaki_slice_cols_transposed(w + ws->w_off[l], din, dout, dout, s->w_dig, s->w_scale, s->colmax, s->colmax_len, 0,
-                                         np, false, ws->stream, &ws->launches);
+                                         np, nullptr, ws->stream, &ws->launches);
     if (rc != OPL_OK) return rc;
     const int8_t *a_dig = s->x_dig;
     const double *a_scale = s->x_scale;
@@ -215,19 +230,21 @@ int int8_forward_layer(opl_mlp *ws, int l, const double *w, const double *in, in
 // dW_l = A_l^T delta_l (+ db = 1^T delta_0 for l = 0) into the flat gradient
 int int8_dw_layer(opl_mlp *ws, int l, const double *in, int64_t rows, double *grad) {
     Int8State *s = ws->int8;
+    const double *colmax_raw = s->dmax_layer == l ? s->dmax : nullptr;
+    s->dmax_layer = -1;
     const int64_t din = ws->width[l], dout = ws->width[l + 1];
     const int64_t kp = ozaki_pad(rows), np = ozaki_pad(dout);
     const int64_t lead_rows = l == 0 ? 1 : 0, lead = lead_rows * dout;
     const int64_t m = din + lead_rows, mp = ozaki_pad(m);
     // B operand: delta_l (rows x dout) -> digits of its transpose, one scale per unit (max over the patterns)
     mark(ws, STAGE_DIGITS * 100 + 50 + l);
-    int rc = ozaki_slice_cols_transposed(ws->delta[l], rows, dout, dout, s->d_dig, s->d_scale, s->colmax, s->colmax_len, 0, np, false,
-                                     ws->stream, &ws->launches);
+    int rc = ozaki_slice_cols_transposed(ws->delta[l], rows, dout, dout, s->d_dig, s->d_scale, s->colmax, s->colmax_len, 0, np, colmax_raw,
+                                         ws->stream, &ws->launches);
     if (rc != OPL_OK) return rc;
     const int8_t *a_dig = s->xt_dig;
     const double *a_scale = s->xt_scale;
     if (l > 0) {
-        rc = ozaki_slice_cols_transposed(in, rows, din, din, s->at_dig, s->at_scale, s->colmax, s->colmax_len, 0, mp, false,
+        rc = ozaki_slice_cols_transposed(in, rows, din, din, s->at_dig, s->at_scale, s->colmax, s->colmax_len, 0, mp, nullptr,
                                          ws->stream, &ws->launches);
         if (rc != OPL_OK) return rc;
         a_dig = s->at_dig;

@@ -486,15 +486,28 @@ __device__ __forceinline__ double oz_scale_of(double amax) {
     return ldexp(1.0, e);
 }
 
-// signed radix-256 digits of r (|r| <= 0.498): t_s = floor(256 r_s + 128/255) in [-128,127], r_{s+1} = 256 r_s - t_s (exact)
-__device__ __forceinline__ void oz_digits(double r, int (&t)[OZ_S]) {
+// Signed radix-256 digits of four scaled values (|r| <= 0.498), packed one 32-bit word per digit plane (byte j = value j).
+// fx = rint(r 2^48) as an integer; u = fx + 0x808080808080 (128 in every byte) lies in [0, 2^48) and its bytes, most
+// significant first, are the digits + 128: r = sum_s (byte_s - 128) 256^-(s+1) exactly, |r - fx 2^-48| <= 2^-49.
+// One FP64 multiply and one conversion per value instead of a floor / clamp / subtract chain per digit.
+__device__ __forceinline__ void oz_digits4(const double (&r)[4], uint32_t (&w)[OZ_S]) {
+    uint32_t lo[4], hi[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const unsigned long long u =
+            ((unsigned long long)(__double2ll_rn(r[j] * 281474976710656.0) + 0x808080808080LL)) ^ 0x808080808080ULL;
+        lo[j] = (uint32_t)u;
+        hi[j] = (uint32_t)(u >> 32);
+    }
+    // plane s takes byte (5 - s) of every value: bytes 5,4 live in hi (bytes 1,0), bytes 3..0 in lo
 #pragma unroll
     for (int s = 0; s < OZ_S; ++s) {
-        r *= 256.0;
-        double f = floor(r + 128.0 / 255.0);
-        f = fmin(fmax(f, -128.0), 127.0);
-        r -= f;
-        t[s] = (int)f;
+        const int byte = 5 - s;
+        const uint32_t *src = byte >= 4 ? hi : lo;
+        const uint32_t b = (uint32_t)(byte & 3);
+        const uint32_t p01 = __byte_perm(src[0], src[1], b | ((4 + b) << 4));          // bytes: v0, v1
+        const uint32_t p23 = __byte_perm(src[2], src[3], b | ((4 + b) << 4));          // bytes: v2, v3
+        w[s] = __byte_perm(p01, p23, 0x5410);
     }
 }
 
@@ -521,15 +534,10 @@ __global__ void __launch_bounds__(256) slice_rows_kernel(const double *__restric
     const double inv = bad ? 0.0 : 1.0 / sc;            // exact (power of two)
     for (int64_t c4 = (int64_t)lane * 4; c4 < cols_pad; c4 += 128) {   // pad columns (contraction index) := 0
         uint32_t w[OZ_S];
+        double r[4];
 #pragma unroll
-        for (int s = 0; s < OZ_S; ++s) w[s] = 0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int t[OZ_S];
-            oz_digits(c4 + j < cols ? x[c4 + j] * inv : 0.0, t);
-#pragma unroll
-            for (int s = 0; s < OZ_S; ++s) w[s] |= (uint32_t)(t[s] & 0xff) << (8 * j);
-        }
+        for (int j = 0; j < 4; ++j) r[j] = c4 + j < cols ? x[c4 + j] * inv : 0.0;
+        oz_digits4(r, w);
 #pragma unroll
         for (int s = 0; s < OZ_S; ++s)
             *reinterpret_cast<uint32_t *>(out + ((int64_t)s * rows_pad + row) * cols_pad + c4) = w[s];
@@ -581,49 +589,81 @@ __global__ void colabsmax_final_kernel(const double *__restrict__ partial, int n
 // (each output row = one column of src, contiguous along src's rows = the contraction index).
 // Block = 128 src rows x 32 src columns; a thread converts 4 consecutive rows of one column into one word per digit
 // plane, the block then writes 128-byte output rows.
+// Scale source: MODE 0 `scale` holds finished scales; MODE 1 `colmax` holds raw column maxima (bit patterns gathered
+// with atomicMax by the producer of src), the scale is derived here and block row 0 publishes it; MODE 2 (small
+// matrices) every block first scans its 32 columns over ALL rows itself, then walks all row chunks (grid.x == 1).
+template <int MODE>
 __global__ void __launch_bounds__(256) slice_cols_transposed_kernel(const double *__restrict__ src, int64_t rows, int64_t cols,
-                                                                    int64_t ld, const double *__restrict__ scale,
+                                                                    int64_t ld, double *__restrict__ scale,
+                                                                    const double *__restrict__ colmax,
                                                                     int8_t *__restrict__ out, int64_t cols_pad, int64_t rows_pad,
                                                                     int64_t row_off) {
     __shared__ uint32_t tile[OZ_S][32][33];    // [digit][col][word along rows], padded
-    const int64_t r0 = blockIdx.x * 128, c0 = blockIdx.y * 32;
+    __shared__ double smax[8][33];
+    const int64_t c0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 8 warps
     const int64_t c = c0 + tx;
-    double inv = 0.0;
-    if (c < cols) {
-        const double sc = scale[c];
-        inv = sc == sc ? 1.0 / sc : 0.0;
-    }
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        const int wq = ty * 4 + g;             // word index along rows: rows r0 + 4 wq ..
-        uint32_t w[OZ_S];
-#pragma unroll
-        for (int s = 0; s < OZ_S; ++s) w[s] = 0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int64_t r = r0 + wq * 4 + j;
-            int t[OZ_S];
-            oz_digits((r < rows && c < cols) ? src[r * ld + c] * inv : 0.0, t);
-#pragma unroll
-            for (int s = 0; s < OZ_S; ++s) w[s] |= (uint32_t)(t[s] & 0xff) << (8 * j);
+    double sc = 1.0;
+    if (MODE == 0) {
+        if (c < cols) sc = scale[c];
+    } else if (MODE == 1) {
+        if (c < cols) {
+            sc = oz_scale_of(colmax[c]);
+            if (blockIdx.x == 0 && ty == 0) scale[c] = sc;
         }
+    } else {
+        double m = 0.0;
+        bool bad = false;
+        if (c < cols)
+            for (int64_t r = ty; r < rows; r += 8) {
+                const double v = fabs(src[r * ld + c]);
+                bad |= !(v <= 1.7976931348623157e308);
+                m = fmax(m, v);
+            }
+        smax[ty][tx] = bad ? __longlong_as_double(0x7ff8000000000000LL) : m;
+        __syncthreads();
+        double t = 0.0;
+        bool nan = false;
 #pragma unroll
-        for (int s = 0; s < OZ_S; ++s) tile[s][tx][wq] = w[s];
-    }
-    __syncthreads();
-    // write: OZ_S x 32 output rows of 128 bytes = 8 x 16 bytes each
-    for (int idx = threadIdx.x; idx < OZ_S * 32 * 8; idx += 256) {
-        const int s = idx >> 8, cc = (idx >> 3) & 31, seg = idx & 7;
-        const int64_t oc = c0 + cc + row_off, r = r0 + seg * 16;
-        if (c0 + cc < cols && r < rows_pad) {
-            uint4 v;
-            v.x = tile[s][cc][seg * 4 + 0];
-            v.y = tile[s][cc][seg * 4 + 1];
-            v.z = tile[s][cc][seg * 4 + 2];
-            v.w = tile[s][cc][seg * 4 + 3];
-            *reinterpret_cast<uint4 *>(out + ((int64_t)s * cols_pad + oc) * rows_pad + r) = v;
+        for (int k = 0; k < 8; ++k) {
+            const double v = smax[k][tx];
+            nan |= v != v;
+            t = fmax(t, v);
         }
+        sc = nan ? __longlong_as_double(0x7ff8000000000000LL) : oz_scale_of(t);
+        if (c < cols && ty == 0) scale[c] = sc;
+    }
+    const double inv = sc == sc ? 1.0 / sc : 0.0;
+    for (int64_t r0 = blockIdx.x * 128; r0 < rows_pad; r0 += (int64_t)gridDim.x * 128) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int wq = ty * 4 + g;             // word index along rows: rows r0 + 4 wq ..
+            uint32_t w[OZ_S];
+            double v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t r = r0 + wq * 4 + j;
+                v[j] = (r < rows && c < cols) ? src[r * ld + c] * inv : 0.0;
+            }
+            oz_digits4(v, w);
+#pragma unroll
+            for (int s = 0; s < OZ_S; ++s) tile[s][tx][wq] = w[s];
+        }
+        __syncthreads();
+        // write: OZ_S x 32 output rows of 128 bytes = 8 x 16 bytes each
+        for (int idx = threadIdx.x; idx < OZ_S * 32 * 8; idx += 256) {
+            const int s = idx >> 8, cc = (idx >> 3) & 31, seg = idx & 7;
+            const int64_t oc = c0 + cc + row_off, r = r0 + seg * 16;
+            if (c0 + cc < cols && r < rows_pad) {
+                uint4 q;
+                q.x = tile[s][cc][seg * 4 + 0];
+                q.y = tile[s][cc][seg * 4 + 1];
+                q.z = tile[s][cc][seg * 4 + 2];
+                q.w = tile[s][cc][seg * 4 + 3];
+                *reinterpret_cast<uint4 *>(out + ((int64_t)s * cols_pad + oc) * rows_pad + r) = q;
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -690,10 +730,24 @@ int ozaki_ones_row(int8_t *slices, double *scale, int64_t rows, int64_t m_pad, c
 }
 
 int ozaki_slice_cols_transposed(const double *src, int64_t rows, int64_t cols, int64_t ld, int8_t *slices, double *scale,
-                                double *scratch, int64_t scratch_len, int64_t row_off, int64_t m_pad, bool zero_fill,
+                                double *scratch, int64_t scratch_len, int64_t row_off, int64_t m_pad, const double *colmax_raw,
                                 cudaStream_t stream, int64_t *launches) {
     const int64_t cp = m_pad > 0 ? m_pad : ozaki_pad(cols + row_off), rp = ozaki_pad(rows);
-    if (zero_fill) OPL_CUDA(cudaMemsetAsync(slices, 0, (size_t)OZ_S * rp * cp, stream));
+    const unsigned gy = (unsigned)ceil_div(cols, 32);
+    if (colmax_raw) {            // maxima gathered by the kernel that produced src
+        slice_cols_transposed_kernel<1><<<dim3((unsigned)ceil_div(rp, 128), gy), 256, 0, stream>>>(
+            src, rows, cols, ld, scale + row_off, colmax_raw, slices, cp, rp, row_off);
+        OPL_LAUNCH_CHECK();
+        if (launches) *launches += 1;
+        return OPL_OK;
+    }
+    if (rows <= 256) {           // tiny matrix: one launch, every block scans its own columns
+        slice_cols_transposed_kernel<2><<<dim3(1, gy), 256, 0, stream>>>(src, rows, cols, ld, scale + row_off, nullptr, slices, cp, rp,
+                                                                         row_off);
+        OPL_LAUNCH_CHECK();
+        if (launches) *launches += 1;
+        return OPL_OK;
+    }
     int64_t nblk = std::max<int64_t>(1, std::min<int64_t>(ceil_div(rows, 256), scratch_len / std::max<int64_t>(cols, 1)));
     nblk = std::min<int64_t>(nblk, 4 * (int64_t)sm_count());
     const int64_t rpb = ceil_div(rows, nblk);
@@ -701,8 +755,8 @@ int ozaki_slice_cols_transposed(const double *src, int64_t rows, int64_t cols, i
     dim3 g1((unsigned)ceil_div(cols, 32), (unsigned)nblk);
     colabsmax_partial_kernel<<<g1, dim3(32, 8), 0, stream>>>(src, rows, cols, ld, rpb, scratch);
     colabsmax_final_kernel<<<(unsigned)ceil_div(cols, 256), 256, 0, stream>>>(scratch, (int)nblk, cols, scale + row_off);
-    dim3 g2((unsigned)ceil_div(rp, 128), (unsigned)ceil_div(cols, 32));
-    slice_cols_transposed_kernel<<<g2, 256, 0, stream>>>(src, rows, cols, ld, scale + row_off, slices, cp, rp, row_off);
+    slice_cols_transposed_kernel<0><<<dim3((unsigned)ceil_div(rp, 128), gy), 256, 0, stream>>>(
+        src, rows, cols, ld, scale + row_off, nullptr, slices, cp, rp, row_off);
     OPL_LAUNCH_CHECK();
     if (launches) *launches += 3;
     return OPL_OK;
@@ -786,7 +840,7 @@ extern "C" int opl_bench_gemm_ozaki(int32_t M, int32_t N, int32_t K, const doubl
     for (int it = 0; it <= iters && rc == OPL_OK; ++it) {
         cudaEventRecord(e0, nullptr);
         rc = ozaki_slice_rows(a_dev, M, K, K, sa, ea, false, nullptr, nullptr);
-        if (rc == OPL_OK) rc = ozaki_slice_cols_transposed(b_dev, K, N, N, sb, eb, scratch, scratch_len, 0, np, false, nullptr, nullptr);
+        if (rc == OPL_OK) rc = ozaki_slice_cols_transposed(b_dev, K, N, N, sb, eb, scratch, scratch_len, 0, np, nullptr, nullptr, nullptr);
         cudaEventRecord(e1, nullptr);
         OzakiArgs g = {};
         g.C = splits > 1 ? partial : c_dev;

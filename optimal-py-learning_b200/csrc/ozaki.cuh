@@ -36,12 +36,13 @@ int64_t ozaki_pad(int64_t v);   // round up to a multiple of 128
 // Padding must already be zero (ozaki_slice_* never write it); pass zero_fill to have it cleared here.
 int ozaki_slice_rows(const double *src, int64_t rows, int64_t cols, int64_t ld, int8_t *slices, double *scale,
                      bool zero_fill, cudaStream_t stream, int64_t *launches);
-// digits of the TRANSPOSE, scaled per COLUMN of src: INT8 [S][pad(cols)][pad(rows)], scale[cols];
-// scratch: >= min(ceil(rows/256), 4*SMs) * cols doubles
+// digits of the TRANSPOSE, scaled per COLUMN of src: INT8 [S][m_pad][pad(rows)], scale[cols];
+// scratch: >= min(ceil(rows/256), 4*SMs) * cols doubles.
 // Output row of src column c is c + row_off (scale[c + row_off]); m_pad = padded row count of the digit array
-// (0: pad(cols + row_off)).
+// (0: pad(cols + row_off)).  colmax_raw (optional): max |src[:, c]| already gathered by the producer of src
+// (atomicMax on the bit patterns, NaN pattern for non-finite entries); saves the column-maximum pass.
 int ozaki_slice_cols_transposed(const double *src, int64_t rows, int64_t cols, int64_t ld, int8_t *slices, double *scale,
-                                double *scratch, int64_t scratch_len, int64_t row_off, int64_t m_pad, bool zero_fill,
+                                double *scratch, int64_t scratch_len, int64_t row_off, int64_t m_pad, const double *colmax_raw,
                                 cudaStream_t stream, int64_t *launches);
 // row 0 of a transposed digit array [S][m_pad][pad(rows)] := a row of ones (scale[0] = 4): the bias-gradient row
 int ozaki_ones_row(int8_t *slices, double *scale, int64_t rows, int64_t m_pad, cudaStream_t stream, int64_t *launches);

@@ -357,7 +357,7 @@ def run_gpu(args):
     if profile and stage_ms:
         flops_eval = algorithmic_flops(SHAPE, ROWS)
         names = {1: "forward GEMM", 2: "row kernel", 3: "dW GEMM", 4: "dW reduce", 5: "dA GEMM", 6: "bias colsum",
-                 7: "loss", 8: "digits", 0: "trial point"}
+                 7: "loss", 8: "digits", 10: "fused head", 0: "trial point"}
         per_kind = {k: sum(v) / args.steps for k, v in stage_ms.items()}
         total = sum(per_kind.values())
         line["stage_ms"] = {"%s L%d" % (names.get(k // 100, "?"), k % 100): round(v, 4) for k, v in sorted(per_kind.items())}

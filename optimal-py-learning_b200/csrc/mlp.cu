@@ -294,6 +294,235 @@ __global__ void __launch_bounds__(256) narrow_backprop_kernel(const double *__re
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Fused narrow head: the last layer (H hidden units -> C <= 16 outputs) of the forward pass, the output transfer and
+// error function, and the head's share of back-propagation, in ONE streaming pass over the hidden activations:
+//     Z = A W,  a = f(Z),  loss,  delta_L = dE/dZ,  dW += A^T delta_L,  delta_prev = (delta_L W^T) o slope
+// The five separate launches re-read A twice and move the logits / deltas through HBM; here A and the slope matrix
+// are read once and delta_prev is written once.  A CTA owns a fixed sequence of row blocks and a fixed-order
+// accumulation, so the result is bit-reproducible; per-CTA dW partials are folded by the split-K reduce kernel.
+// mode (slope of the hidden transfer): 0 none, 1 aux = f' stored by the forward GEMM, 2 aux = tanh activation.
+// ---------------------------------------------------------------------------------------
+struct HeadArgs {
+    const double *A;        // rows x H hidden activations
+    const double *W;        // H x C
+    const double *Y;        // rows x C targets
+    const double *aux;      // rows x H (mode 1: f', mode 2: the activation itself) or null
+    double *delta_prev;     // rows x H out (may alias aux), or null (objective only)
+    double *dw_partial;     // gridDim.x x (H*C), or null
+    double *loss_partial;   // gridDim.x
+    double *colmax;         // H: max |delta_prev[:, j]| (atomicMax on bit patterns) or null
+    int64_t rows;
+    int H, C, R;            // R rows per block step
+    int mode;
+    int tid;                // output transfer
+    double tparam;
+    int eid;
+    double ce_div, mse_mul;
+    int *flag;
+};
+
+// All three products are DMMA.8x8x4 on shared-memory fragments (classes padded to 16 with zeros):
+//   logits  Z[R x 16]   = As[R x H] . Ws[H x 16]            (row tile, class tile, K half) per warp, halves meet in Zs
+//   dA      D0[R x H]   = Ds[R x 16] . Ws^T[16 x H]          warp -> hidden tiles w, w+16, ..; epilogue x slope, store
+//   dW      G[H x 16]  += As^T[H x R] . Ds[R x 16]           warp -> hidden tiles w, w+16, ..; accumulators stay in registers
+// One CTA of 16 warps per SM, R = 32 patterns per step.  The next step's activation tile streams in with cp.async
+// (double buffer) and the step's slope values are requested before the logits are computed, so every global load has
+// a whole phase of compute to hide behind.  Leading dimensions (H+4, 20) make every fragment load conflict-free.
+// The row stage (softmax / error / delta_L) runs one pattern per half-warp, lane = class.
+constexpr int HEAD_R = 32, HEAD_THREADS = 512, HEAD_WARPS = 16;
+template <int MT>    // hidden tiles (8 units) per warp: H <= 128 MT
+__global__ void __launch_bounds__(HEAD_THREADS, 1) narrow_head_kernel(const HeadArgs p) {
+    extern __shared__ double hsm[];
+    __shared__ double scratch[33];
+    constexpr int R = HEAD_R, RM = R / 8;
+    const int H = p.H, C = p.C;
+    const int ldA = H + 4;
+    constexpr int ldW = 20, ldD = 20;
+    double *Ws = hsm;                          // H x 20
+    double *Zs = Ws + (size_t)H * ldW;         // R x 20: logits, then delta_L
+    double *As0 = Zs + R * ldD;                // 2 x R x (H+4)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const bool softmax = p.tid == OPL_TRANSFER_SOFTMAX;
+    const bool backward = p.delta_prev != nullptr;
+    const int h2 = H >> 1;
+    const int64_t nblocks = (p.rows + R - 1) / R;
+    auto fetch = [&](int64_t blk, int buf) {   // cp.async the block's activations (rows past the end := 0)
+        const int64_t r0 = blk * R;
+        double *dst = As0 + (size_t)buf * R * ldA;
+        for (int i = threadIdx.x; i < R * h2; i += HEAD_THREADS) {
+            const int r = i / h2, c2 = i - r * h2;
+            const bool ok = r0 + r < p.rows;
+            cp_async16(dst + (size_t)r * ldA + 2 * c2, p.A + (ok ? (r0 + r) * H + 2 * c2 : 0), ok);
+        }
+        cp_async_commit();
+    };
+    if ((int64_t)blockIdx.x < nblocks) fetch(blockIdx.x, 0);
+    for (int i = threadIdx.x; i < H * 16; i += HEAD_THREADS) {
+        const int h = i >> 4, c = i & 15;
+        Ws[h * ldW + c] = c < C ? p.W[h * C + c] : 0.0;
+    }
+    RowArgs ra = {};                           // error_term() reads its constants from here
+    ra.eid = p.eid;
+    ra.ce_div = p.ce_div;
+    ra.mse_mul = p.mse_mul;
+    double loss = 0.0;
+    bool bad = false, cbad = false;
+    double dw[MT][2][2], cmax[MT][2];
+#pragma unroll
+    for (int i = 0; i < MT; ++i) {
+        cmax[i][0] = cmax[i][1] = 0.0;
+#pragma unroll
+        for (int n = 0; n < 2; ++n) dw[i][n][0] = dw[i][n][1] = 0.0;
+    }
+    int buf = 0;
+    for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x, buf ^= 1) {
+        const int64_t r0 = blk * R;
+        const int nr = (int)min((int64_t)R, p.rows - r0);
+        const double *As = As0 + (size_t)buf * R * ldA;
+        // slope values of this step's delta_prev tiles: requested now, used after the row stage
+        double2 x[MT][RM];
+        if (backward && p.mode != 0) {
+#pragma unroll
+            for (int i = 0; i < MT; ++i) {
+                const int col = 8 * (warp + HEAD_WARPS * i) + 2 * t;
+#pragma unroll
+                for (int mt = 0; mt < RM; ++mt) {
+                    const int row = 8 * mt + g;
+                    x[i][mt] = (col < H && row < nr) ? *reinterpret_cast<const double2 *>(p.aux + (r0 + row) * H + col)
+                                                     : make_double2(1.0, 1.0);
+                }
+            }
+        }
+        for (int i = threadIdx.x; i < R * 16; i += HEAD_THREADS) Zs[(i >> 4) * ldD + (i & 15)] = 0.0;
+        cp_async_wait<0>();
+        __syncthreads();                       // tile `buf` landed, Zs cleared, previous step done with the other buffer
+        if (blk + gridDim.x < nblocks) fetch(blk + gridDim.x, buf ^ 1);
+        // ---- logits: warp -> (row tile, class tile, K half); the two halves add up in Zs ----
+        {
+            const int mt = warp & 3, nt = (warp >> 2) & 1, kh = warp >> 3;
+            double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;       // two independent accumulation chains
+            const int kq = H >> 3;                                // DMMA steps per half
+            const double *ap = As + (size_t)(8 * mt + g) * ldA + 4 * kh * kq + t;
+            const double *bp = Ws + (size_t)(4 * kh * kq + t) * ldW + 8 * nt + g;
+            int k = 0;
+            for (; k + 1 < kq; k += 2) {
+                dmma_8x8x4(c0, c1, ap[4 * k], bp[4 * k * ldW]);
+                dmma_8x8x4(e0, e1, ap[4 * k + 4], bp[(4 * k + 4) * ldW]);
+            }
+            if (k < kq) dmma_8x8x4(c0, c1, ap[4 * k], bp[4 * k * ldW]);
+            double *zp = Zs + (8 * mt + g) * ldD + 8 * nt + 2 * t;
+            atomicAdd(zp, c0 + e0);             // 0 + a + b == 0 + b + a: the order of the two halves does not matter
+            atomicAdd(zp + 1, c1 + e1);
+        }
+        __syncthreads();
+        // ---- output transfer + error + delta_L: one pattern per half-warp, lane = class ----
+        {
+            const int hw = lane >> 4, cl = lane & 15;
+            const int r = warp * 2 + hw;
+            const bool live = r < nr && cl < C;
+            const double z = Zs[r * ldD + cl];
+            double a_out;
+            if (softmax) {   // calculate.py:152-153
+                const double mx = group_max(live ? z : -INFINITY, 16);
+                const double e = live ? exp(z - mx) : 0.0;
+                a_out = e / group_sum(e, 16);
+            } else {
+                a_out = live ? transfer_value(p.tid, p.tparam, z) : 0.0;
+            }
+            double gq = 0.0;
+            if (live) gq = error_term(ra, a_out, p.Y[(r0 + r) * C + cl], loss, bad);
+            double d;
+            if (softmax) {   // delta_k = a_k (g_k - sum_j g_j a_j): dsoftmax contracted (mlp.py:295)
+                const double tt = group_sum(live ? gq * a_out : 0.0, 16);
+                d = a_out * (gq - tt);
+            } else {
+                d = live ? gq * transfer_slope(p.tid, p.tparam, z, a_out) : 0.0;
+            }
+            if (backward) Zs[r * ldD + cl] = live ? d : 0.0;
+        }
+        __syncthreads();
+        if (!backward) continue;
+        // ---- delta_prev = (delta_L W^T) o slope ----
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+            const int nt = warp + HEAD_WARPS * i;        // hidden tile
+            if (8 * nt >= H) break;
+            const int col = 8 * nt + 2 * t;
+            const double *bp = Ws + (size_t)(8 * nt + g) * ldW + t;
+#pragma unroll
+            for (int mt = 0; mt < RM; ++mt) {
+                const int row = 8 * mt + g;
+                double c0 = 0.0, c1 = 0.0;
+                const double *ap = Zs + row * ldD + t;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) dmma_8x8x4(c0, c1, ap[4 * k], bp[4 * k]);
+                if (row < nr) {
+                    double o0 = c0, o1 = c1;
+                    if (p.mode == 1) {
+                        o0 *= x[i][mt].x;
+                        o1 *= x[i][mt].y;
+                    } else if (p.mode == 2) {
+                        o0 *= 1.0 - x[i][mt].x * x[i][mt].x;
+                        o1 *= 1.0 - x[i][mt].y * x[i][mt].y;
+                    }
+                    *reinterpret_cast<double2 *>(p.delta_prev + (r0 + row) * H + col) = make_double2(o0, o1);
+                    const double a0 = fabs(o0), a1 = fabs(o1);
+                    cbad |= !(a0 <= 1.7976931348623157e308) || !(a1 <= 1.7976931348623157e308);
+                    cmax[i][0] = fmax(cmax[i][0], a0);
+                    cmax[i][1] = fmax(cmax[i][1], a1);
+                }
+            }
+        }
+        // ---- dW += A^T delta_L ----
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+            const int mt = warp + HEAD_WARPS * i;        // hidden tile
+            if (8 * mt >= H) break;
+            const double *ap = As + (size_t)t * ldA + 8 * mt + g;
+#pragma unroll
+            for (int n = 0; n < 2; ++n) {
+                const double *bp = Zs + t * ldD + 8 * n + g;
+#pragma unroll
+                for (int k = 0; k < R / 4; ++k) dmma_8x8x4(dw[i][n][0], dw[i][n][1], ap[(size_t)4 * k * ldA], bp[4 * k * ldD]);
+            }
+        }
+        __syncthreads();                       // Zs / this A buffer are free again
+    }
+    cp_async_wait<0>();
+    if (bad) *p.flag = 1;
+    if (backward) {
+        cbad = __any_sync(0xffffffffu, cbad);
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+            const int mt = warp + HEAD_WARPS * i;
+            if (8 * mt >= H) break;
+            double *dst = p.dw_partial + (size_t)blockIdx.x * H * C + (size_t)(8 * mt + g) * C;
+#pragma unroll
+            for (int n = 0; n < 2; ++n) {
+                const int c = 8 * n + 2 * t;
+                if (c < C) dst[c] = dw[i][n][0];
+                if (c + 1 < C) dst[c + 1] = dw[i][n][1];
+            }
+            if (p.colmax) {                               // columns 8 mt + 2t, +1: fold the 8 row groups, then one atomic
+                double m0 = cmax[i][0], m1 = cmax[i][1];
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                    m0 = fmax(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+                    m1 = fmax(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+                }
+                if (g == 0) {
+                    unsigned long long *cm = reinterpret_cast<unsigned long long *>(p.colmax) + 8 * mt + 2 * t;
+                    atomicMax(cm, cbad ? 0x7ff8000000000000ULL : (unsigned long long)__double_as_longlong(m0));
+                    atomicMax(cm + 1, cbad ? 0x7ff8000000000000ULL : (unsigned long long)__double_as_longlong(m1));
+                }
+            }
+        }
+    }
+    loss = block_sum(loss, scratch);
+    if (threadIdx.x == 0) p.loss_partial[blockIdx.x] = loss;
+}
+
 // obj = -(sum/N) for cross entropy, sum/(N*C) for MSE
 __global__ void loss_final_kernel(const double *partial, int nparts, int eid, double n_rows, double n_cols,
                                   double *out) {
@@ -399,6 +628,7 @@ struct opl_mlp {
     FastState *fast = nullptr;
     Int8State *int8 = nullptr;
     int gemm_engine = OPL_ENGINE_INT8;   // which kernels run the large FP64 layer GEMMs
+    bool fused_head = true;              // narrow last layer + error + its back-propagation in one streaming kernel
     int layers = 0;                    // weight matrices
     std::vector<int64_t> width;        // layers + 1
     std::vector<int> transfer;
@@ -438,7 +668,7 @@ struct opl_mlp {
 };
 
 enum { STAGE_TRIAL = 0, STAGE_FWD = 1, STAGE_ROWS = 2, STAGE_DW = 3, STAGE_DW_REDUCE = 4, STAGE_DA = 5,
-       STAGE_BIAS = 6, STAGE_LOSS = 7, STAGE_DIGITS = 8, STAGE_END = 9 };
+       STAGE_BIAS = 6, STAGE_LOSS = 7, STAGE_DIGITS = 8, STAGE_END = 9, STAGE_HEAD = 10 };
 
 namespace {
 
@@ -535,9 +765,11 @@ int epilogue_for(int transfer) {
 namespace {
 
 // forward through all layers; leaves Z_L in act[layers]
-int forward(opl_mlp *ws, const double *w, const double *x, int64_t rows, bool keep_deriv, bool masked = false) {
+int forward(opl_mlp *ws, const double *w, const double *x, int64_t rows, bool keep_deriv, bool masked = false,
+            int layer_end = -1) {
     const double *in = x;
-    for (int l = 0; l < ws->layers; ++l) {
+    if (layer_end < 0) layer_end = ws->layers;
+    for (int l = 0; l < layer_end; ++l) {
         GemmArgs a = {};
         a.A = in;
         a.lda = ws->width[l];
@@ -616,8 +848,9 @@ int output_stage(opl_mlp *ws, const double *y, int64_t rows, bool want_act, bool
     return OPL_OK;
 }
 
-int backward(opl_mlp *ws, const double *w, const double *x, int64_t rows, double *grad) {
-    for (int l = ws->layers - 1; l >= 0; --l) {
+int backward(opl_mlp *ws, const double *w, const double *x, int64_t rows, double *grad, int layer_begin = -1) {
+    if (layer_begin < 0) layer_begin = ws->layers - 1;
+    for (int l = layer_begin; l >= 0; --l) {
         const int din = (int)ws->width[l], dout = (int)ws->width[l + 1];
         // dW_l = A_l^T delta_l  (mlp.py:269-273), reduction over the patterns
         if (int8_dw_ok(ws, l, l == 0 ? x : ws->act[l], rows)) {
@@ -719,6 +952,75 @@ int backward(opl_mlp *ws, const double *w, const double *x, int64_t rows, double
     return OPL_OK;
 }
 
+// Can the fused narrow head replace forward(last layer) + output stage + the head's back-propagation?
+size_t head_smem(int H) { return sizeof(double) * ((size_t)H * 20 + (size_t)HEAD_R * 20 + 2 * (size_t)HEAD_R * (H + 4)); }
+int head_rows_per_step(const opl_mlp *ws) {
+    const int L = ws->layers;
+    if (L < 2 || ws->precision != OPL_PRECISION_F64 || !ws->fused_head) return 0;
+    const int64_t H = ws->width[L - 1], C = ws->width[L];
+    if (C > 16 || H > 512 || (H & 7) || H < 32) return 0;
+    if (ws->transfer[L - 2] == OPL_TRANSFER_SOFTMAX) return 0;
+    return head_smem((int)H) <= 220 * 1024 ? HEAD_R : 0;
+}
+
+// fused head: objective (and, when want_grad, dW_{L-1} and delta_{L-2}); the caller continues back-propagation at L-2
+int fused_head(opl_mlp *ws, const double *w, const double *y, int64_t rows, bool want_grad, double *grad, double *obj_out) {
+    const int L = ws->layers, R = head_rows_per_step(ws);
+    const int H = (int)ws->width[L - 1], C = (int)ws->width[L];
+    const size_t smem = head_smem(H);
+    int grid = (int)std::min<int64_t>(ceil_div(rows, R), (int64_t)sm_count());
+    grid = std::min(grid, ws->loss_blocks);
+    if (want_grad) grid = (int)std::min<int64_t>(grid, ws->partials_len / ((int64_t)H * C));
+    if (grid < 1) return fail(OPL_E_STATE, "fused head: scratch too small");
+    HeadArgs a = {};
+    a.A = ws->act[L - 1];
+    a.W = w + ws->w_off[L - 1];
+    a.Y = y;
+    a.rows = rows;
+    a.H = H;
+    a.C = C;
+    a.R = R;
+    a.tid = ws->transfer[L - 1];
+    a.tparam = ws->tparam[L - 1];
+    a.eid = ws->error_id;
+    a.ce_div = -(double)ws->norm_rows;
+    a.mse_mul = 2.0 / ((double)ws->norm_rows * (double)C);
+    a.flag = ws->flag;
+    a.loss_partial = ws->loss_partial;
+    if (want_grad) {
+        const int t = ws->transfer[L - 2];
+        a.mode = (t == OPL_TRANSFER_SOFTPLUS || t == OPL_TRANSFER_GAUSSIAN) ? 1 : (t == OPL_TRANSFER_TANH ? 2 : 0);
+        a.aux = a.mode == 1 ? ws->deriv[L - 2] : (a.mode == 2 ? ws->act[L - 1] : nullptr);
+        a.delta_prev = ws->delta[L - 2];
+        a.dw_partial = ws->partials;
+        a.colmax = int8_arm_delta_max(ws, L - 2, rows);
+    }
+    static bool configured = false;
+    if (!configured) {
+        OPL_CUDA(cudaFuncSetAttribute(narrow_head_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        OPL_CUDA(cudaFuncSetAttribute(narrow_head_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        configured = true;
+    }
+    mark(ws, STAGE_HEAD * 100 + L - 1);
+    if (H <= 256)
+        narrow_head_kernel<2><<<grid, HEAD_THREADS, smem, ws->stream>>>(a);
+    else
+        narrow_head_kernel<4><<<grid, HEAD_THREADS, smem, ws->stream>>>(a);
+    OPL_LAUNCH_CHECK();
+    ++ws->launches;
+    mark(ws, STAGE_LOSS * 100);
+    loss_final_kernel<<<1, 256, 0, ws->stream>>>(ws->loss_partial, grid, ws->error_id, (double)ws->norm_rows, (double)C, obj_out);
+    OPL_LAUNCH_CHECK();
+    ++ws->launches;
+    if (want_grad) {
+        mark(ws, STAGE_DW_REDUCE * 100 + L - 1);
+        const int64_t count = (int64_t)H * C;
+        int rc = launch_reduce_partials(ws->partials, grid, count, count, grad + ws->w_off[L - 1], ws->stream, &ws->launches);
+        if (rc != OPL_OK) return rc;
+    }
+    return OPL_OK;
+}
+
 }  // namespace
 
 #include "mlp_fast.inl"
@@ -747,11 +1049,19 @@ int evaluate(opl_mlp *ws, const double *x_dev, double alpha, const double *dir_d
         OPL_LAUNCH_CHECK();
         ++ws->launches;
     }
-    rc = forward(ws, ws->w_trial, ws->x, ws->rows, want_grad, true);
-    if (rc != OPL_OK) return rc;
-    rc = output_stage(ws, ws->y, ws->rows, false, want_grad, grad_out_dev + n);
-    if (rc != OPL_OK) return rc;
-    if (want_grad) rc = backward(ws, ws->w_trial, ws->x, ws->rows, grad_out_dev);
+    if (head_rows_per_step(ws) > 0) {
+        rc = forward(ws, ws->w_trial, ws->x, ws->rows, want_grad, true, ws->layers - 1);
+        if (rc != OPL_OK) return rc;
+        rc = fused_head(ws, ws->w_trial, ws->y, ws->rows, want_grad, grad_out_dev, grad_out_dev + n);
+        if (rc != OPL_OK) return rc;
+        if (want_grad) rc = backward(ws, ws->w_trial, ws->x, ws->rows, grad_out_dev, ws->layers - 2);
+    } else {
+        rc = forward(ws, ws->w_trial, ws->x, ws->rows, want_grad, true);
+        if (rc != OPL_OK) return rc;
+        rc = output_stage(ws, ws->y, ws->rows, false, want_grad, grad_out_dev + n);
+        if (rc != OPL_OK) return rc;
+        if (want_grad) rc = backward(ws, ws->w_trial, ws->x, ws->rows, grad_out_dev);
+    }
     if (rc == OPL_OK && want_grad && ws->masks) {   // dW0 = (X o m)^T delta_0 = diag(m) X^T delta_0
         scale_rows_kernel<<<mgrid, 256, 0, ws->stream>>>(grad_out_dev + ws->w_off[0], ws->width[0], ws->width[1], ws->masks);
         OPL_LAUNCH_CHECK();
@@ -859,7 +1169,12 @@ int opl_mlp_create(opl_mlp **out, int32_t n_widths, const int64_t *widths, const
     partials = std::max<int64_t>(partials, (int64_t)(4 * sm_count() + 8) * widths[1]);
     if (precision == OPL_PRECISION_F64) {
         const char *env = getenv("OPL_F64_ENGINE");
-        if (env && std::string(env) == "dmma") ws->gemm_engine = OPL_ENGINE_DMMA;
+        if (env && std::string(env) == "dmma") {
+            ws->gemm_engine = OPL_ENGINE_DMMA;
+            ws->fused_head = false;
+        }
+        if (L >= 2)      // per-CTA dW partials of the fused narrow head
+            partials = std::max<int64_t>(partials, 2 * (int64_t)sm_count() * widths[L - 1] * widths[L]);
         int rc = int8_create(ws, &partials);
         if (rc != OPL_OK) {
             free_all(ws);
@@ -904,6 +1219,7 @@ int opl_mlp_destroy(opl_mlp *ws) {
 int opl_mlp_set_engine(opl_mlp *ws, int32_t engine) {
     if (!ws || (engine != OPL_ENGINE_DMMA && engine != OPL_ENGINE_INT8)) return fail(OPL_E_ARG, "opl_mlp_set_engine: bad arguments");
     ws->gemm_engine = engine;
+    ws->fused_head = engine == OPL_ENGINE_INT8;   // OPL_ENGINE_DMMA = the plain schedule: one kernel per reference operation
     return OPL_OK;
 }
 

@@ -82,6 +82,27 @@ __device__ __forceinline__ void oz_tma_3d(void *dst, const CUtensorMap *map, int
         ::"r"(oz_smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(oz_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// cluster forms: the A tile is loaded once per cluster (every CTA fetches a slab and multicasts it), so a stage is free
+// only when every CTA of the cluster has consumed it -> the consumer's commit arrives on the barrier of every CTA
+__device__ __forceinline__ void oz_tma_3d_mc(void *dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(oz_smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(oz_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void oz_commit_mc(uint64_t *bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(oz_smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t oz_cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void oz_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void oz_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(oz_smem_u32(bar)) : "memory");
 }
@@ -95,6 +116,31 @@ __device__ __forceinline__ void oz_umma_ss(uint32_t tmem_d, uint64_t adesc, uint
         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
         : "memory");
+}
+// 8 doubles (16 columns) of this thread's TMEM lane: the staged FP64 tile lives in the 128 columns the accumulators leave free
+__device__ __forceinline__ void oz_tmem_st_f64x8(uint32_t taddr, const double (&z)[8]) {
+    uint32_t v[16];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        v[2 * j] = (uint32_t)__double2loint(z[j]);
+        v[2 * j + 1] = (uint32_t)__double2hiint(z[j]);
+    }
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void oz_tmem_ld_f64x8(uint32_t taddr, double (&z)[8]) {
+    uint32_t v[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 8; ++j) z[j] = __hiloint2double((int)v[2 * j + 1], (int)v[2 * j]);
 }
 __device__ __forceinline__ void oz_tmem_ld8(uint32_t taddr, int32_t (&v)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -266,7 +312,7 @@ __device__ __forceinline__ void oz_store_chunk(double *patch, const double (&v)[
     __syncwarp();
 }
 
-template <int EPI>
+template <int EPI, int CS>    // CS = CTAs per cluster sharing one A tile (consecutive n tiles of the same rows)
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const OzakiArgs p) {
     extern __shared__ uint8_t oz_smem_raw[];
@@ -288,11 +334,15 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     constexpr int producer_warp = OZ_EPI_WARPS, mma_warp = OZ_EPI_WARPS + 1;
     const int tiles_m = (p.M + OZ_BM - 1) / OZ_BM, tiles_n = (p.N + OZ_BN - 1) / OZ_BN;
     const int ntiles = tiles_m * tiles_n * p.splits;
+    // tile schedule: cluster c takes tile groups c, c + #clusters, ..; rank r of the cluster takes tile CS*group + r
+    const int crank = CS > 1 ? (int)oz_cluster_rank() : 0;
+    const int t_first = (int)(blockIdx.x / CS) * CS + crank, t_step = (int)gridDim.x;
+    constexpr uint16_t cmask = (uint16_t)((1u << CS) - 1u);
 
     if (warp == producer_warp && lane == 0) {
         for (int s = 0; s < OZ_S; ++s) {
             oz_mbar_init(&a_full[s], 1);
-            oz_mbar_init(&a_empty[s], 1);
+            oz_mbar_init(&a_empty[s], CS);
         }
         for (int s = 0; s < 2; ++s) {
             oz_mbar_init(&b_full[s], 1);
@@ -308,6 +358,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     oz_fence_before();
     __syncthreads();
+    if (CS > 1) oz_cluster_sync();                  // every CTA's barriers exist before a peer can signal them
     oz_fence_after();
     if (*tmem_ptr != 0) __trap();                   // the CTA owns all 512 columns, so the allocation starts at column 0
 
@@ -315,7 +366,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         // ============ TMA producer (warp-uniform control flow, one elected lane issues) ============
         const bool leader = oz_elect_one();
         uint32_t kbt = 0;                           // k-blocks produced so far (all tiles)
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        for (int t = t_first; t < ntiles; t += t_step) {
             const OzTile tl = oz_tile(p, t, tiles_m, tiles_n);
             for (int kb = 0; kb < tl.nkb; ++kb, ++kbt) {
                 const int k0 = tl.k_begin + kb * 128;
@@ -331,7 +382,11 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     oz_wait(&a_empty[pp], (kbt & 1) ^ 1);
                     if (leader) {
                         oz_expect_tx(&a_full[pp], OZ_A_BYTES);
-                        oz_tma_3d(sA + pp * OZ_A_BYTES, &tmA, k0, tl.m0, pp, &a_full[pp]);
+                        if (CS == 1)
+                            oz_tma_3d(sA + pp * OZ_A_BYTES, &tmA, k0, tl.m0, pp, &a_full[pp]);
+                        else      // my slab of the tile, delivered to every CTA of the cluster
+                            oz_tma_3d_mc(sA + pp * OZ_A_BYTES + crank * (OZ_A_BYTES / CS), &tmA, k0, tl.m0 + crank * (OZ_BM / CS), pp,
+                                         &a_full[pp], cmask);
                     }
                 }
             }
@@ -349,7 +404,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t desc_hi = (uint32_t)(oz_desc(0) >> 32);
         const uint32_t a_lo0 = (uint32_t)oz_desc(oz_smem_u32(sA)), b_lo0 = (uint32_t)oz_desc(oz_smem_u32(sB));
         uint32_t kbt = 0, local = 0;
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++local) {
+        for (int t = t_first; t < ntiles; t += t_step, ++local) {
             const OzTile tl = oz_tile(p, t, tiles_m, tiles_n);
             oz_wait(acc_empty, (local & 1) ^ 1);     // the previous tile has left TMEM
             oz_fence_after();
@@ -377,7 +432,8 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                 oz_umma_ss(d_tmem, oz_desc_join(desc_hi, a_lo + k * 2), bd, idesc, acc);
                             }
                         }
-                        oz_commit(&a_empty[pp]);
+                        if (CS == 1) oz_commit(&a_empty[pp]);
+                        else oz_commit_mc(&a_empty[pp], cmask);
                         if (pp == OZ_S - 1) oz_commit(&b_empty[bs]);
                     }
                     __syncwarp();
@@ -388,19 +444,21 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
     } else {
         // ============ epilogue ============
-        // Drain: TMEM -> FP64 registers (magic-number int->double, Horner over the 6 diagonals, row scale), 32 columns
-        // per thread; the accumulators are released right after, so the next tile's MMAs overlap the finish phase:
-        // column scale, bias, transfer function, stores.
+        // Drain: TMEM accumulators -> FP64 (magic-number int->double, Horner over the 6 diagonals, row scale) -> back into
+        // the 128 TMEM columns the accumulators leave free (a 128 x 64 FP64 tile is exactly 64 KB); the accumulators are
+        // released right after, so the next tile's MMAs overlap the finish phase (column scale, bias, transfer function,
+        // stores), which re-reads its values 8 at a time and therefore has the registers to interleave 8 FP64 chains
+        // (a dependent DFMA has ~36 cycles of latency on this part).
         const int half = warp >> 2;                   // columns [16 half, 16 half + 16) of the tile
         const int quarter = warp & 3;                 // TMEM lane quarter this warp may read
         const int lrow = quarter * 32 + lane;
         double *patch = sPatch + warp * 256;
         uint32_t local = 0;
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++local) {
+        for (int t = t_first; t < ntiles; t += t_step, ++local) {
             const OzTile tl = oz_tile(p, t, tiles_m, tiles_n);
             const int row = tl.m0 + lrow;
             const double ea = (row < p.M ? p.scale_a[row] : 0.0) * (1.0 / 65536.0);
-            double z[OZ_ZC];
+            const uint32_t stage_addr = ((uint32_t)(quarter * 32) << 16) + (uint32_t)(OZ_S * OZ_BN + half * 2 * OZ_ZC);
             oz_wait(acc_full, local & 1);
             oz_fence_after();
 #pragma unroll
@@ -410,14 +468,17 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 for (int d = 0; d < OZ_S; ++d)
                     oz_tmem_ld8(((uint32_t)(quarter * 32) << 16) + (uint32_t)(d * OZ_BN + half * OZ_ZC + c0), v[d]);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                double zc[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     double s = oz_i2d(v[OZ_S - 1][j]);
 #pragma unroll
                     for (int d = OZ_S - 2; d >= 0; --d) s = fma(s, 1.0 / 256.0, oz_i2d(v[d][j]));
-                    z[c0 + j] = s * ea;
+                    zc[j] = s * ea;
                 }
+                oz_tmem_st_f64x8(stage_addr + 2 * c0, zc);     // FP64 tile -> the 128 spare TMEM columns
             }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             oz_fence_before();
             __syncwarp();
             if (lane == 0) oz_arrive(acc_empty);              // accumulators free again
@@ -430,7 +491,8 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
             for (int ch = 0; ch < OZ_ZC / 8; ++ch) {
                 const int col0 = tl.n0 + half * OZ_ZC + ch * 8;
-                double r[8], x[8], zz[8], mk[8];
+                double r[8], x[8], zz[8], mk[8], zc[8];
+                oz_tmem_ld_f64x8(stage_addr + 16 * ch, zc);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int col = col0 + j;
@@ -438,7 +500,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     const double eb = ok ? __ldg(p.scale_b + col) : 0.0;
                     const double bi = (p.bias && ok) ? __ldg(p.bias + col) : 0.0;
                     mk[j] = (p.colmask && ok) ? __ldg(p.colmask + col) : 1.0;
-                    zz[j] = z[ch * 8 + j] * eb + bi;
+                    zz[j] = zc[j] * eb + bi;
                     x[j] = 0.0;
                 }
                 // the transfer function of all 8 columns in ONE basic block, so the FP64 chains interleave
@@ -466,6 +528,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     oz_fence_before();
     __syncthreads();
+    if (CS > 1) oz_cluster_sync();                  // no CTA leaves while a peer may still write into it / signal it
     if (warp == mma_warp) {
         oz_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(0u), "r"(512u));
@@ -768,27 +831,50 @@ int launch_ozaki_gemm(const int8_t *a_slices, int64_t a_rows_pad, const int8_t *
     if (args.k_per_split % 128 || args.k_per_split > OZ_MAX_K || args.splits < 1 ||
         (int64_t)args.k_per_split * (args.splits - 1) >= args.K)
         return fail(OPL_E_ARG, "ozaki GEMM: k_per_split must be a multiple of 128, <= %d, and every split non-empty", OZ_MAX_K);
+    const int64_t tiles_n = ceil_div(args.N, OZ_BN);
+    const int64_t tiles = ceil_div(args.M, OZ_BM) * tiles_n * args.splits;
+    // cluster size: consecutive n tiles share their A tile (loaded once, multicast)
+    // (pairs by default: clusters of 4 halve the traffic again but, at one 225 KB CTA per SM, leave SMs of odd-sized GPCs idle:
+    //  measured 1.75x slower; OPL_OZ_CLUSTER=4 selects them)
+    int cs = tiles_n % 2 == 0 ? 2 : 1;
+    if (const char *env = getenv("OPL_OZ_CLUSTER")) {
+        const int want = atoi(env);
+        cs = (want >= 4 && tiles_n % 4 == 0) ? 4 : ((want >= 2 && tiles_n % 2 == 0) ? 2 : 1);
+    }
     CUtensorMap ta, tb;
-    int rc = oz_tensor_map(&ta, a_slices, a_rows_pad, k_pad, OZ_BM);
+    int rc = oz_tensor_map(&ta, a_slices, a_rows_pad, k_pad, OZ_BM / cs);
     if (rc == OPL_OK) rc = oz_tensor_map(&tb, b_slices, b_rows_pad, k_pad, OZ_BN);
     if (rc != OPL_OK) return rc;
+    typedef void (*kernel_t)(const CUtensorMap, const CUtensorMap, const OzakiArgs);
+    static const kernel_t table[4][3] = {
+        {ozaki_gemm_kernel<OZ_EPI_STORE, 1>, ozaki_gemm_kernel<OZ_EPI_STORE, 2>, ozaki_gemm_kernel<OZ_EPI_STORE, 4>},
+        {ozaki_gemm_kernel<OZ_EPI_TANH, 1>, ozaki_gemm_kernel<OZ_EPI_TANH, 2>, ozaki_gemm_kernel<OZ_EPI_TANH, 4>},
+        {ozaki_gemm_kernel<OZ_EPI_SOFTPLUS, 1>, ozaki_gemm_kernel<OZ_EPI_SOFTPLUS, 2>, ozaki_gemm_kernel<OZ_EPI_SOFTPLUS, 4>},
+        {ozaki_gemm_kernel<OZ_EPI_GAUSSIAN, 1>, ozaki_gemm_kernel<OZ_EPI_GAUSSIAN, 2>, ozaki_gemm_kernel<OZ_EPI_GAUSSIAN, 4>}};
+    if (args.epi < 0 || args.epi > 3) return fail(OPL_E_ARG, "ozaki GEMM: unknown epilogue %d", args.epi);
     static bool configured = false;
     if (!configured) {
-        OPL_CUDA(cudaFuncSetAttribute(ozaki_gemm_kernel<OZ_EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
-        OPL_CUDA(cudaFuncSetAttribute(ozaki_gemm_kernel<OZ_EPI_TANH>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
-        OPL_CUDA(cudaFuncSetAttribute(ozaki_gemm_kernel<OZ_EPI_SOFTPLUS>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
-        OPL_CUDA(cudaFuncSetAttribute(ozaki_gemm_kernel<OZ_EPI_GAUSSIAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
+        for (int e = 0; e < 4; ++e)
+            for (int c = 0; c < 3; ++c)
+                OPL_CUDA(cudaFuncSetAttribute(table[e][c], cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
         configured = true;
     }
-    const int64_t tiles = ceil_div(args.M, OZ_BM) * ceil_div(args.N, OZ_BN) * args.splits;
-    const unsigned grid = (unsigned)std::min<int64_t>(tiles, sm_count());
-    switch (args.epi) {
-        case OZ_EPI_STORE: ozaki_gemm_kernel<OZ_EPI_STORE><<<grid, OZ_THREADS, OZ_SMEM, stream>>>(ta, tb, args); break;
-        case OZ_EPI_TANH: ozaki_gemm_kernel<OZ_EPI_TANH><<<grid, OZ_THREADS, OZ_SMEM, stream>>>(ta, tb, args); break;
-        case OZ_EPI_SOFTPLUS: ozaki_gemm_kernel<OZ_EPI_SOFTPLUS><<<grid, OZ_THREADS, OZ_SMEM, stream>>>(ta, tb, args); break;
-        case OZ_EPI_GAUSSIAN: ozaki_gemm_kernel<OZ_EPI_GAUSSIAN><<<grid, OZ_THREADS, OZ_SMEM, stream>>>(ta, tb, args); break;
-        default: return fail(OPL_E_ARG, "ozaki GEMM: unknown epilogue %d", args.epi);
-    }
+    const kernel_t kernel = table[args.epi][cs == 4 ? 2 : (cs == 2 ? 1 : 0)];
+    const int64_t groups = tiles / cs;
+    const int64_t nclusters = std::max<int64_t>(1, std::min<int64_t>(groups, sm_count() / cs));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(nclusters * cs));
+    cfg.blockDim = dim3(OZ_THREADS);
+    cfg.dynamicSmemBytes = OZ_SMEM;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = cs > 1 ? 1 : 0;
+    OPL_CUDA(cudaLaunchKernelEx(&cfg, kernel, ta, tb, args));
     OPL_LAUNCH_CHECK();
     if (launches) ++*launches;
     return OPL_OK;

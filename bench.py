@@ -7,7 +7,8 @@
 
 Metric (BASELINE.json): MLP obj+grad evaluations / second, and BFGS H-update HBM GB/s.
 Workload at N = 1: BASELINE configs[1] -- synthetic 60000 x 784 patterns, MLP (784,256,10),
-softplus hidden, softmax + cross entropy, FP64 parity mode.  A step = one full-batch
+softplus hidden, softmax + cross entropy, FP64 parity mode (FP64 in, FP64 out, 1e-10; the large GEMMs run as
+exact INT8 digit products on tcgen05 -- Ozaki splitting -- the rest on FP64 DMMA).  A step = one full-batch
 objective + gradient evaluation (what every optimizer step and every Wolfe probe calls).
 Multi-GPU: weak scaling, 60000 patterns per GPU, the global batch sharded by rows with one NCCL
 all-reduce of [gradient ; objective] per evaluation; value is reported in 60000-pattern
@@ -33,6 +34,8 @@ sys.path.insert(0, os.path.join(ROOT, "optimal-py-learning_b200"))
 ROWS = 60000
 SHAPE = (784, 256, 10)
 BFGS_N = 83328          # (512,128,128,10): n = 128 + 512*128 + 128*128 + 128*10
+# dram bytes (read + write) of one forward-layer-0 launch of ozaki_gemm_kernel, from the committed ncu --set full capture
+OZAKI_FWD_DRAM_BYTES = None
 METRIC = "obj+grad evals/sec"
 UNIT = "evals/s (60000-pattern full-batch obj+grad evaluations, MLP (784,256,10) softmax/CE)"
 
@@ -341,7 +344,8 @@ def run_gpu(args):
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "configs[1]: 60000x784 synthetic per GPU, MLP (784,256,10) softplus/softmax + cross "
-                               "entropy, FP64 parity mode, one full-batch obj+grad evaluation per step",
+                               "entropy, FP64 parity mode (large GEMMs: exact INT8 digit products on tcgen05, FP64 recombination), one full-batch "
+                               "obj+grad evaluation per step",
                    "rows_per_gpu": ROWS, "shape": list(SHAPE), "n_weights": int(n),
                    "parallelism": "batch rows sharded x%d, NCCL all-reduce of [grad;obj]" % world if world > 1 else "single GPU",
                    "l2": "inputs larger than L2 (X shard 376 MB, activations 3 x 123 MB vs 126 MB L2)"},
@@ -361,23 +365,38 @@ def run_gpu(args):
         per_kind = {k: sum(v) / args.steps for k, v in stage_ms.items()}
         total = sum(per_kind.values())
         line["stage_ms"] = {"%s L%d" % (names.get(k // 100, "?"), k % 100): round(v, 4) for k, v in sorted(per_kind.items())}
-        # dominant kernel: the FP64 DMMA GEMM (forward layer 0 + dW layer 0 are ~98% of the flops)
-        gemm_ms = sum(v for k, v in per_kind.items() if k // 100 in (1, 3, 5, 8))   # digit extraction counts as GEMM time
-        fwd0 = per_kind.get(100, None)
+        # dominant kernel: ozaki_gemm_kernel -- the forward-layer-0 and dW-layer-0 GEMMs (98% of the flops) as 21 exact
+        # INT8 products each on tcgen05.  Algorithmic work = the FP64 flops of those two GEMMs; the tensor-pipe peak
+        # it is held against is the measured dense tensor throughput of this pool's B200 converted to the same unit:
+        # INT8 runs at twice the BF16 rate and one FP64 multiply-add costs 21 INT8 multiply-adds.
+        gemm_ms = sum(v for k, v in per_kind.items() if k // 100 in (1, 3, 5, 8, 10))   # incl. digit extraction, fused head
+        fwd0, dw0 = per_kind.get(100, None), per_kind.get(300, None)
         fp64_peak = fp64_gemm_peak(torch)
-        gemm_flops = flops_eval
-        achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
+        oz_flops = 2.0 * ROWS * SHAPE[0] * SHAPE[1] + 2.0 * ROWS * (SHAPE[0] + 1) * SHAPE[1]
+        oz_ms = (fwd0 or 0.0) + (dw0 or 0.0)
+        achieved = oz_flops / (oz_ms * 1e-3) / 1e12 if oz_ms else None
+        int8_peak = 2.0 * peaks["bf16_tflops"]
+        peak_equiv = int8_peak / 21.0
         line["roofline"] = {
-            "bound": "tensor", "kernel": "gemm_f64_kernel (DMMA.8x8x4, FP64 tensor pipe; 5 launches per evaluation)",
-            "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-            "traffic": None,
-            "peak_source": "measured in this run: cuBLAS DGEMM 8192^3 via torch.matmul, best of 5 (MEASURED_PEAKS.json "
-                           "has no FP64 figure)",
-            "algorithmic_flops_per_eval": gemm_flops, "gemm_ms_per_eval": gemm_ms,
-            "gemm_share_of_step": gemm_ms / total if total else None,
-            "fwd_layer0": None if fwd0 is None else {
-                "flops": 2.0 * ROWS * SHAPE[0] * SHAPE[1], "ms": fwd0,
-                "tflops": 2.0 * ROWS * SHAPE[0] * SHAPE[1] / (fwd0 * 1e-3) / 1e12},
+            "bound": "tensor",
+            "kernel": "ozaki_gemm_kernel (tcgen05.mma kind::i8, TMEM accumulators, TMA; FP64-accurate: 6 radix-256 digits, "
+                      "21 exact INT8 products per FP64 product; 2 launches per evaluation)",
+            "achieved": achieved, "peak": peak_equiv, "unit": "TFLOP/s", "frac": achieved / peak_equiv if achieved else None,
+            "traffic": OZAKI_FWD_DRAM_BYTES,
+            "traffic_note": "dram__bytes_read+write of the forward launch, ncu --set full (profiles/r01_ncu_ozaki_gemm_fwd.txt); "
+                            "algorithmic bytes of that launch = X digits 323 MB + A1 and D0 246 MB",
+            "peak_source": "%s: 2 x bf16_tflops (INT8 tensor rate) / 21 INT8 multiply-adds per FP64 multiply-add" % peak_src,
+            "int8_tops_achieved": 21.0 * achieved if achieved else None, "int8_tops_peak": int8_peak,
+            "fp64_dgemm_tflops_measured": fp64_peak,
+            "vs_cublas_dgemm": achieved / fp64_peak if achieved else None,
+            "algorithmic_flops_per_launch_pair": oz_flops, "launch_pair_ms": oz_ms,
+            "fwd_layer0": None if fwd0 is None else {"flops": 2.0 * ROWS * SHAPE[0] * SHAPE[1], "ms": fwd0,
+                                                    "tflops": 2.0 * ROWS * SHAPE[0] * SHAPE[1] / (fwd0 * 1e-3) / 1e12},
+            "dw_layer0": None if dw0 is None else {"flops": 2.0 * ROWS * (SHAPE[0] + 1) * SHAPE[1], "ms": dw0,
+                                                   "tflops": 2.0 * ROWS * (SHAPE[0] + 1) * SHAPE[1] / (dw0 * 1e-3) / 1e12},
+            "whole_evaluation": {"algorithmic_flops": flops_eval, "gemm_ms": gemm_ms,
+                                 "tflops": flops_eval / (ms_per_step * 1e-3) / 1e12,
+                                 "gemm_share_of_step": gemm_ms / total if total else None},
         }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         times = cpu_objgrad_times(5, 1)

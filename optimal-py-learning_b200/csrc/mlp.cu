@@ -15,6 +15,7 @@
 // Everything is enqueued on one stream; the only host sync is the scalar readback in
 // opl_mlp_probe_scalars / the *_host entry points.
 #include <algorithm>
+#include <cstring>
 #include <vector>
 
 #include "gemm_f64.cuh"
@@ -657,6 +658,7 @@ struct opl_mlp {
     double *scal = nullptr;         // device: 4 doubles
     int *flag = nullptr;
     double *pinned = nullptr;       // host pinned: 4 doubles + flag
+    double *pinned_vec = nullptr;   // host pinned staging for the n-vector of the *_host calls (allocated on first use)
     double *masks = nullptr;        // DropoutMLP: [d0 ; d1 ; ... ; d_{L-1}] 0/1 vectors, or null
     std::vector<int64_t> mask_off;  // offset of layer l's mask (l = 0 input, l >= 1 hidden outputs)
     int64_t launches = 0;
@@ -745,6 +747,7 @@ int free_all(opl_mlp *ws) {
     cudaFree(ws->flag);
     cudaFree(ws->masks);
     cudaFreeHost(ws->pinned);
+    cudaFreeHost(ws->pinned_vec);
     for (cudaEvent_t e : ws->ev_pool) cudaEventDestroy(e);
     return OPL_OK;
 }
@@ -1332,9 +1335,13 @@ int opl_mlp_obj_jac_host(opl_mlp *ws, const double *params, double *obj_out, dou
     OPL_CUDA(cudaMemcpyAsync(ws->host_grad, params, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ws->stream));
     int rc = evaluate(ws, ws->host_grad, 0.0, nullptr, true, ws->host_grad);
     if (rc != OPL_OK) return rc;
-    OPL_CUDA(cudaMemcpyAsync(grad_out, ws->host_grad, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ws->stream));
+    // device -> pinned staging at full PCIe rate (a D2H into the caller's pageable array is several times slower),
+    // then one host memcpy after the synchronisation that read_scalars performs anyway
+    if (!ws->pinned_vec) OPL_CUDA(cudaMallocHost(&ws->pinned_vec, sizeof(double) * (size_t)(n + 1)));
+    OPL_CUDA(cudaMemcpyAsync(ws->pinned_vec, ws->host_grad, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ws->stream));
     double s[3];
     rc = read_scalars(ws, ws->host_grad, nullptr, false, s);
+    memcpy(grad_out, ws->pinned_vec, sizeof(double) * (size_t)n);
     *obj_out = s[0];
     return rc;
 }

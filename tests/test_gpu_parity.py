@@ -84,6 +84,8 @@ def test_device_api_matches_host_api_and_probe(L, golden_meta, golden_objgrad):
     ((512, 128, 128, 10), [(2, 0), (2, 0), (4, 0)], 1, 2048),   # config-3 shape
     ((256, 192, 160, 10), [(1, 0), (3, 1.5), (0, 0)], 0, 1100),  # tanh / gaussian / linear + MSE
     ((130, 140, 150, 65), [(4, 0), (2, 0), (2, 0)], 0, 1200),   # hidden softmax, wide output
+    ((300, 64, 7), [(1, 0), (4, 0)], 1, 1500),              # tanh hidden feeding the fused narrow head
+    ((96, 72, 40, 5), [(2, 0), (0, 0), (0, 0)], 0, 1111),   # linear hidden + linear output + MSE through the fused head
     ((40, 70, 33, 65), [(4, 0), (2, 0), (2, 0)], 0, 517),   # hidden softmax, wide output
     ((3, 1), [(0, 0)], 0, 5),
 ])
@@ -103,6 +105,51 @@ def test_objgrad_against_oracle_at_size(L, shape, transfers, eid, rows, precisio
     # bit-reproducible: fixed-order split-K reduction, no atomics
     obj2, grad2 = model._get_obj_jac(w.copy(), x, y)
     assert obj2 == obj and numpy.array_equal(grad2, grad)
+
+
+@pytest.mark.parametrize("M,N,K,heavy", [
+    (128, 64, 128, False), (300, 100, 500, False), (1, 1, 1, False), (257, 65, 130, True), (785, 256, 20000, True),
+    (4096, 256, 784, False),
+])
+def test_int8_digit_gemm_is_fp64_accurate(L, M, N, K, heavy):
+    """ozaki_gemm_kernel (6 radix-256 digits per operand, 21 exact INT8 products on tcgen05, FP64 recombination) against
+    torch's FP64 matmul: the engine behind the parity mode's large GEMMs has to be FP64-accurate on its own."""
+    import torch
+    from learning_b200 import _native as nat, _device as dev
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    a = torch.rand(M, K, dtype=torch.float64, device="cuda", generator=g) * 2 - 1
+    b = (torch.rand(K, N, dtype=torch.float64, device="cuda", generator=g) * 2 - 1) * 0.25
+    if heavy:   # rows / columns spanning many orders of magnitude, exact zeros, an all-zero row, a row of ones
+        b = b * torch.exp(torch.randn(K, 1, dtype=torch.float64, device="cuda", generator=g) * 3) * 1e-7
+        a[:, ::7] = 0.0
+        a[M // 2] = 0.0
+        a[0] = 1.0
+    c = torch.full((M, N), float("nan"), dtype=torch.float64, device="cuda")
+    sm, gm = ctypes.c_float(0), ctypes.c_float(0)
+    nat.check(nat.lib.opl_bench_gemm_ozaki(M, N, K, dev.ptr(a), dev.ptr(b), dev.ptr(c), 0, 1, ctypes.byref(sm), ctypes.byref(gm)))
+    torch.cuda.synchronize()
+    ref = a @ b
+    # error model: each operand is cut at 2^-48 of its row / column scale, so the bound is relative to |A| |B|
+    bound = (a.abs() @ b.abs()).clamp_min(1e-300)
+    assert float(((c - ref).abs() / bound).max()) <= 1e-11
+    assert float((c - ref).norm() / ref.norm().clamp_min(1e-300)) <= 1e-11
+    if heavy:
+        assert float(c[M // 2].abs().max()) == 0.0      # an all-zero row stays exactly zero
+
+
+def test_engines_agree_and_fused_head_matches_plain_schedule(L):
+    """The INT8 engine + fused narrow head against the plain DMMA schedule on the same model and data (config-2 layer
+    shapes, dropout masks included): both are FP64-accurate, so they agree far below the 1e-10 gate."""
+    rng = numpy.random.default_rng(5)
+    shape, transfers, eid = (784, 256, 10), [(2, 0), (4, 0)], 1
+    x, y = mo.random_classification(5000, 784, 10, rng)
+    w = mo.random_params(shape, rng)
+    a = _model(L, shape, transfers, eid, precision="f64")
+    b = _model(L, shape, transfers, eid, precision="f64-dmma")
+    oa, ga = a._get_obj_jac(w.copy(), x, y)
+    ob, gb = b._get_obj_jac(w.copy(), x, y)
+    assert rel_err(oa, ob) <= 1e-12 and rel_err(ga, gb) <= 1e-11, (rel_err(oa, ob), rel_err(ga, gb))
+    assert rel_err(a._get_obj(w.copy(), x, y), ob) <= 1e-12
 
 
 def test_full_size_properties_config2(L):

@@ -35,7 +35,7 @@ ROWS = 60000
 SHAPE = (784, 256, 10)
 BFGS_N = 83328          # (512,128,128,10): n = 128 + 512*128 + 128*128 + 128*10
 # dram bytes (read + write) of one forward-layer-0 launch of ozaki_gemm_kernel, from the committed ncu --set full capture
-OZAKI_FWD_DRAM_BYTES = None
+OZAKI_FWD_DRAM_BYTES = 326867968 + 213068544
 METRIC = "obj+grad evals/sec"
 UNIT = "evals/s (60000-pattern full-batch obj+grad evaluations, MLP (784,256,10) softmax/CE)"
 
@@ -383,7 +383,7 @@ def run_gpu(args):
                       "21 exact INT8 products per FP64 product; 2 launches per evaluation)",
             "achieved": achieved, "peak": peak_equiv, "unit": "TFLOP/s", "frac": achieved / peak_equiv if achieved else None,
             "traffic": OZAKI_FWD_DRAM_BYTES,
-            "traffic_note": "dram__bytes_read+write of the forward launch, ncu --set full (profiles/r01_ncu_ozaki_gemm_fwd.txt); "
+            "traffic_note": "dram__bytes_read+write of the forward launch, ncu --set full (profiles/r01_ncu_final_kernels.txt); "
                             "algorithmic bytes of that launch = X digits 323 MB + A1 and D0 246 MB",
             "peak_source": "%s: 2 x bf16_tflops (INT8 tensor rate) / 21 INT8 multiply-adds per FP64 multiply-add" % peak_src,
             "int8_tops_achieved": 21.0 * achieved if achieved else None, "int8_tops_peak": int8_peak,

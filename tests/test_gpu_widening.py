@@ -50,6 +50,28 @@ def test_dropout_mlp_training_matches_reference(L, golden_meta, wide):
         _get_active_neurons(0.0, 4)
 
 
+def test_dropout_mlp_engines_agree_at_size(L, monkeypatch):
+    """DropoutMLP at a size where the INT8 engine and the fused head are active (masks folded into W0 / dW0 rows and
+    into the forward epilogue): identical seeds give identical masks, so three steps on the INT8 engine and on the
+    plain DMMA schedule must leave the same weights."""
+    rng = numpy.random.default_rng(3)
+    x = rng.random((2048, 200)) * 2 - 1
+    y = numpy.zeros((2048, 6))
+    y[numpy.arange(2048), rng.integers(0, 6, 2048)] = 1.0
+    weights = {}
+    for precision in ("f64", "f64-dmma"):
+        monkeypatch.setenv("OPL_PRECISION", precision)
+        random.seed(11)
+        numpy.random.seed(11)
+        model = L.DropoutMLP((200, 96, 6), transfers=[L.ReluTransfer(), L.SoftmaxTransfer()], error_func=L.CrossEntropyError(),
+                             input_active_probability=0.8, hidden_active_probability=0.6)
+        model.logging = False
+        errs = [model.train_step(x, y) for _ in range(3)]
+        assert all(numpy.isfinite(errs))
+        weights[precision] = numpy.hstack([model._bias_vec] + [m.ravel() for m in model._weight_matrices])
+    assert rel_err(weights["f64"], weights["f64-dmma"]) <= 1e-10, rel_err(weights["f64"], weights["f64-dmma"])
+
+
 def test_regression_models_match_reference(L, golden_meta, wide):
     for case in golden_meta["regression"]:
         k = case["key"]

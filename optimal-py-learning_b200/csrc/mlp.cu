@@ -1335,13 +1335,20 @@ int opl_mlp_obj_jac_host(opl_mlp *ws, const double *params, double *obj_out, dou
     OPL_CUDA(cudaMemcpyAsync(ws->host_grad, params, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ws->stream));
     int rc = evaluate(ws, ws->host_grad, 0.0, nullptr, true, ws->host_grad);
     if (rc != OPL_OK) return rc;
-    // device -> pinned staging at full PCIe rate (a D2H into the caller's pageable array is several times slower),
-    // then one host memcpy after the synchronisation that read_scalars performs anyway
-    if (!ws->pinned_vec) OPL_CUDA(cudaMallocHost(&ws->pinned_vec, sizeof(double) * (size_t)(n + 1)));
-    OPL_CUDA(cudaMemcpyAsync(ws->pinned_vec, ws->host_grad, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ws->stream));
+    // A page-locked destination (e.g. an array handed out by a pinned allocator) takes the gradient at the full PCIe rate
+    // directly; a pageable one is several times slower as a D2H target, so it goes device -> pinned staging -> one host
+    // memcpy after the synchronisation that read_scalars performs anyway.
+    cudaPointerAttributes attr;
+    const bool direct = cudaPointerGetAttributes(&attr, grad_out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    if (!direct) {
+        cudaGetLastError();   // (older drivers report unregistered host memory as an error)
+        if (!ws->pinned_vec) OPL_CUDA(cudaMallocHost(&ws->pinned_vec, sizeof(double) * (size_t)(n + 1)));
+    }
+    OPL_CUDA(cudaMemcpyAsync(direct ? grad_out : ws->pinned_vec, ws->host_grad, sizeof(double) * (size_t)n,
+                             cudaMemcpyDeviceToHost, ws->stream));
     double s[3];
     rc = read_scalars(ws, ws->host_grad, nullptr, false, s);
-    memcpy(grad_out, ws->pinned_vec, sizeof(double) * (size_t)n);
+    if (!direct) memcpy(grad_out, ws->pinned_vec, sizeof(double) * (size_t)n);
     *obj_out = s[0];
     return rc;
 }

@@ -237,7 +237,9 @@ class _KernelModel(Model):
         if not want_grad:
             nat.check(nat.lib.opl_mlp_obj_host(ws.pointer, params.ctypes.data_as(ctypes.c_void_p), ctypes.byref(obj)))
             return obj.value, None
-        grad = numpy.empty_like(params)
+        # a FRESH array per call (the optimizers keep references to earlier gradients), page-locked so the
+        # download runs at the PCIe rate straight into it; torch's caching host allocator recycles the blocks
+        grad = torch.empty(params.shape[0], dtype=torch.float64, pin_memory=True).numpy()
         nat.check(nat.lib.opl_mlp_obj_jac_host(ws.pointer, params.ctypes.data_as(ctypes.c_void_p),
                                                ctypes.byref(obj), grad.ctypes.data_as(ctypes.c_void_p)))
         self.obj_jac_evaluations += 1

@@ -915,6 +915,19 @@ int backward(opl_mlp *ws, const double *w, const double *x, int64_t rows, double
             ++ws->launches;
             continue;
         }
+        if (int8_da_ok(ws, l, rows)) {
+            int rc = int8_da_layer(ws, l, w, rows);
+            if (rc != OPL_OK) return rc;
+            if (ws->transfer[l - 1] == OPL_TRANSFER_SOFTMAX) {
+                mark(ws, STAGE_ROWS * 100 + l - 1);
+                const int group = row_group(din);
+                softmax_backward_rows_kernel<double><<<row_grid(rows, group), 256, 0, ws->stream>>>(
+                    ws->delta[l - 1], ws->act[l], rows, din, din, group);
+                OPL_LAUNCH_CHECK();
+                ++ws->launches;
+            }
+            continue;
+        }
         GemmArgs a = {};
         a.A = ws->delta[l];
         a.lda = dout;

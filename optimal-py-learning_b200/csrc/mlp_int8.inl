@@ -11,7 +11,7 @@
 // Layers that are too small for the tensor-core tile (the narrow head) stay on the DMMA / streaming kernels.
 
 struct Int8State {
-    std::vector<char> fwd, dw;         // per layer: shape qualifies
+    std::vector<char> fwd, dw, da;     // per layer: shape qualifies (da[l]: delta_{l-1} = delta_l W_l^T)
     int64_t rows_pad = 0;              // pad128(max_rows)
     // layer-0 operands, constant between set_data calls
     int8_t *x_dig = nullptr;           // [S][rows_pad][pad(d0)]
@@ -88,6 +88,7 @@ int int8_create(opl_mlp *ws, int64_t *partials_needed) {
     Int8State *s = new Int8State();
     s->fwd.assign(L, 0);
     s->dw.assign(L, 0);
+    s->da.assign(L, 0);
     s->rows_pad = ozaki_pad(ws->max_rows);
     bool any = false;
     int64_t w_bytes = 0, a_cols = 0, d_cols = 0, at_rows = 0, scale_len = 0;
@@ -101,7 +102,8 @@ int int8_create(opl_mlp *ws, int64_t *partials_needed) {
         scale_len = std::max<int64_t>(scale_len, std::max(ozaki_pad(dout), ozaki_pad(din + 1)));
         d_cols = std::max<int64_t>(d_cols, ozaki_pad(dout));
         if (l >= 1) {
-            a_cols = std::max<int64_t>(a_cols, ozaki_pad(din));
+            s->da[l] = 1;
+            a_cols = std::max<int64_t>(a_cols, std::max(ozaki_pad(din), ozaki_pad(dout)));   // A_l rows (forward), delta_l rows (dA)
             at_rows = std::max<int64_t>(at_rows, ozaki_pad(din));
         }
         const Int8Plan plan = int8_plan(din + (l == 0 ? 1 : 0), dout, s->rows_pad);
@@ -225,6 +227,48 @@ int int8_forward_layer(opl_mlp *ws, int l, const double *w, const double *in, in
     if (kp > OZ_MAX_K) return fail(OPL_E_STATE, "int8 forward: layer %d is wider than %d inputs", l, OZ_MAX_K);
     mark(ws, STAGE_FWD * 100 + l);
     return launch_ozaki_gemm(a_dig, a_rows_pad, s->w_dig, np, kp, g, ws->stream, &ws->launches);
+}
+
+bool int8_da_ok(const opl_mlp *ws, int l, int64_t rows) { return l >= 1 && int8_use(ws, rows) && ws->int8->da[l]; }
+
+// delta_{l-1} = (delta_l W_l^T) o f'_{l-1}: A = delta_l (row digits, one scale per pattern), B = W_l, which is already
+// [N = din][K = dout] with K contiguous, so its row digits (one scale per hidden unit) are the operand as it stands
+int int8_da_layer(opl_mlp *ws, int l, const double *w, int64_t rows) {
+    Int8State *s = ws->int8;
+    const int64_t din = ws->width[l], dout = ws->width[l + 1];
+    const int64_t kp = ozaki_pad(dout), np = ozaki_pad(din), mp = ozaki_pad(rows);
+    if (kp > OZ_MAX_K) return fail(OPL_E_STATE, "int8 back-propagation: layer %d is wider than %d outputs", l, OZ_MAX_K);
+    mark(ws, STAGE_DIGITS * 100 + 70 + l);
+    int rc = ozaki_slice_rows(w + ws->w_off[l], din, dout, dout, s->w_dig, s->w_scale, false, ws->stream, &ws->launches);
+    if (rc != OPL_OK) return rc;
+    rc = ozaki_slice_rows(ws->delta[l], rows, dout, dout, s->a_dig, s->a_scale, false, ws->stream, &ws->launches);
+    if (rc != OPL_OK) return rc;
+    OzakiArgs g = {};
+    g.C = ws->delta[l - 1];
+    g.ldc = din;
+    g.M = (int)rows;
+    g.N = (int)din;
+    g.K = (int)kp;
+    g.k_per_split = (int)kp;
+    g.splits = 1;
+    g.scale_a = s->a_scale;
+    g.scale_b = s->w_scale;
+    g.ldaux = din;
+    switch (ws->transfer[l - 1]) {
+        case OPL_TRANSFER_SOFTPLUS:
+        case OPL_TRANSFER_GAUSSIAN:
+            g.epi = OZ_EPI_MUL_AUX;
+            g.aux_in = ws->deriv[l - 1];
+            break;
+        case OPL_TRANSFER_TANH:
+            g.epi = OZ_EPI_MUL_DTANH;
+            g.aux_in = ws->act[l];
+            break;
+        default:
+            g.epi = OZ_EPI_STORE;
+    }
+    mark(ws, STAGE_DA * 100 + l);
+    return launch_ozaki_gemm(s->a_dig, mp, s->w_dig, np, kp, g, ws->stream, &ws->launches);
 }
 
 // dW_l = A_l^T delta_l (+ db = 1^T delta_0 for l = 0) into the flat gradient

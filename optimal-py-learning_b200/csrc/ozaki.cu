@@ -288,8 +288,10 @@ __device__ __forceinline__ OzTile oz_tile(const OzakiArgs &p, int t, int tiles_m
 
 // one 8-column chunk of a warp's 32 rows: registers -> per-warp shared patch -> 64-byte row segments in global memory.
 // Patch row = 64 bytes = four 16-byte chunks, chunk c of row r stored at c ^ ((r >> 1) & 3): conflict-free both ways.
+// MUL: 0 plain store, 1 value x mul[same position], 2 value x (1 - mul^2) -- read where it is written, so mul may alias base
+template <int MUL>
 __device__ __forceinline__ void oz_store_chunk(double *patch, const double (&v)[8], double *base, int64_t ld, int row0, int col0,
-                                               int M, int N, bool vec, int lane) {
+                                               int M, int N, bool vec, int lane, const double *mul = nullptr) {
     double2 *pw = reinterpret_cast<double2 *>(patch + lane * 8);
 #pragma unroll
     for (int j = 0; j < 4; ++j) pw[j ^ ((lane >> 1) & 3)] = make_double2(v[2 * j], v[2 * j + 1]);
@@ -298,14 +300,31 @@ __device__ __forceinline__ void oz_store_chunk(double *patch, const double (&v)[
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int prow = (lane >> 2) + 8 * i, grow = row0 + prow;
-        const double2 q = *reinterpret_cast<const double2 *>(patch + prow * 8 + 2 * (pc ^ ((prow >> 1) & 3)));
+        double2 q = *reinterpret_cast<const double2 *>(patch + prow * 8 + 2 * (pc ^ ((prow >> 1) & 3)));
         if (grow < M) {
             double *dst = base + (int64_t)grow * ld + gcol;
             if (vec && gcol + 1 < N) {
+                if (MUL != 0) {
+                    const double2 m = *reinterpret_cast<const double2 *>(mul + (int64_t)grow * ld + gcol);
+                    q.x *= MUL == 1 ? m.x : 1.0 - m.x * m.x;
+                    q.y *= MUL == 1 ? m.y : 1.0 - m.y * m.y;
+                }
                 *reinterpret_cast<double2 *>(dst) = q;
             } else {
-                if (gcol < N) dst[0] = q.x;
-                if (gcol + 1 < N) dst[1] = q.y;
+                if (gcol < N) {
+                    if (MUL != 0) {
+                        const double m = mul[(int64_t)grow * ld + gcol];
+                        q.x *= MUL == 1 ? m : 1.0 - m * m;
+                    }
+                    dst[0] = q.x;
+                }
+                if (gcol + 1 < N) {
+                    if (MUL != 0) {
+                        const double m = mul[(int64_t)grow * ld + gcol + 1];
+                        q.y *= MUL == 1 ? m : 1.0 - m * m;
+                    }
+                    dst[1] = q.y;
+                }
             }
         }
     }
@@ -521,8 +540,10 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
                     for (int j = 0; j < 8; ++j) r[j] = zz[j] * mk[j];
                 }
-                oz_store_chunk(patch, r, C, p.ldc, row0, col0, p.M, p.N, vec_c, lane);
-                if (want_x) oz_store_chunk(patch, x, p.aux_out, p.ldaux, row0, col0, p.M, p.N, vec_x, lane);
+                constexpr int MUL = EPI == OZ_EPI_MUL_AUX ? 1 : (EPI == OZ_EPI_MUL_DTANH ? 2 : 0);
+                oz_store_chunk<MUL>(patch, r, C, p.ldc, row0, col0, p.M, p.N,
+                                    vec_c && (MUL == 0 || (reinterpret_cast<uintptr_t>(p.aux_in) & 15) == 0), lane, p.aux_in);
+                if (want_x) oz_store_chunk<0>(patch, x, p.aux_out, p.ldaux, row0, col0, p.M, p.N, vec_x, lane);
             }
         }
     }
@@ -846,15 +867,18 @@ int launch_ozaki_gemm(const int8_t *a_slices, int64_t a_rows_pad, const int8_t *
     if (rc == OPL_OK) rc = oz_tensor_map(&tb, b_slices, b_rows_pad, k_pad, OZ_BN);
     if (rc != OPL_OK) return rc;
     typedef void (*kernel_t)(const CUtensorMap, const CUtensorMap, const OzakiArgs);
-    static const kernel_t table[4][3] = {
+    static const kernel_t table[6][3] = {
         {ozaki_gemm_kernel<OZ_EPI_STORE, 1>, ozaki_gemm_kernel<OZ_EPI_STORE, 2>, ozaki_gemm_kernel<OZ_EPI_STORE, 4>},
         {ozaki_gemm_kernel<OZ_EPI_TANH, 1>, ozaki_gemm_kernel<OZ_EPI_TANH, 2>, ozaki_gemm_kernel<OZ_EPI_TANH, 4>},
         {ozaki_gemm_kernel<OZ_EPI_SOFTPLUS, 1>, ozaki_gemm_kernel<OZ_EPI_SOFTPLUS, 2>, ozaki_gemm_kernel<OZ_EPI_SOFTPLUS, 4>},
-        {ozaki_gemm_kernel<OZ_EPI_GAUSSIAN, 1>, ozaki_gemm_kernel<OZ_EPI_GAUSSIAN, 2>, ozaki_gemm_kernel<OZ_EPI_GAUSSIAN, 4>}};
-    if (args.epi < 0 || args.epi > 3) return fail(OPL_E_ARG, "ozaki GEMM: unknown epilogue %d", args.epi);
+        {ozaki_gemm_kernel<OZ_EPI_GAUSSIAN, 1>, ozaki_gemm_kernel<OZ_EPI_GAUSSIAN, 2>, ozaki_gemm_kernel<OZ_EPI_GAUSSIAN, 4>},
+        {ozaki_gemm_kernel<OZ_EPI_MUL_AUX, 1>, ozaki_gemm_kernel<OZ_EPI_MUL_AUX, 2>, ozaki_gemm_kernel<OZ_EPI_MUL_AUX, 4>},
+        {ozaki_gemm_kernel<OZ_EPI_MUL_DTANH, 1>, ozaki_gemm_kernel<OZ_EPI_MUL_DTANH, 2>, ozaki_gemm_kernel<OZ_EPI_MUL_DTANH, 4>}};
+    if (args.epi < 0 || args.epi > 5) return fail(OPL_E_ARG, "ozaki GEMM: unknown epilogue %d", args.epi);
+    if (args.epi >= OZ_EPI_MUL_AUX && !args.aux_in) return fail(OPL_E_ARG, "ozaki GEMM: epilogue %d needs aux_in", args.epi);
     static bool configured = false;
     if (!configured) {
-        for (int e = 0; e < 4; ++e)
+        for (int e = 0; e < 6; ++e)
             for (int c = 0; c < 3; ++c)
                 OPL_CUDA(cudaFuncSetAttribute(table[e][c], cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
         configured = true;

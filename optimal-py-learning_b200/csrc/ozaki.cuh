@@ -11,7 +11,11 @@ constexpr int OZ_BM = 128;
 constexpr int OZ_BN = 64;        // 6 diagonal accumulators x 64 INT32 columns = 384 of 512 TMEM columns
 constexpr int OZ_MAX_K = 16384;  // 6 * 16384 * 128^2 < 2^31: INT32 accumulation stays exact
 
-enum OzakiEpilogue { OZ_EPI_STORE = 0, OZ_EPI_TANH = 1, OZ_EPI_SOFTPLUS = 2, OZ_EPI_GAUSSIAN = 3 };
+enum OzakiEpilogue {
+    OZ_EPI_STORE = 0, OZ_EPI_TANH = 1, OZ_EPI_SOFTPLUS = 2, OZ_EPI_GAUSSIAN = 3,   // forward: transfer (+ derivative into aux_out)
+    OZ_EPI_MUL_AUX = 4,      // back-propagation: C = (A.B) o aux_in            (aux_in = f' stored by the forward pass; may alias C)
+    OZ_EPI_MUL_DTANH = 5     // back-propagation: C = (A.B) o (1 - aux_in^2)    (aux_in = the tanh activation)
+};
 
 struct OzakiArgs {
     double *C;
@@ -25,6 +29,7 @@ struct OzakiArgs {
     const double *bias;
     double *aux_out;
     int64_t ldaux;
+    const double *aux_in;     // OZ_EPI_MUL_*: same leading dimension as C
     int epi;
     double tparam;
     const double *colmask;

@@ -28,6 +28,7 @@
 //               inside the SM's shared-memory bandwidth.
 // Tried and dropped (profiles/r01_ozaki_gemm_variants_v3.txt): staging A in the spare TMEM columns by tcgen05.cp
 // (no faster than SS once the MMAs were merged: the copy serialises with the MMAs) or by loader warps + tcgen05.st.
+#include <cooperative_groups.h>
 #include <cudaTypedefs.h>
 
 #include <algorithm>
@@ -675,13 +676,15 @@ __global__ void colabsmax_final_kernel(const double *__restrict__ partial, int n
 // plane, the block then writes 128-byte output rows.
 // Scale source: MODE 0 `scale` holds finished scales; MODE 1 `colmax` holds raw column maxima (bit patterns gathered
 // with atomicMax by the producer of src), the scale is derived here and block row 0 publishes it; MODE 2 (small
-// matrices) every block first scans its 32 columns over ALL rows itself, then walks all row chunks (grid.x == 1).
+// matrices) every block first scans its 32 columns over ALL rows itself, then walks all row chunks (grid.x == 1);
+// MODE 3 (cooperative launch, matrices whose grid is co-resident: the weight matrices) every block leaves the maxima of
+// its own 128 x 32 patch in `partial`, the grid synchronises, and the maxima are folded from there: one launch instead of three.
 template <int MODE>
 __global__ void __launch_bounds__(256) slice_cols_transposed_kernel(const double *__restrict__ src, int64_t rows, int64_t cols,
                                                                     int64_t ld, double *__restrict__ scale,
                                                                     const double *__restrict__ colmax,
                                                                     int8_t *__restrict__ out, int64_t cols_pad, int64_t rows_pad,
-                                                                    int64_t row_off) {
+                                                                    int64_t row_off, double *partial) {
     __shared__ uint32_t tile[OZ_S][32][33];    // [digit][col][word along rows], padded
     __shared__ double smax[8][33];
     const int64_t c0 = blockIdx.y * 32;
@@ -693,6 +696,42 @@ __global__ void __launch_bounds__(256) slice_cols_transposed_kernel(const double
     } else if (MODE == 1) {
         if (c < cols) {
             sc = oz_scale_of(colmax[c]);
+            if (blockIdx.x == 0 && ty == 0) scale[c] = sc;
+        }
+    } else if (MODE == 3) {
+        double m = 0.0;
+        bool bad = false;
+        const int64_t rb = blockIdx.x * 128;
+        if (c < cols)
+            for (int64_t r = rb + ty; r < min(rows, rb + 128); r += 8) {
+                const double v = fabs(src[r * ld + c]);
+                bad |= !(v <= 1.7976931348623157e308);
+                m = fmax(m, v);
+            }
+        smax[ty][tx] = bad ? __longlong_as_double(0x7ff8000000000000LL) : m;
+        __syncthreads();
+        if (ty == 0 && c < cols) {
+            double t = 0.0;
+            bool nan = false;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const double v = smax[k][tx];
+                nan |= v != v;
+                t = fmax(t, v);
+            }
+            partial[blockIdx.x * cols + c] = nan ? __longlong_as_double(0x7ff8000000000000LL) : t;
+        }
+        __threadfence();
+        cooperative_groups::this_grid().sync();
+        if (c < cols) {
+            double t = 0.0;
+            bool nan = false;
+            for (unsigned k = 0; k < gridDim.x; ++k) {
+                const double v = __ldcg(partial + k * cols + c);
+                nan |= v != v;
+                t = fmax(t, v);
+            }
+            sc = nan ? __longlong_as_double(0x7ff8000000000000LL) : oz_scale_of(t);
             if (blockIdx.x == 0 && ty == 0) scale[c] = sc;
         }
     } else {
@@ -820,17 +859,36 @@ int ozaki_slice_cols_transposed(const double *src, int64_t rows, int64_t cols, i
     const unsigned gy = (unsigned)ceil_div(cols, 32);
     if (colmax_raw) {            // maxima gathered by the kernel that produced src
         slice_cols_transposed_kernel<1><<<dim3((unsigned)ceil_div(rp, 128), gy), 256, 0, stream>>>(
-            src, rows, cols, ld, scale + row_off, colmax_raw, slices, cp, rp, row_off);
+            src, rows, cols, ld, scale + row_off, colmax_raw, slices, cp, rp, row_off, nullptr);
         OPL_LAUNCH_CHECK();
         if (launches) *launches += 1;
         return OPL_OK;
     }
     if (rows <= 256) {           // tiny matrix: one launch, every block scans its own columns
         slice_cols_transposed_kernel<2><<<dim3(1, gy), 256, 0, stream>>>(src, rows, cols, ld, scale + row_off, nullptr, slices, cp, rp,
-                                                                         row_off);
+                                                                         row_off, nullptr);
         OPL_LAUNCH_CHECK();
         if (launches) *launches += 1;
         return OPL_OK;
+    }
+    {   // the whole grid fits on the device at once (weight matrices): cooperative single launch
+        const int64_t gx = ceil_div(rp, 128);
+        static int coop_blocks_per_sm = -1;
+        if (coop_blocks_per_sm < 0) {
+            int v = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, slice_cols_transposed_kernel<3>, 256, 0) != cudaSuccess) v = 0;
+            coop_blocks_per_sm = v;
+        }
+        if (gx * gy <= (int64_t)coop_blocks_per_sm * sm_count() && gx * cols <= scratch_len) {
+            double *scale_p = scale + row_off;
+            const double *no_colmax = nullptr;
+            void *params[] = {(void *)&src, (void *)&rows, (void *)&cols, (void *)&ld, (void *)&scale_p, (void *)&no_colmax,
+                              (void *)&slices, (void *)&cp, (void *)&rp, (void *)&row_off, (void *)&scratch};
+            OPL_CUDA(cudaLaunchCooperativeKernel((const void *)slice_cols_transposed_kernel<3>, dim3((unsigned)gx, gy), dim3(256),
+                                                 params, 0, stream));
+            if (launches) *launches += 1;
+            return OPL_OK;
+        }
     }
     int64_t nblk = std::max<int64_t>(1, std::min<int64_t>(ceil_div(rows, 256), scratch_len / std::max<int64_t>(cols, 1)));
     nblk = std::min<int64_t>(nblk, 4 * (int64_t)sm_count());
@@ -840,7 +898,7 @@ int ozaki_slice_cols_transposed(const double *src, int64_t rows, int64_t cols, i
     colabsmax_partial_kernel<<<g1, dim3(32, 8), 0, stream>>>(src, rows, cols, ld, rpb, scratch);
     colabsmax_final_kernel<<<(unsigned)ceil_div(cols, 256), 256, 0, stream>>>(scratch, (int)nblk, cols, scale + row_off);
     slice_cols_transposed_kernel<0><<<dim3((unsigned)ceil_div(rp, 128), gy), 256, 0, stream>>>(
-        src, rows, cols, ld, scale + row_off, nullptr, slices, cp, rp, row_off);
+        src, rows, cols, ld, scale + row_off, nullptr, slices, cp, rp, row_off, nullptr);
     OPL_LAUNCH_CHECK();
     if (launches) *launches += 3;
     return OPL_OK;

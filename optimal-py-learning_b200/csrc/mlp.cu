@@ -331,12 +331,13 @@ struct HeadArgs {
 // (double buffer) and the step's slope values are requested before the logits are computed, so every global load has
 // a whole phase of compute to hide behind.  Leading dimensions (H+4, 20) make every fragment load conflict-free.
 // The row stage (softmax / error / delta_L) runs one pattern per half-warp, lane = class.
-constexpr int HEAD_R = 32, HEAD_THREADS = 512, HEAD_WARPS = 16;
-template <int MT>    // hidden tiles (8 units) per warp: H <= 128 MT
-__global__ void __launch_bounds__(HEAD_THREADS, 1) narrow_head_kernel(const HeadArgs p) {
+// Two shapes: R = 32 patterns per step with 16 warps (one CTA per SM) or R = 16 with 8 warps (two CTAs per SM, whose
+// latency-bound row stages and DMMA phases overlap each other).
+template <int MT, int R, int HEAD_WARPS>    // MT = hidden tiles (8 units) per warp: H <= 8 MT HEAD_WARPS
+__global__ void __launch_bounds__(HEAD_WARPS * 32, R == 16 ? 2 : 1) narrow_head_kernel(const HeadArgs p) {
     extern __shared__ double hsm[];
     __shared__ double scratch[33];
-    constexpr int R = HEAD_R, RM = R / 8;
+    constexpr int RM = R / 8, HEAD_THREADS = HEAD_WARPS * 32;
     const int H = p.H, C = p.C;
     const int ldA = H + 4;
     constexpr int ldW = 20, ldD = 20;
@@ -401,7 +402,7 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) narrow_head_kernel(const Head
         if (blk + gridDim.x < nblocks) fetch(blk + gridDim.x, buf ^ 1);
         // ---- logits: warp -> (row tile, class tile, K half); the two halves add up in Zs ----
         {
-            const int mt = warp & 3, nt = (warp >> 2) & 1, kh = warp >> 3;
+            const int mt = warp % RM, nt = (warp / RM) & 1, kh = warp / (2 * RM);
             double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;       // two independent accumulation chains
             const int kq = H >> 3;                                // DMMA steps per half
             const double *ap = As + (size_t)(8 * mt + g) * ldA + 4 * kh * kq + t;
@@ -419,6 +420,7 @@ __global__ void __launch_bounds__(HEAD_THREADS, 1) narrow_head_kernel(const Head
         __syncthreads();
         // ---- output transfer + error + delta_L: one pattern per half-warp, lane = class ----
         {
+            static_assert(HEAD_WARPS * 2 == R && 4 * RM == HEAD_WARPS, "one pattern per half-warp, two K halves per logits tile");
             const int hw = lane >> 4, cl = lane & 15;
             const int r = warp * 2 + hw;
             const bool live = r < nr && cl < C;
@@ -969,22 +971,27 @@ int backward(opl_mlp *ws, const double *w, const double *x, int64_t rows, double
 }
 
 // Can the fused narrow head replace forward(last layer) + output stage + the head's back-propagation?
-size_t head_smem(int H) { return sizeof(double) * ((size_t)H * 20 + (size_t)HEAD_R * 20 + 2 * (size_t)HEAD_R * (H + 4)); }
+size_t head_smem(int H, int R) { return sizeof(double) * ((size_t)H * 20 + (size_t)R * 20 + 2 * (size_t)R * (H + 4)); }
 int head_rows_per_step(const opl_mlp *ws) {
     const int L = ws->layers;
     if (L < 2 || ws->precision != OPL_PRECISION_F64 || !ws->fused_head) return 0;
     const int64_t H = ws->width[L - 1], C = ws->width[L];
-    if (C > 16 || H > 512 || (H & 7) || H < 32) return 0;
+    if (C > 16 || H > 256 || (H & 7) || H < 32) return 0;
     if (ws->transfer[L - 2] == OPL_TRANSFER_SOFTMAX) return 0;
-    return head_smem((int)H) <= 220 * 1024 ? HEAD_R : 0;
+    static int r16 = -1;
+    if (r16 < 0) {
+        const char *env = getenv("OPL_HEAD_R");
+        r16 = (env && atoi(env) == 32) ? 0 : 1;
+    }
+    return r16 ? 16 : 32;
 }
 
 // fused head: objective (and, when want_grad, dW_{L-1} and delta_{L-2}); the caller continues back-propagation at L-2
 int fused_head(opl_mlp *ws, const double *w, const double *y, int64_t rows, bool want_grad, double *grad, double *obj_out) {
     const int L = ws->layers, R = head_rows_per_step(ws);
     const int H = (int)ws->width[L - 1], C = (int)ws->width[L];
-    const size_t smem = head_smem(H);
-    int grid = (int)std::min<int64_t>(ceil_div(rows, R), (int64_t)sm_count());
+    const size_t smem = head_smem(H, R);
+    int grid = (int)std::min<int64_t>(ceil_div(rows, R), (int64_t)sm_count() * (R == 16 ? 2 : 1));
     grid = std::min(grid, ws->loss_blocks);
     if (want_grad) grid = (int)std::min<int64_t>(grid, ws->partials_len / ((int64_t)H * C));
     if (grid < 1) return fail(OPL_E_STATE, "fused head: scratch too small");
@@ -1013,15 +1020,15 @@ int fused_head(opl_mlp *ws, const double *w, const double *y, int64_t rows, bool
     }
     static bool configured = false;
     if (!configured) {
-        OPL_CUDA(cudaFuncSetAttribute(narrow_head_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        OPL_CUDA(cudaFuncSetAttribute(narrow_head_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        OPL_CUDA(cudaFuncSetAttribute(narrow_head_kernel<2, 32, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_smem(256, 32)));
+        OPL_CUDA(cudaFuncSetAttribute(narrow_head_kernel<4, 16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_smem(256, 16)));
         configured = true;
     }
     mark(ws, STAGE_HEAD * 100 + L - 1);
-    if (H <= 256)
-        narrow_head_kernel<2><<<grid, HEAD_THREADS, smem, ws->stream>>>(a);
+    if (R == 32)
+        narrow_head_kernel<2, 32, 16><<<grid, 512, smem, ws->stream>>>(a);
     else
-        narrow_head_kernel<4><<<grid, HEAD_THREADS, smem, ws->stream>>>(a);
+        narrow_head_kernel<4, 16, 8><<<grid, 256, smem, ws->stream>>>(a);
     OPL_LAUNCH_CHECK();
     ++ws->launches;
     mark(ws, STAGE_LOSS * 100);
@@ -1190,7 +1197,7 @@ int opl_mlp_create(opl_mlp **out, int32_t n_widths, const int64_t *widths, const
             ws->fused_head = false;
         }
         if (L >= 2)      // per-CTA dW partials of the fused narrow head
-            partials = std::max<int64_t>(partials, 2 * (int64_t)sm_count() * widths[L - 1] * widths[L]);
+            partials = std::max<int64_t>(partials, 2 * (int64_t)sm_count() * widths[L - 1] * widths[L]);   // up to 2 CTAs per SM
         int rc = int8_create(ws, &partials);
         if (rc != OPL_OK) {
             free_all(ws);

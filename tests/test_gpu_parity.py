@@ -152,6 +152,29 @@ def test_engines_agree_and_fused_head_matches_plain_schedule(L):
     assert rel_err(a._get_obj(w.copy(), x, y), ob) <= 1e-12
 
 
+@pytest.mark.parametrize("precision", ["f64", "f64-dmma"])
+def test_saturated_head_keeps_reference_semantics(L, precision):
+    """Degenerate numerics on the fused-head / INT8 path: logits so large that target-class probabilities underflow to
+    exactly 0 (log(0) -> nan_to_num -> -1.797e308 in the loss, Y/A -> 1.797e308 and a zero softmax Jacobian row in the
+    gradient, error.py:89-116), and a linear output + cross entropy whose negative prediction must raise
+    FloatingPointError (error.py:89-91)."""
+    rng = numpy.random.default_rng(9)
+    shape, transfers = (48, 64, 6), [(1, 0), (4, 0)]
+    x, y = mo.random_classification(1300, 48, 6, rng)
+    w = mo.random_params(shape, rng)
+    w[64 + 48 * 64:] *= 4000.0                       # saturate the softmax
+    with numpy.errstate(all="ignore"):
+        want_obj, want_grad = mo.objective_gradient(w, shape, transfers, 1, x, y, literal_softmax=True)
+    assert want_obj > 1e300                          # the case really is degenerate
+    model = _model(L, shape, transfers, 1, precision=precision)
+    obj, grad = model._get_obj_jac(w.copy(), x, y)
+    assert rel_err(obj, want_obj) <= TOL
+    assert rel_err(grad, want_grad) <= 1e-9, rel_err(grad, want_grad)
+    lin = _model(L, (48, 64, 6), [(1, 0), (0, 0)], 1, precision=precision)
+    with pytest.raises(FloatingPointError):
+        lin._get_obj_jac(mo.random_params(shape, rng), x, y)
+
+
 def test_full_size_properties_config2(L):
     """BASELINE config 2 at full size (60000 x 784, (784,256,10) softmax/CE): size-independent
     properties -- obj == obj_jac[0], directional derivative vs central differences, row-shard

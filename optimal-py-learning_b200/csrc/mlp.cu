@@ -304,16 +304,20 @@ __global__ void __launch_bounds__(256) narrow_backprop_kernel(const double *__re
 // accumulation, so the result is bit-reproducible; per-CTA dW partials are folded by the split-K reduce kernel.
 // mode (slope of the hidden transfer): 0 none, 1 aux = f' stored by the forward GEMM, 2 aux = tanh activation.
 // ---------------------------------------------------------------------------------------
-struct HeadArgs {
-    const double *A;        // rows x H hidden activations
+// T = storage type of the activation-side matrices: double (parity mode) or float (fast mode: TF32-rounded operands)
+template <typename T>
+struct HeadArgsT {
+    const T *A;             // rows x H hidden activations, row stride ld
     const double *W;        // H x C
     const double *Y;        // rows x C targets
-    const double *aux;      // rows x H (mode 1: f', mode 2: the activation itself) or null
-    double *delta_prev;     // rows x H out (may alias aux), or null (objective only)
+    const T *aux;           // rows x H (mode 1: f', mode 2: the activation itself) or null, row stride ld
+    T *delta_prev;          // rows x H out (may alias aux), or null (objective only), row stride ld
     double *dw_partial;     // gridDim.x x (H*C), or null
     double *loss_partial;   // gridDim.x
     double *colmax;         // H: max |delta_prev[:, j]| (atomicMax on bit patterns) or null
+    double *colsum_partial; // gridDim.x x H: column sums of delta_prev (the bias gradient when delta_prev is delta_0) or null
     int64_t rows;
+    int64_t ld;
     int H, C, R;            // R rows per block step
     int mode;
     int tid;                // output transfer
@@ -322,6 +326,23 @@ struct HeadArgs {
     double ce_div, mse_mul;
     int *flag;
 };
+using HeadArgs = HeadArgsT<double>;
+
+__device__ __forceinline__ double2 head_load2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+__device__ __forceinline__ double2 head_load2(const float *p) {
+    const float2 v = *reinterpret_cast<const float2 *>(p);
+    return make_double2((double)v.x, (double)v.y);
+}
+// stores the pair as the operand type requires and returns what was stored
+__device__ __forceinline__ double2 head_store2(double *p, double a, double b) {
+    *reinterpret_cast<double2 *>(p) = make_double2(a, b);
+    return make_double2(a, b);
+}
+__device__ __forceinline__ double2 head_store2(float *p, double a, double b) {
+    const float2 v = make_float2(round_tf32((float)a), round_tf32((float)b));
+    *reinterpret_cast<float2 *>(p) = v;
+    return make_double2((double)v.x, (double)v.y);
+}
 
 // All three products are DMMA.8x8x4 on shared-memory fragments (classes padded to 16 with zeros):
 //   logits  Z[R x 16]   = As[R x H] . Ws[H x 16]            (row tile, class tile, K half) per warp, halves meet in Zs
@@ -333,29 +354,30 @@ struct HeadArgs {
 // The row stage (softmax / error / delta_L) runs one pattern per half-warp, lane = class.
 // Two shapes: R = 32 patterns per step with 16 warps (one CTA per SM) or R = 16 with 8 warps (two CTAs per SM, whose
 // latency-bound row stages and DMMA phases overlap each other).
-template <int MT, int R, int HEAD_WARPS>    // MT = hidden tiles (8 units) per warp: H <= 8 MT HEAD_WARPS
-__global__ void __launch_bounds__(HEAD_WARPS * 32, R == 16 ? 2 : 1) narrow_head_kernel(const HeadArgs p) {
+template <typename T, int MT, int R, int HEAD_WARPS, bool CSUM>    // MT = hidden tiles (8 units) per warp: H <= 8 MT HEAD_WARPS
+__global__ void __launch_bounds__(HEAD_WARPS * 32, R == 16 ? 2 : 1) narrow_head_kernel(const HeadArgsT<T> p) {
     extern __shared__ double hsm[];
     __shared__ double scratch[33];
     constexpr int RM = R / 8, HEAD_THREADS = HEAD_WARPS * 32;
+    constexpr int EPC = 16 / (int)sizeof(T);   // elements per 16-byte chunk
     const int H = p.H, C = p.C;
-    const int ldA = H + 4;
+    const int ldA = H + (sizeof(T) == 8 ? 4 : 8);   // conflict-free fragment loads for 8-byte / 4-byte elements
     constexpr int ldW = 20, ldD = 20;
     double *Ws = hsm;                          // H x 20
     double *Zs = Ws + (size_t)H * ldW;         // R x 20: logits, then delta_L
-    double *As0 = Zs + R * ldD;                // 2 x R x (H+4)
+    T *As0 = reinterpret_cast<T *>(Zs + R * ldD);   // 2 x R x ldA
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const bool softmax = p.tid == OPL_TRANSFER_SOFTMAX;
     const bool backward = p.delta_prev != nullptr;
-    const int h2 = H >> 1;
+    const int h2 = H / EPC;                    // 16-byte chunks per row (H is a multiple of 8)
     const int64_t nblocks = (p.rows + R - 1) / R;
     auto fetch = [&](int64_t blk, int buf) {   // cp.async the block's activations (rows past the end := 0)
         const int64_t r0 = blk * R;
-        double *dst = As0 + (size_t)buf * R * ldA;
+        T *dst = As0 + (size_t)buf * R * ldA;
         for (int i = threadIdx.x; i < R * h2; i += HEAD_THREADS) {
             const int r = i / h2, c2 = i - r * h2;
             const bool ok = r0 + r < p.rows;
-            cp_async16(dst + (size_t)r * ldA + 2 * c2, p.A + (ok ? (r0 + r) * H + 2 * c2 : 0), ok);
+            cp_async16(dst + (size_t)r * ldA + EPC * c2, p.A + (ok ? (r0 + r) * p.ld + EPC * c2 : 0), ok);
         }
         cp_async_commit();
     };
@@ -370,10 +392,11 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, R == 16 ? 2 : 1) narrow_head_
     ra.mse_mul = p.mse_mul;
     double loss = 0.0;
     bool bad = false, cbad = false;
-    double dw[MT][2][2], cmax[MT][2];
+    double dw[MT][2][2], cmax[MT][2], csum[CSUM ? MT : 1][2];
 #pragma unroll
     for (int i = 0; i < MT; ++i) {
         cmax[i][0] = cmax[i][1] = 0.0;
+        if (CSUM) csum[CSUM ? i : 0][0] = csum[CSUM ? i : 0][1] = 0.0;
 #pragma unroll
         for (int n = 0; n < 2; ++n) dw[i][n][0] = dw[i][n][1] = 0.0;
     }
@@ -381,7 +404,7 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, R == 16 ? 2 : 1) narrow_head_
     for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x, buf ^= 1) {
         const int64_t r0 = blk * R;
         const int nr = (int)min((int64_t)R, p.rows - r0);
-        const double *As = As0 + (size_t)buf * R * ldA;
+        const T *As = As0 + (size_t)buf * R * ldA;
         // slope values of this step's delta_prev tiles: requested now, used after the row stage
         double2 x[MT][RM];
         if (backward && p.mode != 0) {
@@ -391,8 +414,7 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, R == 16 ? 2 : 1) narrow_head_
 #pragma unroll
                 for (int mt = 0; mt < RM; ++mt) {
                     const int row = 8 * mt + g;
-                    x[i][mt] = (col < H && row < nr) ? *reinterpret_cast<const double2 *>(p.aux + (r0 + row) * H + col)
-                                                     : make_double2(1.0, 1.0);
+                    x[i][mt] = (col < H && row < nr) ? head_load2(p.aux + (r0 + row) * p.ld + col) : make_double2(1.0, 1.0);
                 }
             }
         }
@@ -405,14 +427,14 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, R == 16 ? 2 : 1) narrow_head_
             const int mt = warp % RM, nt = (warp / RM) & 1, kh = warp / (2 * RM);
             double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;       // two independent accumulation chains
             const int kq = H >> 3;                                // DMMA steps per half
-            const double *ap = As + (size_t)(8 * mt + g) * ldA + 4 * kh * kq + t;
+            const T *ap = As + (size_t)(8 * mt + g) * ldA + 4 * kh * kq + t;
             const double *bp = Ws + (size_t)(4 * kh * kq + t) * ldW + 8 * nt + g;
             int k = 0;
             for (; k + 1 < kq; k += 2) {
-                dmma_8x8x4(c0, c1, ap[4 * k], bp[4 * k * ldW]);
-                dmma_8x8x4(e0, e1, ap[4 * k + 4], bp[(4 * k + 4) * ldW]);
+                dmma_8x8x4(c0, c1, (double)ap[4 * k], bp[4 * k * ldW]);
+                dmma_8x8x4(e0, e1, (double)ap[4 * k + 4], bp[(4 * k + 4) * ldW]);
             }
-            if (k < kq) dmma_8x8x4(c0, c1, ap[4 * k], bp[4 * k * ldW]);
+            if (k < kq) dmma_8x8x4(c0, c1, (double)ap[4 * k], bp[4 * k * ldW]);
             double *zp = Zs + (8 * mt + g) * ldD + 8 * nt + 2 * t;
             atomicAdd(zp, c0 + e0);             // 0 + a + b == 0 + b + a: the order of the two halves does not matter
             atomicAdd(zp + 1, c1 + e1);
@@ -469,11 +491,15 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, R == 16 ? 2 : 1) narrow_head_
                         o0 *= 1.0 - x[i][mt].x * x[i][mt].x;
                         o1 *= 1.0 - x[i][mt].y * x[i][mt].y;
                     }
-                    *reinterpret_cast<double2 *>(p.delta_prev + (r0 + row) * H + col) = make_double2(o0, o1);
-                    const double a0 = fabs(o0), a1 = fabs(o1);
+                    const double2 st = head_store2(p.delta_prev + (r0 + row) * p.ld + col, o0, o1);
+                    const double a0 = fabs(st.x), a1 = fabs(st.y);
                     cbad |= !(a0 <= 1.7976931348623157e308) || !(a1 <= 1.7976931348623157e308);
                     cmax[i][0] = fmax(cmax[i][0], a0);
                     cmax[i][1] = fmax(cmax[i][1], a1);
+                    if (CSUM) {
+                        csum[CSUM ? i : 0][0] += st.x;
+                        csum[CSUM ? i : 0][1] += st.y;
+                    }
                 }
             }
         }
@@ -482,12 +508,13 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, R == 16 ? 2 : 1) narrow_head_
         for (int i = 0; i < MT; ++i) {
             const int mt = warp + HEAD_WARPS * i;        // hidden tile
             if (8 * mt >= H) break;
-            const double *ap = As + (size_t)t * ldA + 8 * mt + g;
+            const T *ap = As + (size_t)t * ldA + 8 * mt + g;
 #pragma unroll
             for (int n = 0; n < 2; ++n) {
                 const double *bp = Zs + t * ldD + 8 * n + g;
 #pragma unroll
-                for (int k = 0; k < R / 4; ++k) dmma_8x8x4(dw[i][n][0], dw[i][n][1], ap[(size_t)4 * k * ldA], bp[4 * k * ldD]);
+                for (int k = 0; k < R / 4; ++k)
+                    dmma_8x8x4(dw[i][n][0], dw[i][n][1], (double)ap[(size_t)4 * k * ldA], bp[4 * k * ldD]);
             }
         }
         __syncthreads();                       // Zs / this A buffer are free again
@@ -506,6 +533,18 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, R == 16 ? 2 : 1) narrow_head_
                 const int c = 8 * n + 2 * t;
                 if (c < C) dst[c] = dw[i][n][0];
                 if (c + 1 < C) dst[c + 1] = dw[i][n][1];
+            }
+            if (CSUM && p.colsum_partial) {               // fixed-order fold of the 8 row groups, one partial per CTA
+                double s0 = csum[CSUM ? i : 0][0], s1 = csum[CSUM ? i : 0][1];
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                }
+                if (g == 0) {
+                    p.colsum_partial[(size_t)blockIdx.x * H + 8 * mt + 2 * t] = s0;
+                    p.colsum_partial[(size_t)blockIdx.x * H + 8 * mt + 2 * t + 1] = s1;
+                }
             }
             if (p.colmax) {                               // columns 8 mt + 2t, +1: fold the 8 row groups, then one atomic
                 double m0 = cmax[i][0], m1 = cmax[i][1];
@@ -971,7 +1010,9 @@ int backward(opl_mlp *ws, const double *w, const double *x, int64_t rows, double
 }
 
 // Can the fused narrow head replace forward(last layer) + output stage + the head's back-propagation?
-size_t head_smem(int H, int R) { return sizeof(double) * ((size_t)H * 20 + (size_t)R * 20 + 2 * (size_t)R * (H + 4)); }
+size_t head_smem(int H, int R, size_t elem = sizeof(double)) {
+    return sizeof(double) * ((size_t)H * 20 + (size_t)R * 20) + elem * 2 * (size_t)R * (H + (elem == 8 ? 4 : 8));
+}
 int head_rows_per_step(const opl_mlp *ws) {
     const int L = ws->layers;
     if (L < 2 || ws->precision != OPL_PRECISION_F64 || !ws->fused_head) return 0;
@@ -1000,6 +1041,7 @@ int fused_head(opl_mlp *ws, const double *w, const double *y, int64_t rows, bool
     a.W = w + ws->w_off[L - 1];
     a.Y = y;
     a.rows = rows;
+    a.ld = H;
     a.H = H;
     a.C = C;
     a.R = R;
@@ -1020,15 +1062,15 @@ int fused_head(opl_mlp *ws, const double *w, const double *y, int64_t rows, bool
     }
     static bool configured = false;
     if (!configured) {
-        OPL_CUDA(cudaFuncSetAttribute(narrow_head_kernel<2, 32, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_smem(256, 32)));
-        OPL_CUDA(cudaFuncSetAttribute(narrow_head_kernel<4, 16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_smem(256, 16)));
+        OPL_CUDA(cudaFuncSetAttribute(narrow_head_kernel<double, 2, 32, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_smem(256, 32)));
+        OPL_CUDA(cudaFuncSetAttribute(narrow_head_kernel<double, 4, 16, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_smem(256, 16)));
         configured = true;
     }
     mark(ws, STAGE_HEAD * 100 + L - 1);
     if (R == 32)
-        narrow_head_kernel<2, 32, 16><<<grid, 512, smem, ws->stream>>>(a);
+        narrow_head_kernel<double, 2, 32, 16, false><<<grid, 512, smem, ws->stream>>>(a);
     else
-        narrow_head_kernel<4, 16, 8><<<grid, 256, smem, ws->stream>>>(a);
+        narrow_head_kernel<double, 4, 16, 8, false><<<grid, 256, smem, ws->stream>>>(a);
     OPL_LAUNCH_CHECK();
     ++ws->launches;
     mark(ws, STAGE_LOSS * 100);
@@ -1190,14 +1232,14 @@ int opl_mlp_create(opl_mlp **out, int32_t n_widths, const int64_t *widths, const
         partials = std::max<int64_t>(partials, (int64_t)(plan.splits + 1) * (widths[l] * widths[l + 1] + widths[l + 1]));
     }
     partials = std::max<int64_t>(partials, (int64_t)(4 * sm_count() + 8) * widths[1]);
+    if (L >= 2)      // per-CTA dW (+ bias-gradient) partials of the fused narrow head, up to 2 CTAs per SM
+        partials = std::max<int64_t>(partials, 2 * (int64_t)sm_count() * widths[L - 1] * (widths[L] + 1));
     if (precision == OPL_PRECISION_F64) {
         const char *env = getenv("OPL_F64_ENGINE");
         if (env && std::string(env) == "dmma") {
             ws->gemm_engine = OPL_ENGINE_DMMA;
             ws->fused_head = false;
         }
-        if (L >= 2)      // per-CTA dW partials of the fused narrow head
-            partials = std::max<int64_t>(partials, 2 * (int64_t)sm_count() * widths[L - 1] * widths[L]);   // up to 2 CTAs per SM
         int rc = int8_create(ws, &partials);
         if (rc != OPL_OK) {
             free_all(ws);

@@ -182,10 +182,11 @@ int tepi_for(int transfer) {
     }
 }
 
-int fast_forward(opl_mlp *ws, const float *x32, int64_t rows, bool keep_deriv) {
+int fast_forward(opl_mlp *ws, const float *x32, int64_t rows, bool keep_deriv, int layer_end = -1) {
     FastState *f = ws->fast;
     const float *in = x32;
-    for (int l = 0; l < ws->layers; ++l) {
+    if (layer_end < 0) layer_end = ws->layers;
+    for (int l = 0; l < layer_end; ++l) {
         Tf32GemmArgs a = {};
         a.C = f->act[l + 1];
         a.ldc = f->pw[l + 1];
@@ -257,9 +258,10 @@ int fast_output(opl_mlp *ws, const double *y, int64_t rows, bool want_act, bool 
     return OPL_OK;
 }
 
-int fast_backward(opl_mlp *ws, const float *x32, int64_t rows, double *grad) {
+int fast_backward(opl_mlp *ws, const float *x32, int64_t rows, double *grad, int layer_begin = -1, bool have_bias_grad = false) {
     FastState *f = ws->fast;
-    for (int l = ws->layers - 1; l >= 0; --l) {
+    if (layer_begin < 0) layer_begin = ws->layers - 1;
+    for (int l = layer_begin; l >= 0; --l) {
         const int64_t pin = f->pw[l], pout = f->pw[l + 1];
         {   // dW_l = A_l^T delta_l : both operands MN-major, split-K over the patterns
             SplitPlan plan = plan_split_tf32(pin, pout, rows);
@@ -321,7 +323,7 @@ int fast_backward(opl_mlp *ws, const float *x32, int64_t rows, double *grad) {
             ++ws->launches;
         }
     }
-    {   // db = column sums of delta_0
+    if (!have_bias_grad) {   // db = column sums of delta_0
         const int cols = (int)ws->width[1];
         int64_t nblk = std::max<int64_t>(1, std::min<int64_t>(ceil_div(rows, 64), (2 * (int64_t)sm_count()) / ceil_div(cols, 32) + 1));
         if (nblk * cols > ws->partials_len) nblk = std::max<int64_t>(1, ws->partials_len / cols);
@@ -338,10 +340,92 @@ int fast_backward(opl_mlp *ws, const float *x32, int64_t rows, double *grad) {
     return OPL_OK;
 }
 
+// The fused narrow head on FP32 (TF32-rounded) activations: same kernel as the parity mode, FP64 arithmetic inside (the
+// head is streaming, not tensor work), FP32 loads / TF32-rounded stores.  When the head's delta_prev is delta_0 (two-layer
+// networks) its per-CTA column sums are the bias gradient and the separate column-sum pass disappears.
+bool fast_head_ok(const opl_mlp *ws) {
+    const int L = ws->layers;
+    if (L < 2 || !ws->fused_head) return false;
+    const int64_t H = ws->width[L - 1], C = ws->width[L];
+    if (C > 16 || H > 256 || (H & 7) || H < 32) return false;
+    return ws->transfer[L - 2] != OPL_TRANSFER_SOFTMAX;
+}
+
+int fast_fused_head(opl_mlp *ws, bool want_grad, double *grad, double *obj_out) {
+    FastState *f = ws->fast;
+    const int L = ws->layers;
+    const int H = (int)ws->width[L - 1], C = (int)ws->width[L];
+    constexpr int R = 16;
+    const size_t smem = head_smem(H, R, sizeof(float));
+    int grid = (int)std::min<int64_t>(ceil_div(ws->rows, R), 2 * (int64_t)sm_count());
+    grid = std::min(grid, ws->loss_blocks);
+    if (want_grad) grid = (int)std::min<int64_t>(grid, ws->partials_len / ((int64_t)H * (C + 1)));
+    if (grid < 1) return fail(OPL_E_STATE, "fused head (fast mode): scratch too small");
+    HeadArgsT<float> a = {};
+    a.A = f->act[L - 1];
+    a.ld = f->pw[L - 1];
+    a.W = ws->w_trial + ws->w_off[L - 1];
+    a.Y = ws->y;
+    a.rows = ws->rows;
+    a.H = H;
+    a.C = C;
+    a.R = R;
+    a.tid = ws->transfer[L - 1];
+    a.tparam = ws->tparam[L - 1];
+    a.eid = ws->error_id;
+    a.ce_div = -(double)ws->norm_rows;
+    a.mse_mul = 2.0 / ((double)ws->norm_rows * (double)C);
+    a.flag = ws->flag;
+    a.loss_partial = ws->loss_partial;
+    const bool bias_here = want_grad && L == 2;
+    if (want_grad) {
+        const int t = ws->transfer[L - 2];
+        a.mode = (t == OPL_TRANSFER_SOFTPLUS || t == OPL_TRANSFER_GAUSSIAN) ? 1 : (t == OPL_TRANSFER_TANH ? 2 : 0);
+        a.aux = a.mode == 1 ? f->deriv[L - 2] : (a.mode == 2 ? f->act[L - 1] : nullptr);
+        a.delta_prev = f->delta[L - 2];
+        a.dw_partial = ws->partials;
+        a.colsum_partial = bias_here ? ws->partials + (size_t)grid * H * C : nullptr;
+    }
+    static bool configured = false;
+    if (!configured) {
+        OPL_CUDA(cudaFuncSetAttribute(narrow_head_kernel<float, 4, 16, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)head_smem(256, R, sizeof(float))));
+        configured = true;
+    }
+    mark(ws, STAGE_HEAD * 100 + L - 1);
+    narrow_head_kernel<float, 4, 16, 8, true><<<grid, 256, smem, ws->stream>>>(a);
+    OPL_LAUNCH_CHECK();
+    ++ws->launches;
+    mark(ws, STAGE_LOSS * 100);
+    loss_final_kernel<<<1, 256, 0, ws->stream>>>(ws->loss_partial, grid, ws->error_id, (double)ws->norm_rows, (double)C, obj_out);
+    OPL_LAUNCH_CHECK();
+    ++ws->launches;
+    if (want_grad) {
+        mark(ws, STAGE_DW_REDUCE * 100 + L - 1);
+        const int64_t count = (int64_t)H * C;
+        int rc = launch_reduce_partials(ws->partials, grid, count, count, grad + ws->w_off[L - 1], ws->stream, &ws->launches);
+        if (rc != OPL_OK) return rc;
+        if (bias_here) {
+            mark(ws, STAGE_BIAS * 100);
+            rc = launch_reduce_partials(a.colsum_partial, grid, H, H, grad, ws->stream, &ws->launches);
+            if (rc != OPL_OK) return rc;
+        }
+    }
+    return OPL_OK;
+}
+
 int fast_evaluate(opl_mlp *ws, bool want_grad, double *grad_out_dev) {
     FastState *f = ws->fast;
     int rc = fast_convert_w(ws, ws->w_trial);
     if (rc != OPL_OK) return rc;
+    if (fast_head_ok(ws)) {
+        rc = fast_forward(ws, f->x32, ws->rows, want_grad, ws->layers - 1);
+        if (rc != OPL_OK) return rc;
+        rc = fast_fused_head(ws, want_grad, grad_out_dev, grad_out_dev + ws->n);
+        if (rc != OPL_OK) return rc;
+        if (want_grad) rc = fast_backward(ws, f->x32, ws->rows, grad_out_dev, ws->layers - 2, ws->layers == 2);
+        return rc;
+    }
     rc = fast_forward(ws, f->x32, ws->rows, want_grad);
     if (rc != OPL_OK) return rc;
     rc = fast_output(ws, ws->y, ws->rows, false, want_grad, grad_out_dev + ws->n);

@@ -91,63 +91,142 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
 // ------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------
-constexpr int tf32_stages(int bn) { return bn >= 128 ? 3 : TF32_STAGES; }
+constexpr int tf32_stages(int bn) { return bn >= 128 ? 6 : 8; }
 
 template <int BN>
 struct Tf32Smem {
     static constexpr int STAGES = tf32_stages(BN);
     static constexpr int A_BYTES = TF32_BM * 128;
     static constexpr int B_BYTES = BN * 128;
-    static constexpr int BYTES = STAGES * (A_BYTES + B_BYTES) + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    static constexpr int PATCH_BYTES = 8 * 4096;   // per epilogue warp: 32 rows x 32 floats, 16-byte chunks swizzled
+    static constexpr int BYTES = STAGES * (A_BYTES + B_BYTES) + PATCH_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
+constexpr int TF32_THREADS = 320;      // TMA producer, MMA issuer, 8 epilogue warps
 
-__device__ __forceinline__ float epi_apply(const Tf32GemmArgs &p, float z, float aux, float &aux_out_val) {
+// 32 rows x 32 columns held row-per-thread -> the warp's shared patch -> four full 128-byte row segments per store
+// instruction (a row-per-thread float4 store touches 32 different lines per instruction and makes the LSU the bottleneck)
+__device__ __forceinline__ void tf32_store_patch(float *patch, const float (&v)[32], float *base, int64_t ld, int row0, int col0,
+                                                 int M, int lane) {
+    float4 *pw = reinterpret_cast<float4 *>(patch + lane * 32);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) pw[c ^ (lane & 7)] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    __syncwarp();
+    const int chunk = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int prow = (lane >> 3) + 4 * i, grow = row0 + prow;
+        const float4 q = *reinterpret_cast<const float4 *>(patch + prow * 32 + 4 * (chunk ^ (prow & 7)));
+        if (grow < M) *reinterpret_cast<float4 *>(base + (int64_t)grow * ld + col0 + 4 * chunk) = q;
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// four columns at a time with the switch OUTSIDE the element loop, so the four transcendental chains sit in one basic
+// block and interleave (a per-element switch serialises them)
+__device__ __forceinline__ void epi_apply4(const Tf32GemmArgs &p, const float (&z)[4], const float (&aux)[4], float (&r)[4],
+                                           float (&ao)[4]) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) ao[e] = 0.f;
     switch (p.epi) {
-        case TEPI_TANH: return tanhf(z);
+        case TEPI_TANH:
+#pragma unroll
+            for (int e = 0; e < 4; ++e) r[e] = tanhf(z[e]);
+            break;
         case TEPI_SOFTPLUS: {
-            const float e = expf(z);
-            aux_out_val = isinf(e) ? 1.0f : e / (1.0f + e);
-            const float r = log1pf(e);
-            return isinf(r) ? z : r;
+            float ex[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) ex[e] = expf(z[e]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) ao[e] = isinf(ex[e]) ? 1.0f : ex[e] / (1.0f + ex[e]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float l = log1pf(ex[e]);
+                r[e] = isinf(l) ? z[e] : l;
+            }
+            break;
         }
-        case TEPI_GAUSSIAN: {
-            const float a = expf(-(z * z / p.tparam));
-            aux_out_val = -2.0f * z * a / p.tparam;
-            return a;
-        }
-        case TEPI_MUL_AUX: return z * aux;
-        case TEPI_MUL_DTANH: return z * (1.0f - aux * aux);
-        default: return z;
+        case TEPI_GAUSSIAN:
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                r[e] = expf(-(z[e] * z[e] / p.tparam));
+                ao[e] = -2.0f * z[e] * r[e] / p.tparam;
+            }
+            break;
+        case TEPI_MUL_AUX:
+#pragma unroll
+            for (int e = 0; e < 4; ++e) r[e] = z[e] * aux[e];
+            break;
+        case TEPI_MUL_DTANH:
+#pragma unroll
+            for (int e = 0; e < 4; ++e) r[e] = z[e] * (1.0f - aux[e] * aux[e]);
+            break;
+        default:
+#pragma unroll
+            for (int e = 0; e < 4; ++e) r[e] = z[e];
     }
 }
 
+struct Tf32Tile {
+    int m0, n0, k_begin, nkb, split;
+};
+__device__ __forceinline__ Tf32Tile tf32_tile(const Tf32GemmArgs &p, int t, int tiles_m, int tiles_n, int bn) {
+    Tf32Tile r;
+    const int n = t % tiles_n, rest = t / tiles_n;
+    r.split = rest / tiles_m;
+    r.m0 = (rest % tiles_m) * TF32_BM;
+    r.n0 = n * bn;
+    r.k_begin = r.split * p.k_per_split;
+    const int k_end = min(p.K, r.k_begin + p.k_per_split);
+    r.nkb = k_end > r.k_begin ? (k_end - r.k_begin + TF32_BK - 1) / TF32_BK : 0;
+    return r;
+}
+
+// Persistent: one CTA per SM walks tiles (n fastest) with a static schedule; the accumulator is double buffered in
+// TMEM (2 x BN columns), so the 8 epilogue warps drain / transform / store tile t while the MMA warp is already
+// accumulating tile t+1, and the TMA producer runs ahead across tile boundaries through a 6-8 stage ring.
 template <bool A_MN, bool B_MN, int BN>
-__global__ void __launch_bounds__(192, 1)
-gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Tf32GemmArgs p) {
+__global__ void __launch_bounds__(TF32_THREADS, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Tf32GemmArgs p, int splits) {
     using S = Tf32Smem<BN>;
     constexpr int STAGES = S::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     uint8_t *sA = smem;
     uint8_t *sB = smem + STAGES * S::A_BYTES;
-    uint64_t *full = reinterpret_cast<uint64_t *>(sB + STAGES * S::B_BYTES);
+    float *sPatch = reinterpret_cast<float *>(sB + STAGES * S::B_BYTES);
+    uint64_t *full = reinterpret_cast<uint64_t *>(sB + STAGES * S::B_BYTES + S::PATCH_BYTES);
     uint64_t *empty = full + STAGES;
-    uint64_t *tmem_full = empty + STAGES;
-    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_full + 1);
+    uint64_t *acc_full = empty + STAGES;       // [2]
+    uint64_t *acc_empty = acc_full + 2;        // [2]
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * TF32_BM, n0 = blockIdx.x * BN;
-    const int k_begin = blockIdx.z * p.k_per_split;
-    const int k_end = min(p.K, k_begin + p.k_per_split);
-    const int nkb = k_end > k_begin ? (k_end - k_begin + TF32_BK - 1) / TF32_BK : 0;
-    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    const int tiles_m = (p.M + TF32_BM - 1) / TF32_BM, tiles_n = (p.N + BN - 1) / BN;
+    const int ntiles = tiles_m * tiles_n * splits;
+    constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
-        mbar_init(tmem_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&acc_full[s], 1);
+            mbar_init(&acc_empty[s], 8);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) tmem_alloc(tmem_ptr, TMEM_COLS);
@@ -158,93 +237,135 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     if (warp == 0 && lane == 0) {
         // ================= TMA producer =================
-        for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb % STAGES;
-            const uint32_t phase = (kb / STAGES) & 1;
-            mbar_wait(&empty[s], phase ^ 1);
-            mbar_expect_tx(&full[s], S::A_BYTES + S::B_BYTES);
-            const int k0 = k_begin + kb * TF32_BK;
-            uint8_t *a = sA + s * S::A_BYTES, *b = sB + s * S::B_BYTES;
-            if (!A_MN) tma_load_2d(a, &tmA, k0, m0, &full[s]);                       // box {32 k, 128 m}
-            else
-                for (int j = 0; j < TF32_BM / 32; ++j) tma_load_2d(a + j * 4096, &tmA, m0 + 32 * j, k0, &full[s]);   // box {32 m, 32 k}
-            if (!B_MN) tma_load_2d(b, &tmB, k0, n0, &full[s]);                       // box {32 k, BN n}
-            else
-                for (int j = 0; j < BN / 32; ++j) tma_load_2d(b + j * 4096, &tmB, n0 + 32 * j, k0, &full[s]);        // box {32 n, 32 k}
+        uint32_t it = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            const Tf32Tile tl = tf32_tile(p, t, tiles_m, tiles_n, BN);
+            for (int kb = 0; kb < tl.nkb; ++kb, ++it) {
+                const int s = it % STAGES;
+                const uint32_t phase = (it / STAGES) & 1;
+                mbar_wait(&empty[s], phase ^ 1);
+                mbar_expect_tx(&full[s], S::A_BYTES + S::B_BYTES);
+                const int k0 = tl.k_begin + kb * TF32_BK;
+                uint8_t *a = sA + s * S::A_BYTES, *b = sB + s * S::B_BYTES;
+                if (!A_MN) tma_load_2d(a, &tmA, k0, tl.m0, &full[s]);                       // box {32 k, 128 m}
+                else
+                    for (int j = 0; j < TF32_BM / 32; ++j) tma_load_2d(a + j * 4096, &tmA, tl.m0 + 32 * j, k0, &full[s]);   // box {32 m, 32 k}
+                if (!B_MN) tma_load_2d(b, &tmB, k0, tl.n0, &full[s]);                       // box {32 k, BN n}
+                else
+                    for (int j = 0; j < BN / 32; ++j) tma_load_2d(b + j * 4096, &tmB, tl.n0 + 32 * j, k0, &full[s]);        // box {32 n, 32 k}
+            }
         }
     } else if (warp == 1 && lane == 0) {
         // ================= MMA issuer =================
         // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, majors, N>>3, M>>4
         constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                                    ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TF32_BM >> 4) << 24);
-        for (int kb = 0; kb < nkb; ++kb) {
-            const int s = kb % STAGES;
-            const uint32_t phase = (kb / STAGES) & 1;
-            mbar_wait(&full[s], phase);
+        uint32_t it = 0, local = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            const Tf32Tile tl = tf32_tile(p, t, tiles_m, tiles_n, BN);
+            if (tl.nkb == 0) continue;                 // (the epilogue writes zeros without a handshake)
+            const uint32_t buf = local & 1;
+            mbar_wait(&acc_empty[buf], ((local >> 1) & 1) ^ 1);
             tc_fence_after();
-            const uint32_t a = smem_u32(sA + s * S::A_BYTES), b = smem_u32(sB + s * S::B_BYTES);
+            const uint32_t d_tmem = tmem_base + buf * BN;
+            for (int kb = 0; kb < tl.nkb; ++kb, ++it) {
+                const int s = it % STAGES;
+                const uint32_t phase = (it / STAGES) & 1;
+                mbar_wait(&full[s], phase);
+                tc_fence_after();
+                const uint32_t a = smem_u32(sA + s * S::A_BYTES), b = smem_u32(sB + s * S::B_BYTES);
 #pragma unroll
-            for (int k = 0; k < TF32_BK / 8; ++k) {
-                // K-major: 8 tf32 = 32 bytes further along the swizzled 128-byte row; SBO = 8 rows x 128 B
-                // MN-major: 8 k-rows = 1024 bytes further (two 4-row atoms, SBO = 512 B);
-                //           LBO = next 32-wide MN block (one TMA box of 32 k-rows = 4096 B)
-                const uint64_t ad = A_MN ? smem_desc(a + k * 1024, 4096, 512, 1) : smem_desc(a + k * 32, 16, 1024, 2);
-                const uint64_t bd = B_MN ? smem_desc(b + k * 1024, 4096, 512, 1) : smem_desc(b + k * 32, 16, 1024, 2);
-                umma_tf32(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < TF32_BK / 8; ++k) {
+                    // K-major: 8 tf32 = 32 bytes further along the swizzled 128-byte row; SBO = 8 rows x 128 B
+                    // MN-major: 8 k-rows = 1024 bytes further (two 4-row atoms, SBO = 512 B);
+                    //           LBO = next 32-wide MN block (one TMA box of 32 k-rows = 4096 B)
+                    const uint64_t ad = A_MN ? smem_desc(a + k * 1024, 4096, 512, 1) : smem_desc(a + k * 32, 16, 1024, 2);
+                    const uint64_t bd = B_MN ? smem_desc(b + k * 1024, 4096, 512, 1) : smem_desc(b + k * 32, 16, 1024, 2);
+                    umma_tf32(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(&empty[s]);       // smem stage reusable once these MMAs have read it
             }
-            umma_commit(&empty[s]);       // smem stage reusable once these MMAs have read it
+            umma_commit(&acc_full[buf]);
+            ++local;
         }
-        if (nkb > 0) umma_commit(tmem_full);
     } else if (warp >= 2) {
         // ================= epilogue: TMEM -> registers -> global =================
         const int lane_group = warp & 3;                 // tcgen05.ld: warp w may touch lanes 32*(w%4)..+31
-        const int row = m0 + lane_group * 32 + lane;
-        if (nkb > 0) {
-            mbar_wait(tmem_full, 0);
-            tc_fence_after();
-        }
-        float *C = p.C + (int64_t)blockIdx.z * p.split_stride;
+        const int half = (warp - 2) >> 2;                // columns [half * BN/2, (half+1) * BN/2) of the tile
+        constexpr int CH = BN / 2;                       // columns per thread
+        constexpr int CW = CH >= 32 ? 32 : 16;           // columns per TMEM load
+        uint32_t local = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            const Tf32Tile tl = tf32_tile(p, t, tiles_m, tiles_n, BN);
+            const int row = tl.m0 + lane_group * 32 + lane;
+            const uint32_t buf = local & 1;
+            if (tl.nkb > 0) {
+                mbar_wait(&acc_full[buf], (local >> 1) & 1);
+                tc_fence_after();
+            }
+            float *C = p.C + (int64_t)tl.split * p.split_stride;
+            const bool need_aux_in = p.epi == TEPI_MUL_AUX || p.epi == TEPI_MUL_DTANH;
+            const bool have_aux_out = p.aux_out != nullptr && (p.epi == TEPI_SOFTPLUS || p.epi == TEPI_GAUSSIAN);
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t v[32];
-            if (nkb > 0) tmem_ld32(tmem_base + ((uint32_t)(lane_group * 32) << 16) + (uint32_t)c0, v);
-            else
+            for (int c0 = half * CH; c0 < half * CH + CH; c0 += CW) {
+                uint32_t v[CW];
+                if (tl.nkb > 0) {
+                    const uint32_t taddr = tmem_base + ((uint32_t)(lane_group * 32) << 16) + (uint32_t)(buf * BN + c0);
+                    if constexpr (CW == 32) tmem_ld32(taddr, v);
+                    else tmem_ld16(taddr, v);
+                } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = 0u;
-            const int col0 = n0 + c0;
-            if (row < p.M && col0 < p.N) {
-                float out[32], aux_o[32];
-                const bool need_aux_in = p.epi == TEPI_MUL_AUX || p.epi == TEPI_MUL_DTANH;
-                const bool have_aux_out = p.aux_out != nullptr && (p.epi == TEPI_SOFTPLUS || p.epi == TEPI_GAUSSIAN);
+                    for (int j = 0; j < CW; ++j) v[j] = 0u;
+                }
+                if (c0 + CW >= half * CH + CH && tl.nkb > 0) {     // last read of this buffer by this warp: release it
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                }
+                const int col0 = tl.n0 + c0;
+                if (CW == 32 ? col0 < p.N : (row < p.M && col0 < p.N)) {     // (the patch path needs the whole warp)
+                    float out[CW], aux_o[CW];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    float4 ax = make_float4(0.f, 0.f, 0.f, 0.f), bs = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (need_aux_in) ax = *reinterpret_cast<const float4 *>(p.aux_in + (int64_t)row * p.ldaux + col0 + 4 * q);
-                    if (p.bias) bs = *reinterpret_cast<const float4 *>(p.bias + col0 + 4 * q);
-                    const float axv[4] = {ax.x, ax.y, ax.z, ax.w}, bsv[4] = {bs.x, bs.y, bs.z, bs.w};
+                    for (int q = 0; q < CW / 4; ++q) {
+                        float4 ax = make_float4(0.f, 0.f, 0.f, 0.f), bs = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (need_aux_in && row < p.M) ax = *reinterpret_cast<const float4 *>(p.aux_in + (int64_t)row * p.ldaux + col0 + 4 * q);
+                        if (p.bias) bs = *reinterpret_cast<const float4 *>(p.bias + col0 + 4 * q);
+                        const float axv[4] = {ax.x, ax.y, ax.z, ax.w}, bsv[4] = {bs.x, bs.y, bs.z, bs.w};
+                        float zq[4], rq[4], aq[4];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int j = 4 * q + e;
-                        float ao = 0.f;
-                        float r = epi_apply(p, __uint_as_float(v[j]) + bsv[e], axv[e], ao);
-                        if (p.round_out) r = round_tf32(r);
-                        if (col0 + j >= p.n_valid) {      // layer padding stays exactly zero
-                            r = 0.f;
-                            ao = 0.f;
+                        for (int e = 0; e < 4; ++e) zq[e] = __uint_as_float(v[4 * q + e]) + bsv[e];
+                        epi_apply4(p, zq, axv, rq, aq);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int j = 4 * q + e;
+                            float r = p.round_out ? round_tf32(rq[e]) : rq[e];
+                            float ao = aq[e];
+                            if (col0 + j >= p.n_valid) {      // layer padding stays exactly zero
+                                r = 0.f;
+                                ao = 0.f;
+                            }
+                            out[j] = r;
+                            aux_o[j] = ao;
                         }
-                        out[j] = r;
-                        aux_o[j] = ao;
+                    }
+                    if constexpr (CW == 32) {
+                        float *patch = sPatch + (warp - 2) * 1024;
+                        const int row0 = tl.m0 + lane_group * 32;
+                        tf32_store_patch(patch, out, C, p.ldc, row0, col0, p.M, lane);
+                        if (have_aux_out) tf32_store_patch(patch, aux_o, p.aux_out, p.ldaux, row0, col0, p.M, lane);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < CW / 4; ++q) {
+                            *reinterpret_cast<float4 *>(C + (int64_t)row * p.ldc + col0 + 4 * q) =
+                                make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
+                            if (have_aux_out)
+                                *reinterpret_cast<float4 *>(p.aux_out + (int64_t)row * p.ldaux + col0 + 4 * q) =
+                                    make_float4(aux_o[4 * q], aux_o[4 * q + 1], aux_o[4 * q + 2], aux_o[4 * q + 3]);
+                        }
                     }
                 }
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    *reinterpret_cast<float4 *>(C + (int64_t)row * p.ldc + col0 + 4 * q) =
-                        make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
-                    if (have_aux_out)
-                        *reinterpret_cast<float4 *>(p.aux_out + (int64_t)row * p.ldaux + col0 + 4 * q) =
-                            make_float4(aux_o[4 * q], aux_o[4 * q + 1], aux_o[4 * q + 2], aux_o[4 * q + 3]);
-                }
             }
+            if (tl.nkb > 0) ++local;
         }
         tc_fence_before();
     }
@@ -299,8 +420,9 @@ int launch_tf32(const CUtensorMap &ta, const CUtensorMap &tb, const Tf32GemmArgs
         OPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Tf32Smem<BN>::BYTES));
         configured = true;
     }
-    dim3 grid((unsigned)ceil_div(a.N, BN), (unsigned)ceil_div(a.M, TF32_BM), (unsigned)splits);
-    kern<<<grid, 192, Tf32Smem<BN>::BYTES, stream>>>(ta, tb, a);
+    const int64_t tiles = ceil_div(a.N, BN) * ceil_div(a.M, TF32_BM) * splits;
+    const unsigned grid = (unsigned)std::min<int64_t>(tiles, sm_count());
+    kern<<<grid, TF32_THREADS, Tf32Smem<BN>::BYTES, stream>>>(ta, tb, a, splits);
     OPL_LAUNCH_CHECK();
     return OPL_OK;
 }

@@ -448,6 +448,36 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, R == 16 ? 2 : 1) narrow_head_
             const bool live = r < nr && cl < C;
             const double z = Zs[r * ldD + cl];
             double a_out;
+            if (sizeof(T) == 4 && softmax && p.eid == OPL_ERROR_CROSS_ENTROPY) {
+                // fast mode, classification head: the row stage in FP32 (a dependent FP64 operation costs ~36 cycles here,
+                // an FP32 one 4); same formulas, FLT_MAX where the FP64 path has DBL_MAX
+                const float zf = (float)z;
+                float mx = live ? zf : -INFINITY;
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                const float e = live ? expf(zf - mx) : 0.f;
+                float den = e;
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) den += __shfl_xor_sync(0xffffffffu, den, o);
+                const float a = e / den;
+                float gq = 0.f;
+                if (live) {
+                    const float y = (float)p.Y[(r0 + r) * C + cl];
+                    float lg = logf(a);
+                    lg = isnan(lg) ? 0.f : (isinf(lg) ? (lg > 0 ? 3.4028234664e38f : -3.4028234664e38f) : lg);
+                    loss += (double)(lg * y);
+                    float q = y / a;
+                    q = isnan(q) ? 0.f : (isinf(q) ? (q > 0 ? 3.4028234664e38f : -3.4028234664e38f) : q);
+                    gq = q / (float)p.ce_div;
+                }
+                float tt = live ? gq * a : 0.f;
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) tt += __shfl_xor_sync(0xffffffffu, tt, o);
+                if (backward) Zs[r * ldD + cl] = live ? (double)(a * (gq - tt)) : 0.0;
+                __syncthreads();
+                if (!backward) continue;
+                goto head_backward;
+            }
             if (softmax) {   // calculate.py:152-153
                 const double mx = group_max(live ? z : -INFINITY, 16);
                 const double e = live ? exp(z - mx) : 0.0;
@@ -468,6 +498,7 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, R == 16 ? 2 : 1) narrow_head_
         }
         __syncthreads();
         if (!backward) continue;
+    head_backward:
         // ---- delta_prev = (delta_L W^T) o slope ----
 #pragma unroll
         for (int i = 0; i < MT; ++i) {

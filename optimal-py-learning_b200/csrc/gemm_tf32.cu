@@ -91,7 +91,7 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
 // ------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------
-constexpr int tf32_stages(int bn) { return bn >= 128 ? 6 : 8; }
+constexpr int tf32_stages(int bn) { return bn >= 128 ? 4 : 8; }
 
 template <int BN>
 struct Tf32Smem {
@@ -184,9 +184,22 @@ struct Tf32Tile {
 };
 __device__ __forceinline__ Tf32Tile tf32_tile(const Tf32GemmArgs &p, int t, int tiles_m, int tiles_n, int bn) {
     Tf32Tile r;
-    const int n = t % tiles_n, rest = t / tiles_n;
-    r.split = rest / tiles_m;
-    r.m0 = (rest % tiles_m) * TF32_BM;
+    const int per_split = tiles_m * tiles_n;
+    r.split = t / per_split;
+    const int u = t - r.split * per_split;
+    int m, n;
+    if (tiles_n >= 8 && tiles_m >= 8) {
+        // grouped raster for square-ish problems: the CTAs running at the same time cover 8 rows of tiles x ~18 columns
+        // instead of ~2 rows x all columns, so the operand set a wave touches fits the L2
+        const int group = u / (8 * tiles_n), within = u - group * 8 * tiles_n;
+        const int gm = min(8, tiles_m - group * 8);
+        m = group * 8 + within % gm;
+        n = within / gm;
+    } else {
+        n = u % tiles_n;
+        m = u / tiles_n;
+    }
+    r.m0 = m * TF32_BM;
     r.n0 = n * bn;
     r.k_begin = r.split * p.k_per_split;
     const int k_end = min(p.K, r.k_begin + p.k_per_split);

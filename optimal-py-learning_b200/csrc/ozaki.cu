@@ -276,9 +276,23 @@ struct OzTile {
 };
 __device__ __forceinline__ OzTile oz_tile(const OzakiArgs &p, int t, int tiles_m, int tiles_n) {
     OzTile r;
-    const int n = t % tiles_n, rest = t / tiles_n;
-    const int m = rest % tiles_m;
-    r.split = rest / tiles_m;
+    const int per_split = tiles_m * tiles_n;
+    r.split = t / per_split;
+    const int u = t - r.split * per_split;
+    int m, n;
+    if (tiles_n >= 16 && (tiles_n & 1) == 0 && tiles_m >= 8) {
+        // grouped raster for square-ish problems (keeps the operand set of one wave inside the L2).  Groups of 8 tile rows;
+        // inside a group the tile columns advance in PAIRS so that a 2-CTA cluster still holds neighbouring columns of
+        // one row (tiles_n is even whenever clusters are used).
+        const int group = u / (8 * tiles_n), within = u - group * 8 * tiles_n;
+        const int gm = min(8, tiles_m - group * 8);
+        const int pair = within / (2 * gm), rem = within - pair * 2 * gm;
+        m = group * 8 + rem / 2;
+        n = 2 * pair + (rem & 1);
+    } else {
+        n = u % tiles_n;
+        m = u / tiles_n;
+    }
     r.m0 = m * OZ_BM;
     r.n0 = n * OZ_BN;
     r.k_begin = r.split * p.k_per_split;

@@ -1,10 +1,11 @@
 #!/usr/bin/env python
 """Run every BASELINE.json config for a few optimizer steps through the public plugin API (Model.train_step with the
 reference's default optimizers) on one GPU and print one JSON line per config: wall time per step, objective+gradient
-evaluations per step, evaluations per second, objective trajectory.  Config 4 (H row-sharded over 8 GPUs) runs its
-single-GPU-sized sibling here (the same code path with one shard); its multi-rank form is tests/dist_gpu_check.py.
+evaluations per step, evaluations per second, objective trajectory.  Config 4 (H row-sharded over 8 GPUs) runs when the
+script is launched by torchrun with one rank per GPU.
 
     python tools/run_configs.py [1 2 3 5 ...]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 tools/run_configs.py     # config 4
 """
 import json
 import os
@@ -55,7 +56,43 @@ def run(name, model, x, y, steps):
     print(json.dumps(out), flush=True)
 
 
+def run_config4():
+    """Config 4 under torchrun (one rank per GPU): (1024,256,256,32), BFGS with n = 336128 weights, H (904 GB FP64)
+    row-sharded over the ranks, 65536 patterns sharded by rows with an NCCL all-reduce of [gradient ; objective]."""
+    import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    world, rank = dist.get_world_size(), dist.get_rank()
+    rows = 65536 // world
+    x, y = synthetic(rows, 1024, 32, 100 + rank)
+    numpy.random.seed(0)
+    m = L.MLP((1024, 256, 256, 32), transfers=L.SoftmaxTransfer(), error_func=L.CrossEntropyError(),
+              optimizer=L.optimize.BFGS(shard_rows=True))
+    m.logging = False
+    objs, times = [], []
+    for _ in range(6):
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        objs.append(float(m.train_step(x, y)))
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+    free, total = torch.cuda.mem_get_info()
+    if rank == 0:
+        n = 256 + 1024 * 256 + 256 * 256 + 256 * 32
+        print(json.dumps({"config": "4: (1024,256,256,32) 65536 patterns over %d GPUs, BFGS n=%d, H row-sharded (%.1f GB per GPU)"
+                                    % (world, n, n * n * 8 / world / 2 ** 30),
+                          "objective": [round(o, 6) for o in objs], "s_per_step": [round(t, 4) for t in times],
+                          "obj_grad_evaluations": m.obj_jac_evaluations,
+                          "gpu_mem_used_gb_rank0": round((total - free) / 2 ** 30, 1)}), flush=True)
+        assert all(numpy.isfinite(objs)) and objs[-1] < objs[0], objs
+    dist.destroy_process_group()
+
+
 def main():
+    if "WORLD_SIZE" in os.environ and int(os.environ["WORLD_SIZE"]) > 1:
+        return run_config4()
     which = [int(a) for a in sys.argv[1:]] or [1, 2, 3, 5]
     opt = L.optimize
     if 1 in which:   # README iris-sized MLP (4,2,3), BFGS + Wolfe (runs on the CPU in the reference)

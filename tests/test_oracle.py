@@ -139,3 +139,39 @@ def test_rank2_bfgs_iterates_track_literal():
         _, xa = a.step(f, fo, xa)
         _, xb = b.step(f, fo, xb)
         assert rel_err(xb, xa) <= 1e-9
+
+
+# ----------------------------------------------------------------------------------------
+# the digit arithmetic of the parity mode's INT8 engine (oracle/ozaki_oracle.py restates csrc/ozaki.cu)
+# ----------------------------------------------------------------------------------------
+def test_radix256_digits_are_an_error_free_transformation():
+    import ozaki_oracle as oz
+    rng = numpy.random.default_rng(0)
+    x = rng.standard_normal((7, 300)) * numpy.exp(rng.standard_normal((7, 1)) * 8)
+    x[0, :5] = [0.0, 1.0, -1.0, 2.0 ** -40, -(2.0 ** 20)]
+    x[3] = 0.0
+    scale = oz.scale_of(numpy.abs(x).max(axis=1, keepdims=True))
+    assert (numpy.log2(scale) % 1 == 0).all() and (numpy.abs(x) <= 0.495 * scale + 1e-300).all()
+    d = oz.digits(x, scale)
+    assert d.min() >= -128 and d.max() <= 127
+    # the digits reproduce x to 2^-49 of the row scale, exactly the rounding of x / scale * 2^48 to an integer
+    assert (numpy.abs(oz.reconstruct(d, scale) - x) <= 2.0 ** -49 * scale * (1 + 1e-12)).all()
+    assert (d[:, 3] == 0).all()                                   # a zero row has zero digits (scale 1)
+
+
+def test_digit_gemm_matches_float64_and_stays_inside_int32():
+    import ozaki_oracle as oz
+    rng = numpy.random.default_rng(1)
+    for (m, n, k, heavy) in [(33, 17, 200, False), (20, 9, 1500, True), (5, 4, 3, False)]:
+        a = rng.random((m, k)) * 2 - 1
+        b = (rng.random((k, n)) * 2 - 1) * 0.25
+        if heavy:
+            b *= numpy.exp(rng.standard_normal((k, 1)) * 3) * 1e-7
+            a[:, ::7] = 0.0
+        c, acc = oz.gemm(a, b)
+        ref = a @ b
+        bound = numpy.abs(a) @ numpy.abs(b)
+        assert (numpy.abs(c - ref) <= 1e-12 * bound + 1e-300).all()
+        assert numpy.abs(acc).max() < 2 ** 31                     # what one INT32 TMEM accumulator has to hold
+    # worst case for the accumulators: every digit at -128, the longest contraction a tile is allowed
+    assert oz.S * oz.MAX_K * 128 * 128 < 2 ** 31

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Prototype: FP64-accurate GEMM on the INT8 tensor cores (Ozaki scheme), torch only.
+"""First prototype (kept for the record; the kernel in csrc/ozaki.cu uses 6 radix-256 digits, see oracle/ozaki_oracle.py):
+FP64-accurate GEMM on the INT8 tensor cores (Ozaki scheme), torch only.
 
 C = A @ B with A [M,K] sliced per ROW and B [K,N] sliced per COLUMN into S signed 7-bit slices
 (error-free: each slice is an exact truncation of the scaled remainder); the S(S+1)/2 slice products

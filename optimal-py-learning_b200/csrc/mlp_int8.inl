@@ -95,14 +95,14 @@ int int8_create(opl_mlp *ws, int64_t *partials_needed) {
     for (int l = 0; l < L; ++l) {
         const int64_t din = ws->width[l], dout = ws->width[l + 1];
         if (!int8_shape_ok(din, dout, l) || ws->max_rows < INT8_MIN_ROWS) continue;
-        s->fwd[l] = l < L - 1;
-        s->dw[l] = 1;
+        s->fwd[l] = l < L - 1 && ozaki_pad(din) <= OZ_MAX_K;     // one tile contracts at most OZ_MAX_K (INT32 exactness);
+        s->dw[l] = 1;                                              // wider layers stay on the DMMA kernels
         any = true;
         w_bytes = std::max<int64_t>(w_bytes, (int64_t)OZ_S * ozaki_pad(dout) * ozaki_pad(din));
         scale_len = std::max<int64_t>(scale_len, std::max(ozaki_pad(dout), ozaki_pad(din + 1)));
         d_cols = std::max<int64_t>(d_cols, ozaki_pad(dout));
         if (l >= 1) {
-            s->da[l] = 1;
+            s->da[l] = ozaki_pad(dout) <= OZ_MAX_K;
             a_cols = std::max<int64_t>(a_cols, std::max(ozaki_pad(din), ozaki_pad(dout)));   // A_l rows (forward), delta_l rows (dA)
             at_rows = std::max<int64_t>(at_rows, ozaki_pad(din));
         }

@@ -142,20 +142,52 @@ int opl_vec_scale_device(int64_t n, double a, const double *x, double *out, void
     return OPL_OK;
 }
 
+}  // extern "C"
+
+namespace {
+// Per-device reduction scratch and page-locked scalar for the synchronous vector calls: the calls block until their
+// scalar is on the host, so one buffer per device is enough.  (A cudaMallocAsync / cudaFreeAsync pair plus a download into
+// a pageable stack variable made one dot product cost 0.4 ms -- as much as half an objective evaluation.)
+struct VecScratch {
+    double *dev = nullptr;
+    double *host = nullptr;
+    int blocks = 0;
+};
+int vec_scratch(int blocks, VecScratch **out) {
+    static VecScratch table[64];
+    int device = 0;
+    OPL_CUDA(cudaGetDevice(&device));
+    if (device < 0 || device >= 64) return fail(OPL_E_CUDA, "device index %d out of range", device);
+    VecScratch &v = table[device];
+    if (v.blocks < blocks) {
+        cudaFree(v.dev);
+        v.dev = nullptr;
+        v.blocks = 0;
+        OPL_CUDA(cudaMalloc(&v.dev, sizeof(double) * (size_t)(blocks + 1)));
+        v.blocks = blocks;
+    }
+    if (!v.host) OPL_CUDA(cudaMallocHost(&v.host, sizeof(double) * 2));
+    *out = &v;
+    return OPL_OK;
+}
+}  // namespace
+
+extern "C" {
+
 int opl_vec_penalty_device(int64_t n, const double *w, int32_t kind, double lambda, double *grad_inout,
                            double *host_out, void *cuda_stream) {
     if (n < 1 || !w || !host_out || (kind != 1 && kind != 2)) return fail(OPL_E_ARG, "opl_vec_penalty_device: bad arguments");
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const int blocks = vec_grid(n, 256);
-    double *scratch = nullptr;
-    OPL_CUDA(cudaMallocAsync(&scratch, sizeof(double) * (blocks + 1), st));
-    penalty_partial_kernel<<<blocks, 256, 0, st>>>(n, w, kind, scratch);
-    penalty_apply_kernel<<<blocks, 256, 0, st>>>(n, w, kind, lambda, blocks, scratch, grad_inout, scratch + blocks);
-    cudaError_t e = cudaMemcpyAsync(host_out, scratch + blocks, sizeof(double), cudaMemcpyDeviceToHost, st);
-    cudaFreeAsync(scratch, st);
-    if (e != cudaSuccess) return fail(OPL_E_CUDA, "penalty readback: %s", cudaGetErrorString(e));
+    VecScratch *v = nullptr;
+    int rc = vec_scratch(blocks, &v);
+    if (rc != OPL_OK) return rc;
+    penalty_partial_kernel<<<blocks, 256, 0, st>>>(n, w, kind, v->dev);
+    penalty_apply_kernel<<<blocks, 256, 0, st>>>(n, w, kind, lambda, blocks, v->dev, grad_inout, v->dev + blocks);
+    OPL_CUDA(cudaMemcpyAsync(v->host, v->dev + blocks, sizeof(double), cudaMemcpyDeviceToHost, st));
     OPL_CUDA(cudaStreamSynchronize(st));
     OPL_LAUNCH_CHECK();
+    *host_out = v->host[0];
     return OPL_OK;
 }
 
@@ -163,15 +195,15 @@ int opl_vec_dot_device(int64_t n, const double *x, const double *y, double *host
     if (n < 0 || !host_out || (n > 0 && (!x || !y))) return fail(OPL_E_ARG, "opl_vec_dot_device: null pointer");
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const int blocks = n > 0 ? vec_grid(n, 256) : 1;
-    double *scratch = nullptr;
-    OPL_CUDA(cudaMallocAsync(&scratch, sizeof(double) * (blocks + 1), st));
-    dot_partial_kernel<<<blocks, 256, 0, st>>>(n, x, y, scratch);
-    dot_final_kernel<<<1, 256, 0, st>>>(blocks, scratch, scratch + blocks);
-    cudaError_t e = cudaMemcpyAsync(host_out, scratch + blocks, sizeof(double), cudaMemcpyDeviceToHost, st);
-    cudaFreeAsync(scratch, st);
-    if (e != cudaSuccess) return fail(OPL_E_CUDA, "dot readback: %s", cudaGetErrorString(e));
+    VecScratch *v = nullptr;
+    int rc = vec_scratch(blocks, &v);
+    if (rc != OPL_OK) return rc;
+    dot_partial_kernel<<<blocks, 256, 0, st>>>(n, x, y, v->dev);
+    dot_final_kernel<<<1, 256, 0, st>>>(blocks, v->dev, v->dev + blocks);
+    OPL_CUDA(cudaMemcpyAsync(v->host, v->dev + blocks, sizeof(double), cudaMemcpyDeviceToHost, st));
     OPL_CUDA(cudaStreamSynchronize(st));
     OPL_LAUNCH_CHECK();
+    *host_out = v->host[0];
     return OPL_OK;
 }
 

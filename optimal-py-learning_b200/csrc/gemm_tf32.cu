@@ -444,6 +444,7 @@ template <bool A_MN, bool B_MN>
 int launch_bn(int bn, const CUtensorMap &ta, const CUtensorMap &tb, const Tf32GemmArgs &a, int splits, cudaStream_t stream) {
     if (bn == 32) return launch_tf32<A_MN, B_MN, 32>(ta, tb, a, splits, stream);
     if (bn == 64) return launch_tf32<A_MN, B_MN, 64>(ta, tb, a, splits, stream);
+    if (bn == 256) return launch_tf32<A_MN, B_MN, 256>(ta, tb, a, splits, stream);
     return launch_tf32<A_MN, B_MN, 128>(ta, tb, a, splits, stream);
 }
 
@@ -455,7 +456,8 @@ int launch_gemm_tf32(int layout, const float *A, int64_t lda, const float *B, in
     // K may be ragged only for the TN layout (K = patterns): TMA zero-fills rows beyond the tensor
     if ((layout != 2 && args.K % TF32_BK) || args.k_per_split % TF32_BK || args.N % 32 || args.ldc % 4)
         return fail(OPL_E_ARG, "tf32 GEMM needs N %% 32 == 0 and K %% 32 == 0 (padded layer widths)");
-    const int bn = args.N >= 128 ? 128 : (args.N >= 64 ? 64 : 32);
+    // 128 x 256 tiles (the whole 512-column TMEM as two accumulators) for wide outputs: 25 % less operand traffic per flop
+    const int bn = (args.N >= 512 && args.N % 256 == 0) ? 256 : (args.N >= 128 ? 128 : (args.N >= 64 ? 64 : 32));
     const bool a_mn = layout == 2, b_mn = layout != 1;
     CUtensorMap ta, tb;
     int rc;

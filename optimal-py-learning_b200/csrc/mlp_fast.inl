@@ -93,7 +93,7 @@ void fast_free(FastState *f) {
 }
 
 SplitPlan plan_split_tf32(int64_t M, int64_t N, int64_t K) {
-    const int64_t bn = N >= 128 ? 128 : (N >= 64 ? 64 : 32);
+    const int64_t bn = (N >= 512 && N % 256 == 0) ? 256 : (N >= 128 ? 128 : (N >= 64 ? 64 : 32));
     const int64_t tiles = ceil_div(M, TF32_BM) * ceil_div(N, bn);
     int64_t want = (2 * (int64_t)sm_count()) / std::max<int64_t>(tiles, 1);
     want = std::max<int64_t>(1, std::min<int64_t>(want, K / 1024));

@@ -1,0 +1,142 @@
+// Table-driven FP64 softplus + logistic for the forward GEMM epilogue (reference: ReluTransfer = softplus,
+// learning/calculate.py:128-141: log(1.0 + exp(z)) with overflowing entries replaced by z; derivative
+// 1 / (1 + exp(-z)) from the INPUT).
+//
+// Why it is written out: on B200 the FP64 work of the epilogue does not hide under the tensor pipe, so its
+// cost is its FP64 instruction count.  Library exp + log + division are ~200 FP64 instructions per element, the
+// polynomial-only version this replaces was ~60; this one is ~26:
+//   t  = exp(-|z|)         n = rint(-|z| 64/ln2), r = -|z| - n ln2/64 (two-part constant), 2^(n/64) from a 64-entry table,
+//                          exp(r) - 1 by a degree-5 Taylor polynomial (|r| <= ln2/128: remainder 3.5e-17)      10 FP64
+//   u  = 1 + t             in [1, 2]  (rounded exactly like the reference's 1.0 + exp(z) for z <= 0)           1
+//   1/u                    MUFU seed (2^-20) + one cubic Newton step                                           3
+//   log u                  i = top 8 mantissa bits of u, w = u rc_i - 1 (one FMA, |w| <= 2^-8), degree-7 Taylor of log1p(w),
+//                          + L_i = -log(rc_i)                                                                  9
+//   softplus = max(z,0) + log u,  logistic = z >= 0 ? 1/u : t/u                                                2
+// Selections and special cases (|z| >= 708, NaN) are integer operations on the high words, not FP64 compares.
+// Errors ~1 ulp (tests/test_host_logic.py compiles this header for the host and checks it against mpmath).
+//
+// The header compiles for the device (nvcc) and for the host (g++, used only by that test).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define OZT_FN __device__ __forceinline__
+#define OZT_TABLE_QUAL __device__ const __align__(16)
+#else
+#include <math.h>
+#include <string.h>
+#define OZT_FN static inline
+#define OZT_TABLE_QUAL static const __attribute__((aligned(16)))
+#endif
+
+#include "oz_tables.inc"
+
+namespace opl {
+
+#if defined(__CUDACC__)
+OZT_FN int ozt_hi(double x) { return __double2hiint(x); }
+OZT_FN int ozt_lo(double x) { return __double2loint(x); }
+OZT_FN double ozt_make(int hi, int lo) { return __hiloint2double(hi, lo); }
+OZT_FN double ozt_fma(double a, double b, double c) { return fma(a, b, c); }
+OZT_FN double ozt_rcp_seed(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+}
+OZT_FN double ozt_exp_tab(int j) { return __longlong_as_double((long long)__ldg(&OZT_EXP_BITS[j])); }
+OZT_FN void ozt_log_tab(int i, double &rc, double &L) {
+    const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(&OZT_LOG_BITS[i][0]));
+    rc = __longlong_as_double((long long)v.x);
+    L = __longlong_as_double((long long)v.y);
+}
+#else
+OZT_FN int ozt_hi(double x) { uint64_t b; memcpy(&b, &x, 8); return (int)(uint32_t)(b >> 32); }
+OZT_FN int ozt_lo(double x) { uint64_t b; memcpy(&b, &x, 8); return (int)(uint32_t)b; }
+OZT_FN double ozt_make(int hi, int lo) {
+    const uint64_t b = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
+    double x;
+    memcpy(&x, &b, 8);
+    return x;
+}
+OZT_FN double ozt_fma(double a, double b, double c) { return fma(a, b, c); }
+// host model of MUFU.RCP64H: the low 32 bits of the operand are ignored, the result carries ~20 good bits
+OZT_FN double ozt_rcp_seed(double x) { return ozt_make(ozt_hi(1.0 / ozt_make(ozt_hi(x), 0)), 0); }
+OZT_FN double ozt_exp_tab(int j) { double x; memcpy(&x, &OZT_EXP_BITS[j], 8); return x; }
+OZT_FN void ozt_log_tab(int i, double &rc, double &L) { memcpy(&rc, &OZT_LOG_BITS[i][0], 8); memcpy(&L, &OZT_LOG_BITS[i][1], 8); }
+#endif
+
+// W elements advance in lockstep through every step, so W independent FP64 chains are adjacent in program order
+// (a dependent DFMA has ~36 cycles of latency on this part).
+template <int W>
+OZT_FN void ozt_softplus_logistic_n(const double (&z)[W], double (&sp)[W], double (&sg)[W]) {
+    double a[W], t[W], r[W], s[W], u[W], y[W];
+    // ---- t = exp(-|z|) ----
+#pragma unroll
+    for (int i = 0; i < W; ++i) a[i] = -fabs(z[i]);
+#pragma unroll
+    for (int i = 0; i < W; ++i) t[i] = ozt_fma(a[i], 92.332482616893656877, 6755399441055744.0);   // 64/ln2; low word = n
+#pragma unroll
+    for (int i = 0; i < W; ++i) r[i] = t[i] - 6755399441055744.0;
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        const double nd = r[i];
+        r[i] = ozt_fma(nd, -6.93147180369123816490e-01 / 64.0, a[i]);     // ln2_hi / 64: 21 trailing zero bits, n ln2_hi/64 exact
+        r[i] = ozt_fma(nd, -1.90821492927058770002e-10 / 64.0, r[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        const double x = r[i], x2 = x * x;
+        double p = ozt_fma(x, 8.3333333333333332e-03, 4.1666666666666664e-02);    // 1/5! x + 1/4!
+        p = ozt_fma(p, x, 1.6666666666666666e-01);
+        p = ozt_fma(p, x, 0.5);
+        s[i] = ozt_fma(x2, p, x);                                                 // exp(r) - 1
+    }
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        const int n = ozt_lo(t[i]);
+        const double T = ozt_exp_tab(n & 63);
+        const double q = ozt_fma(T, s[i], T);                                     // 2^(j/64) exp(r) in [0.5, 1]
+        const double scaled = ozt_make(ozt_hi(q) + ((n >> 6) << 20), ozt_lo(q));   // * 2^(n >> 6), no underflow above -708
+        const bool tiny = (uint32_t)(ozt_hi(z[i]) & 0x7fffffff) >= 0x40862000u;   // |z| >= 708 (inf, NaN included)
+        t[i] = tiny ? 0.0 : scaled;
+    }
+    // ---- u = 1 + t in [1, 2];  1/u ----
+#pragma unroll
+    for (int i = 0; i < W; ++i) u[i] = 1.0 + t[i];
+#pragma unroll
+    for (int i = 0; i < W; ++i) y[i] = ozt_rcp_seed(u[i]);
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        const double e = ozt_fma(-u[i], y[i], 1.0);
+        y[i] = ozt_fma(y[i], ozt_fma(e, e, e), y[i]);
+    }
+    // ---- log u ----
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        uint32_t idx = (uint32_t)(ozt_hi(u[i]) - 0x3ff00000) >> 12;
+        idx = idx > 256u ? 256u : idx;
+        double rc, L;
+        ozt_log_tab((int)idx, rc, L);
+        const double w = ozt_fma(u[i], rc, -1.0), w2 = w * w;
+        double p = ozt_fma(w, 1.4285714285714285e-01, -1.6666666666666666e-01);    // w/7 - 1/6
+        p = ozt_fma(p, w, 0.2);
+        p = ozt_fma(p, w, -0.25);
+        p = ozt_fma(p, w, 3.3333333333333331e-01);
+        p = ozt_fma(p, w, -0.5);
+        r[i] = L + ozt_fma(w2, p, w);
+    }
+    // ---- assemble ----
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        const int hz = ozt_hi(z[i]);
+        const bool neg = hz < 0;
+        const bool isnan = ((uint32_t)(hz & 0x7fffffff) | (ozt_lo(z[i]) != 0 ? 1u : 0u)) > 0x7ff00000u;
+        const double spv = (neg ? 0.0 : z[i]) + r[i];
+        const double ty = t[i] * y[i];
+        const double sgv = neg ? ty : y[i];
+        sp[i] = isnan ? z[i] : spv;
+        sg[i] = isnan ? z[i] : sgv;
+    }
+}
+
+}  // namespace opl

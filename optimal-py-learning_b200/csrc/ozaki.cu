@@ -15,26 +15,33 @@
 // split (`splits`) and folded in FP64 by the caller.
 //
 // Kernel: persistent, one CTA per SM, static tile schedule (n fastest).  Warp roles:
-//   warps 0..3 / 4..7  two epilogue groups taking alternate tiles.  Drain: TMEM -> FP64 registers (magic-number
-//               int->double, Horner over the 6 diagonals, row scale), 64 columns per thread; the accumulators are
-//               released right after, so the next tile's MMAs (and the other group's next drain) overlap this
-//               group's finish phase: column scale, bias, transfer function (FP64 exp/log), and stores that go
-//               through a per-warp shared patch to become 64-byte row segments.
-//   warp 8      TMA producer: per 128-wide k-block the 6 B digit tiles (64 x 128 B each, one barrier, double
-//               buffered) and the 6 A digit tiles (128 x 128 B each, one stage per digit = a whole k-block in flight)
-//   warp 9      MMA issuer: A_p meets B_0..B_{5-p}; those B tiles are contiguous in shared memory and their
-//               accumulators p..5 are contiguous in TMEM, so each A_p needs one tcgen05.mma of N = 64 (6-p)
+//   warps 0..15 epilogue (warp w: TMEM lane quarter w % 4, 16 of the 64 columns).  Drain: TMEM -> integer recombination of
+//               the 6 diagonals -> FP64 (two exact magic-number conversions, one rounding), row scale -> staged in the 128
+//               TMEM columns the accumulators leave free; the accumulators are released right after, so the next tile's
+//               MMAs overlap the finish phase: column scale, bias, transfer function (csrc/oz_transcend.cuh), and stores
+//               that go through a per-warp shared patch to become 64-byte row segments.
+//   warps 16,17 MMA issuers taking k-blocks in turn: A_p meets B_0..B_{5-p}; those B tiles are contiguous in shared memory
+//               and their accumulators p..5 are contiguous in TMEM, so each A_p needs one tcgen05.mma of N = 64 (6-p)
 //               (two when N > 256) per K = 32 step: 32 MMAs per k-block, not 84, and with N >= 128 the SS form stays
 //               inside the SM's shared-memory bandwidth.
+//   warp 18     TMA producer: per 128-wide k-block the 6 B digit tiles (64 x 128 B each, one barrier, double
+//               buffered) and the 6 A digit tiles (128 x 128 B each, one stage per digit = a whole k-block in flight)
+// What the per-warp clock64 timeline shows (profiles/r01_ozaki_epilogue_timeline.txt): while the tensor queue is busy the
+// epilogue's FP64 instructions run 4-6x slower than with the queue idle (in EVERY sub-partition, not only the issuer's),
+// i.e. DFMA and tcgen05.mma compete for the same hardware and the MMAs win; the transfer-function epilogue therefore costs
+// roughly its stand-alone time on top of the GEMM, and the lever is its FP64 instruction count (71 -> 31 per element).
 // Tried and dropped (profiles/r01_ozaki_gemm_variants_v3.txt): staging A in the spare TMEM columns by tcgen05.cp
 // (no faster than SS once the MMAs were merged: the copy serialises with the MMAs) or by loader warps + tcgen05.st.
 #include <cooperative_groups.h>
 #include <cudaTypedefs.h>
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "ozaki.cuh"
+#include "oz_transcend.cuh"
 
 namespace opl {
 
@@ -47,10 +54,13 @@ constexpr int OZ_ZC = OZ_BN / 4;               // columns of a tile row one epil
 constexpr int OZ_OFF_A = 2 * OZ_S * OZ_B_BYTES;                 // 96 KB of B first (1024-aligned tiles)
 constexpr int OZ_OFF_PATCH = OZ_OFF_A + OZ_S * OZ_A_BYTES;      // + 96 KB of A: one stage per digit
 constexpr int OZ_OFF_BAR = OZ_OFF_PATCH + OZ_EPI_WARPS * 2048;   // per warp: 32 rows x 8 columns, 16-byte chunks swizzled
-constexpr int OZ_SMEM = OZ_OFF_BAR + 256 + 1024;
-constexpr int OZ_THREADS = 32 * (OZ_EPI_WARPS + 2);            // 576
+constexpr int OZ_SMEM = OZ_OFF_BAR + 384 + 1024;
+constexpr int OZ_MMA_WARPS = 2;                // issuers in different sub-partitions taking k-blocks in turn (see the MMA issuer below);
+                                               // 4 measure the same as 2, but 21 warps are allocated as 24 and leave 80 registers per thread
+constexpr int OZ_THREADS = 32 * (OZ_EPI_WARPS + OZ_MMA_WARPS + 1);   // 608
 static_assert(OZ_SMEM <= 232448, "shared memory budget");
 static_assert(OZ_S * OZ_BN <= 512, "TMEM budget");
+static_assert(OZ_S == 6, "the drain recombines exactly six diagonals as two 48-bit integers");
 
 __device__ __forceinline__ uint32_t oz_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void oz_mbar_init(uint64_t *bar, uint32_t count) {
@@ -170,105 +180,9 @@ __device__ __forceinline__ bool oz_elect_one() {
     return pred != 0;
 }
 
-// exact int32 -> double without the conversion pipe: bits(2^52 + 2^31 + v) - (2^52 + 2^31)
-__device__ __forceinline__ double oz_i2d(int32_t v) {
-    return __hiloint2double(0x43300000, (int)((uint32_t)v ^ 0x80000000u)) - 4503601774854144.0;
-}
-
-// ---- branch-free FP64 softplus + logistic for the fused epilogue ----------------------------------------------
-// The library exp / log / division cost ~200 FP64-pipe instructions per element and their rare-path branches keep
-// the 8 columns a thread works on from interleaving; the epilogue of the forward GEMM is FP64-pipe bound, so these
-// are written out: t = exp(-|z|), u = 1 + t, softplus = max(z,0) + log(u), logistic = z >= 0 ? 1/u : t/u
-// (for z < 0 this IS the reference's log(1 + exp(z)); for z >= 0 it is the same value without the overflow detour
-// of calculate.py:128-135).  ~60 FP64 instructions, errors ~1 ulp.
-// W elements advance in lockstep through every step, so W independent FP64 chains are adjacent in program order.
-template <int W>
-__device__ __forceinline__ void oz_rcp_n(const double (&x)[W], double (&y)[W]) {   // x in [1, 4]: approximation + 2 Newton steps
-    double e[W];
-#pragma unroll
-    for (int i = 0; i < W; ++i) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y[i]) : "d"(x[i]));
-#pragma unroll
-    for (int i = 0; i < W; ++i) e[i] = fma(-x[i], y[i], 1.0);
-#pragma unroll
-    for (int i = 0; i < W; ++i) y[i] = fma(y[i], e[i], y[i]);
-#pragma unroll
-    for (int i = 0; i < W; ++i) e[i] = fma(-x[i], y[i], 1.0);
-#pragma unroll
-    for (int i = 0; i < W; ++i) y[i] = fma(y[i], e[i], y[i]);
-}
-template <int W>
-__device__ __forceinline__ void oz_softplus_logistic_n(const double (&z)[W], double (&sp)[W], double (&sg)[W]) {
-    // ---- t = exp(-|z|) (0 below -708): n = rint(a log2 e), r = a - n ln2, Taylor degree 13, exponent insert ----
-    double a[W], t[W], nd[W], r[W], q[W];
-#pragma unroll
-    for (int i = 0; i < W; ++i) a[i] = -fabs(z[i]);
-#pragma unroll
-    for (int i = 0; i < W; ++i) t[i] = fma(a[i], 1.4426950408889634, 6755399441055744.0);
-#pragma unroll
-    for (int i = 0; i < W; ++i) nd[i] = t[i] - 6755399441055744.0;
-#pragma unroll
-    for (int i = 0; i < W; ++i) r[i] = fma(nd[i], -6.93147180369123816490e-01, a[i]);
-#pragma unroll
-    for (int i = 0; i < W; ++i) r[i] = fma(nd[i], -1.90821492927058770002e-10, r[i]);
-    // Estrin's scheme: 16 operations at dependency depth 4 instead of Horner's 13 (the finish phase is bound by the
-    // latency of dependent FP64 operations, not by their count)
-#pragma unroll
-    for (int i = 0; i < W; ++i) {
-        const double x = r[i], x2 = x * x, x4 = x2 * x2, x8 = x4 * x4;
-        const double a0 = fma(x, 1.0, 1.0);                                          // 1/0! + x/1!
-        const double a1 = fma(x, 0.16666666666666666, 0.5);                          // 1/2! + x/3!
-        const double a2 = fma(x, 0.008333333333333333, 0.041666666666666664);        // 1/4! + x/5!
-        const double a3 = fma(x, 0.0001984126984126984, 0.001388888888888889);       // 1/6! + x/7!
-        const double a4 = fma(x, 2.7557319223985893e-06, 2.48015873015873e-05);      // 1/8! + x/9!
-        const double a5 = fma(x, 2.505210838544172e-08, 2.755731922398589e-07);      // 1/10! + x/11!
-        const double a6 = fma(x, 1.6059043836821613e-10, 2.08767569878681e-09);      // 1/12! + x/13!
-        const double b0 = fma(a1, x2, a0), b1 = fma(a3, x2, a2), b2 = fma(a5, x2, a4);
-        const double d0 = fma(b1, x4, b0), d1 = fma(a6, x4, b2);
-        q[i] = fma(d1, x8, d0);
-    }
-#pragma unroll
-    for (int i = 0; i < W; ++i) {
-        const double scaled = __hiloint2double(__double2hiint(q[i]) + (__double2loint(t[i]) << 20), __double2loint(q[i]));
-        t[i] = a[i] < -708.0 ? 0.0 : scaled;
-    }
-    // ---- u = 1 + t in [1, 2]; 1/u; log(u) with the fdlibm e_log.c kernel ----
-    double u[W], ru[W], m[W], dk[W], f[W], d2[W], rd[W], s_[W], w[W], R[W];
-#pragma unroll
-    for (int i = 0; i < W; ++i) u[i] = 1.0 + t[i];
-    oz_rcp_n<W>(u, ru);
-#pragma unroll
-    for (int i = 0; i < W; ++i) {
-        const bool big = u[i] > 1.4142135623730951;
-        m[i] = big ? u[i] * 0.5 : u[i];
-        dk[i] = big ? 1.0 : 0.0;
-    }
-#pragma unroll
-    for (int i = 0; i < W; ++i) f[i] = m[i] - 1.0;
-#pragma unroll
-    for (int i = 0; i < W; ++i) d2[i] = 2.0 + f[i];
-    oz_rcp_n<W>(d2, rd);
-#pragma unroll
-    for (int i = 0; i < W; ++i) s_[i] = f[i] * rd[i];
-#pragma unroll
-    for (int i = 0; i < W; ++i) w[i] = s_[i] * s_[i];
-#pragma unroll
-    for (int i = 0; i < W; ++i) {
-        const double x = w[i], x2 = x * x, x4 = x2 * x2;
-        const double e0 = fma(x, 3.999999999940941908e-01, 6.666666666666735130e-01);
-        const double e1 = fma(x, 2.222219843214978396e-01, 2.857142874366239149e-01);
-        const double e2 = fma(x, 1.531383769920937332e-01, 1.818357216161805012e-01);
-        const double g0 = fma(e1, x2, e0), g1 = fma(1.479819860511658591e-01, x2, e2);
-        R[i] = fma(g1, x4, g0) * x;
-    }
-#pragma unroll
-    for (int i = 0; i < W; ++i) {
-        const double hfsq = 0.5 * f[i] * f[i];
-        const double l = dk[i] * 6.93147180369123816490e-01 -
-                         ((hfsq - (s_[i] * (hfsq + R[i]) + dk[i] * 1.90821492927058770002e-10)) - f[i]);
-        const double spv = fmax(z[i], 0.0) + l, sgv = z[i] >= 0.0 ? ru[i] : t[i] * ru[i];
-        sp[i] = z[i] != z[i] ? z[i] : spv;
-        sg[i] = z[i] != z[i] ? z[i] : sgv;
-    }
+// exact int64 -> double for |v| < 2^51: bits(1.5 * 2^52) + v, minus 1.5 * 2^52
+__device__ __forceinline__ double oz_l2d(long long v) {
+    return __longlong_as_double(0x4338000000000000LL + v) - 6755399441055744.0;
 }
 
 struct OzTile {
@@ -355,9 +269,9 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint8_t *sA = smem + OZ_OFF_A;                        // 6 x 16 KB: one stage per digit
     double *sPatch = reinterpret_cast<double *>(smem + OZ_OFF_PATCH);
     uint64_t *a_full = reinterpret_cast<uint64_t *>(smem + OZ_OFF_BAR);
-    uint64_t *a_empty = a_full + OZ_S;
+    uint64_t *a_empty = a_full + 4 * OZ_S;           // a_full / b_full: one set per k-block residue mod 4 (a single waiter each)
     uint64_t *b_full = a_empty + OZ_S;
-    uint64_t *b_empty = b_full + 2;
+    uint64_t *b_empty = b_full + 4;
     uint64_t *acc_full = b_empty + 2;
     uint64_t *acc_empty = acc_full + 1;
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(acc_empty + 1);
@@ -365,7 +279,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // warp roles: 0..15 epilogue (warp w: TMEM lane quarter w % 4, column quarter w / 4), 16 TMA producer, 17 MMA issuer (the
     // arbiter favours the highest warp id of a sub-partition, and the issuing thread is the latency-critical one)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int producer_warp = OZ_EPI_WARPS, mma_warp = OZ_EPI_WARPS + 1;
+    constexpr int mma_warp = OZ_EPI_WARPS, producer_warp = OZ_EPI_WARPS + OZ_MMA_WARPS;   // MMA warps 16.., then the producer
     const int tiles_m = (p.M + OZ_BM - 1) / OZ_BM, tiles_n = (p.N + OZ_BN - 1) / OZ_BN;
     const int ntiles = tiles_m * tiles_n * p.splits;
     // tile schedule: cluster c takes tile groups c, c + #clusters, ..; rank r of the cluster takes tile CS*group + r
@@ -374,14 +288,10 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     constexpr uint16_t cmask = (uint16_t)((1u << CS) - 1u);
 
     if (warp == producer_warp && lane == 0) {
-        for (int s = 0; s < OZ_S; ++s) {
-            oz_mbar_init(&a_full[s], 1);
-            oz_mbar_init(&a_empty[s], CS);
-        }
-        for (int s = 0; s < 2; ++s) {
-            oz_mbar_init(&b_full[s], 1);
-            oz_mbar_init(&b_empty[s], 1);
-        }
+        for (int s = 0; s < 4 * OZ_S; ++s) oz_mbar_init(&a_full[s], 1);
+        for (int s = 0; s < OZ_S; ++s) oz_mbar_init(&a_empty[s], CS);
+        for (int s = 0; s < 4; ++s) oz_mbar_init(&b_full[s], 1);
+        for (int s = 0; s < 2; ++s) oz_mbar_init(&b_empty[s], 1);
         oz_mbar_init(acc_full, 1);
         oz_mbar_init(acc_empty, OZ_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -404,29 +314,41 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const OzTile tl = oz_tile(p, t, tiles_m, tiles_n);
             for (int kb = 0; kb < tl.nkb; ++kb, ++kbt) {
                 const int k0 = tl.k_begin + kb * 128;
-                const uint32_t bs = kbt & 1;
+                const uint32_t bs = kbt & 1, set = kbt & 3;     // smem stage of B; barrier set of this k-block
+                uint64_t *a_full_k = a_full + set * OZ_S;
                 oz_wait(&b_empty[bs], ((kbt >> 1) & 1) ^ 1);
                 if (leader) {
-                    oz_expect_tx(&b_full[bs], OZ_S * OZ_B_BYTES);
+                    oz_expect_tx(&b_full[set], OZ_S * OZ_B_BYTES);
 #pragma unroll
-                    for (int q = 0; q < OZ_S; ++q) oz_tma_3d(sB + (bs * OZ_S + q) * OZ_B_BYTES, &tmB, k0, tl.n0, q, &b_full[bs]);
+                    for (int q = 0; q < OZ_S; ++q) oz_tma_3d(sB + (bs * OZ_S + q) * OZ_B_BYTES, &tmB, k0, tl.n0, q, &b_full[set]);
                 }
 #pragma unroll
                 for (int pp = 0; pp < OZ_S; ++pp) {   // digit pp always travels through stage pp
                     oz_wait(&a_empty[pp], (kbt & 1) ^ 1);
                     if (leader) {
-                        oz_expect_tx(&a_full[pp], OZ_A_BYTES);
+                        oz_expect_tx(&a_full_k[pp], OZ_A_BYTES);
                         if (CS == 1)
-                            oz_tma_3d(sA + pp * OZ_A_BYTES, &tmA, k0, tl.m0, pp, &a_full[pp]);
+                            oz_tma_3d(sA + pp * OZ_A_BYTES, &tmA, k0, tl.m0, pp, &a_full_k[pp]);
                         else      // my slab of the tile, delivered to every CTA of the cluster
                             oz_tma_3d_mc(sA + pp * OZ_A_BYTES + crank * (OZ_A_BYTES / CS), &tmA, k0, tl.m0 + crank * (OZ_BM / CS), pp,
-                                         &a_full[pp], cmask);
+                                         &a_full_k[pp], cmask);
                     }
                 }
             }
         }
-    } else if (warp == mma_warp) {
-        // ============ MMA issuer (warp-uniform control flow, one elected lane issues) ============
+    } else if (warp >= mma_warp) {
+        // ============ MMA issuers (warp-uniform control flow, one elected lane issues) ============
+        // p.mma_warps (1 or 2) warps in different sub-partitions take the k-blocks in turn: the plain GEMM gains 6 % over a
+        // single issuer (8192^3: 3083 -> 3248 INT8 TOP/s), whose sub-partition's epilogue warps were also the last to finish
+        // every tile (per-warp clock64 traces, profiles/r01_ozaki_epilogue_timeline.txt).
+        // Ordering needs no extra handshake: INT32 accumulation is exact and commutative, the accumulators are
+        // (re)initialised by digit 0 of a tile's first k-block, and digit pp of k-block k+1 can only be issued after
+        // digit pp of k-block k has COMPLETED (its stage is reloaded after that commit) -- so the first k-block's
+        // initialising MMAs precede every other MMA of the tile, and when the last k-block's last digit is issued all
+        // earlier k-blocks are complete: the issuer of the last k-block commits acc_full for the whole tile.
+        const int me = warp - mma_warp;
+        const uint32_t turn_mask = (uint32_t)p.mma_warps - 1u;
+        const int nt_mine = me < p.mma_warps ? ntiles : 0;   // launch_ozaki_gemm keeps mma_warps <= k-blocks per tile (see there)
         // The B digit tiles of one k-block are contiguous 8 KB blocks of 64 rows, and the accumulators of diagonals
         // p..5 are contiguous TMEM columns, so A_p . [B_0; ..; B_{5-p}]^T is ONE MMA of N = 64 (6 - p) columns
         // (cut at N = 256): 8 instructions per K = 32 step instead of 21.  All 512 TMEM columns are ours, so every
@@ -438,19 +360,29 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t desc_hi = (uint32_t)(oz_desc(0) >> 32);
         const uint32_t a_lo0 = (uint32_t)oz_desc(oz_smem_u32(sA)), b_lo0 = (uint32_t)oz_desc(oz_smem_u32(sB));
         uint32_t kbt = 0, local = 0;
-        for (int t = t_first; t < ntiles; t += t_step, ++local) {
+        for (int t = t_first; t < nt_mine; t += t_step, ++local) {
             const OzTile tl = oz_tile(p, t, tiles_m, tiles_n);
-            oz_wait(acc_empty, (local & 1) ^ 1);     // the previous tile has left TMEM
-            oz_fence_after();
+            if (tl.nkb == 0 && me == 0) {            // nothing to contract: hand the (stale) accumulators over as they are
+                oz_wait(acc_empty, (local & 1) ^ 1);
+                if (leader) oz_commit(acc_full);
+                __syncwarp();
+            }
             for (int kb = 0; kb < tl.nkb; ++kb, ++kbt) {
-                const uint32_t bs = kbt & 1;
+                if ((kbt & turn_mask) != (uint32_t)me) continue;
+                if (kb == 0) {
+                    oz_wait(acc_empty, (local & 1) ^ 1);     // the previous tile has left TMEM
+                    oz_fence_after();
+                    if (p.trace && blockIdx.x == 0 && leader && local < 32) p.trace[(local * 18 + 17) * 8 + 0] = clock64();
+                }
+                const uint32_t bs = kbt & 1, set = kbt & 3, par = (kbt >> 2) & 1;
+                const uint64_t *a_full_k = a_full + set * OZ_S;
                 const uint32_t b_lo = b_lo0 + bs * (uint32_t)((OZ_S * OZ_B_BYTES) >> 4);
                 const uint32_t first = kb > 0 ? 1u : 0u;
-                oz_wait(&b_full[bs], (kbt >> 1) & 1);
+                oz_wait(&b_full[set], par);
 #pragma unroll
                 for (int pp = 0; pp < OZ_S; ++pp) {
                     const uint32_t a_lo = a_lo0 + (uint32_t)((pp * OZ_A_BYTES) >> 4);
-                    oz_wait(&a_full[pp], kbt & 1);
+                    oz_wait(const_cast<uint64_t *>(&a_full_k[pp]), par);
                     oz_fence_after();
                     if (leader) {
                         const int nq = OZ_S - pp;              // B digits this A digit meets
@@ -472,9 +404,12 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     }
                     __syncwarp();
                 }
+                if (kb == tl.nkb - 1) {
+                    if (leader) oz_commit(acc_full);
+                    if (p.trace && blockIdx.x == 0 && leader && local < 32) p.trace[(local * 18 + 17) * 8 + 1] = clock64();
+                    __syncwarp();
+                }
             }
-            if (leader) oz_commit(acc_full);
-            __syncwarp();
         }
     } else {
         // ============ epilogue ============
@@ -491,10 +426,14 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int t = t_first; t < ntiles; t += t_step, ++local) {
             const OzTile tl = oz_tile(p, t, tiles_m, tiles_n);
             const int row = tl.m0 + lrow;
-            const double ea = (row < p.M ? p.scale_a[row] : 0.0) * (1.0 / 65536.0);
+            const double ea = (row < p.M ? p.scale_a[row] : 0.0) * (1.0 / 4294967296.0);
             const uint32_t stage_addr = ((uint32_t)(quarter * 32) << 16) + (uint32_t)(OZ_S * OZ_BN + half * 2 * OZ_ZC);
+            const bool tracer = p.trace && blockIdx.x == 0 && lane == 0 && local < 32;
+            long long *tr = p.trace + (local * 18 + warp) * 8;
+            if (tracer) tr[2] = clock64();
             oz_wait(acc_full, local & 1);
             oz_fence_after();
+            if (tracer) tr[3] = clock64();
 #pragma unroll
             for (int c0 = 0; c0 < OZ_ZC; c0 += 8) {
                 int32_t v[OZ_S][8];
@@ -502,20 +441,26 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 for (int d = 0; d < OZ_S; ++d)
                     oz_tmem_ld8(((uint32_t)(quarter * 32) << 16) + (uint32_t)(d * OZ_BN + half * OZ_ZC + c0), v[d]);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                // sum_d acc_d 256^-d, recombined in INTEGER arithmetic (the FP64 pipe is the scarce one here): two exact
+                // 48-bit integers hi = acc0 2^16 + acc1 2^8 + acc2 and lo = acc3 2^16 + acc4 2^8 + acc5, each converted exactly
+                // (magic-number add), joined by ONE rounding: (hi + lo 2^-24) 2^-16.  The 2^-16 rides on the row scale.
                 double zc[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    double s = oz_i2d(v[OZ_S - 1][j]);
-#pragma unroll
-                    for (int d = OZ_S - 2; d >= 0; --d) s = fma(s, 1.0 / 256.0, oz_i2d(v[d][j]));
-                    zc[j] = s * ea;
+                    const long long hi = ((long long)v[0][j] << 16) + ((long long)v[1][j] << 8) + (long long)v[2][j];
+                    const long long lo = ((long long)v[3][j] << 16) + ((long long)v[4][j] << 8) + (long long)v[5][j];
+                    zc[j] = fma(oz_l2d(lo), 1.0 / 16777216.0, oz_l2d(hi)) * ea;
                 }
                 oz_tmem_st_f64x8(stage_addr + 2 * c0, zc);     // FP64 tile -> the 128 spare TMEM columns
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             oz_fence_before();
             __syncwarp();
-            if (lane == 0) oz_arrive(acc_empty);              // accumulators free again
+            // FP64-heavy epilogues release the accumulators only after their finish phase: under a busy tensor queue the
+            // FP64 work crawls anyway (see the header), and undisturbed MMAs + an undisturbed finish measure 2 % faster
+            constexpr bool LATE = EPI == OZ_EPI_SOFTPLUS || EPI == OZ_EPI_TANH || EPI == OZ_EPI_GAUSSIAN;
+            if (lane == 0 && !LATE) oz_arrive(acc_empty);      // accumulators free again
+            if (tracer) tr[4] = clock64();
             // ---- finish: 2 chunks of 8 columns ----
             double *C = p.C + (int64_t)tl.split * p.split_stride;
             const bool vec_c = ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
@@ -527,6 +472,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const int col0 = tl.n0 + half * OZ_ZC + ch * 8;
                 double r[8], x[8], zz[8], mk[8], zc[8];
                 oz_tmem_ld_f64x8(stage_addr + 16 * ch, zc);
+                if (tracer && ch == 0) tr[6] = clock64();
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int col = col0 + j;
@@ -539,7 +485,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 }
                 // the transfer function of all 8 columns in ONE basic block, so the FP64 chains interleave
                 if (EPI == OZ_EPI_SOFTPLUS) {
-                    oz_softplus_logistic_n<8>(zz, r, x);
+                    ozt_softplus_logistic_n<8>(zz, r, x);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) r[j] *= mk[j];
                 } else if (EPI == OZ_EPI_TANH) {
@@ -556,10 +502,13 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     for (int j = 0; j < 8; ++j) r[j] = zz[j] * mk[j];
                 }
                 constexpr int MUL = EPI == OZ_EPI_MUL_AUX ? 1 : (EPI == OZ_EPI_MUL_DTANH ? 2 : 0);
+                if (tracer && ch == 0) tr[7] = clock64();
                 oz_store_chunk<MUL>(patch, r, C, p.ldc, row0, col0, p.M, p.N,
                                     vec_c && (MUL == 0 || (reinterpret_cast<uintptr_t>(p.aux_in) & 15) == 0), lane, p.aux_in);
                 if (want_x) oz_store_chunk<0>(patch, x, p.aux_out, p.ldaux, row0, col0, p.M, p.N, vec_x, lane);
             }
+            if (lane == 0 && LATE) oz_arrive(acc_empty);
+            if (tracer) tr[5] = clock64();
         }
     }
     oz_fence_before();
@@ -955,6 +904,20 @@ int launch_ozaki_gemm(const int8_t *a_slices, int64_t a_rows_pad, const int8_t *
                 OPL_CUDA(cudaFuncSetAttribute(table[e][c], cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
         configured = true;
     }
+    static int mma_warps = 0;
+    if (mma_warps == 0) {
+        const char *env = getenv("OPL_OZ_MMA_WARPS");
+        const int want = env ? atoi(env) : OZ_MMA_WARPS;
+        mma_warps = std::min(OZ_MMA_WARPS, want >= 4 ? 4 : (want >= 2 ? 2 : 1));
+    }
+    OzakiArgs largs = args;
+    // every issuing warp must own a k-block in EVERY tile: a warp reaches a tile's first k-block having issued into the
+    // previous tile, which pins the phase of the accumulator barrier it then waits on (parity waits cannot tell phases
+    // two apart)
+    const int nkb_regular = args.k_per_split / 128;
+    const int nkb_last = (int)ceil_div((int64_t)args.K - (int64_t)(args.splits - 1) * args.k_per_split, 128);
+    largs.mma_warps = mma_warps;
+    while (largs.mma_warps > 1 && largs.mma_warps > std::min(nkb_regular, nkb_last)) largs.mma_warps >>= 1;
     const kernel_t kernel = table[args.epi][cs == 4 ? 2 : (cs == 2 ? 1 : 0)];
     const int64_t groups = tiles / cs;
     const int64_t nclusters = std::max<int64_t>(1, std::min<int64_t>(groups, sm_count() / cs));
@@ -970,7 +933,7 @@ int launch_ozaki_gemm(const int8_t *a_slices, int64_t a_rows_pad, const int8_t *
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = cs > 1 ? 1 : 0;
-    OPL_CUDA(cudaLaunchKernelEx(&cfg, kernel, ta, tb, args));
+    OPL_CUDA(cudaLaunchKernelEx(&cfg, kernel, ta, tb, largs));
     OPL_LAUNCH_CHECK();
     if (launches) ++*launches;
     return OPL_OK;
@@ -1013,6 +976,14 @@ extern "C" int opl_bench_gemm_ozaki(int32_t M, int32_t N, int32_t K, const doubl
     if (splits > 1) OPL_CUDA(cudaMalloc(&partial, sizeof(double) * (size_t)splits * M * N));
     OPL_CUDA(cudaMemset(sa, 0, (size_t)OZ_S * mp * kp));
     OPL_CUDA(cudaMemset(sb, 0, (size_t)OZ_S * np * kp));
+    // OPL_OZ_TRACE=<file>: per-tile clock64() stamps of CTA 0 in the last iteration (MMA warp: first issue, last commit;
+    // epilogue warp 0: wait begin, accumulators ready, accumulators released, finish done), one text line per tile
+    long long *trace = nullptr;
+    const char *trace_path = getenv("OPL_OZ_TRACE");
+    if (trace_path) {
+        OPL_CUDA(cudaMalloc(&trace, sizeof(long long) * 32 * 18 * 8));
+        OPL_CUDA(cudaMemset(trace, 0, sizeof(long long) * 32 * 18 * 8));
+    }
     cudaEvent_t e0, e1, e2;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
@@ -1038,6 +1009,7 @@ extern "C" int opl_bench_gemm_ozaki(int32_t M, int32_t N, int32_t K, const doubl
         g.scale_b = eb;
         g.epi = epi;
         g.tparam = 1.0;
+        g.trace = (it == iters) ? trace : nullptr;
         if (rc == OPL_OK) rc = launch_ozaki_gemm(sa, mp, sb, np, kp, g, nullptr, nullptr);
         if (rc == OPL_OK && splits > 1)
             oz_fold_kernel<<<oz_grid1((int64_t)M * N, 256), 256>>>(partial, splits, (int64_t)M * N, (int64_t)M * N, c_dev);
@@ -1053,6 +1025,23 @@ extern "C" int opl_bench_gemm_ozaki(int32_t M, int32_t N, int32_t K, const doubl
     }
     *slice_ms_out = slice_ms / iters;
     *gemm_ms_out = gemm_ms / iters;
+    if (trace) {
+        static long long host[32 * 18 * 8];
+        cudaMemcpy(host, trace, sizeof(host), cudaMemcpyDeviceToHost);
+        if (FILE *f = fopen(trace_path, "a")) {
+            const long long t0 = host[17 * 8];
+            fprintf(f, "# M=%d N=%d K=%d epi=%d; cycles since the first MMA stamp.  'mma' tile begin issued | per epilogue warp: wait_begin acc_ready released chunk0_loaded chunk0_transfer_done finish_done\n", M, N, K, epi);
+            for (int t = 0; t < 32 && host[(t * 18 + 17) * 8 + 1]; ++t) {
+                fprintf(f, "mma %d %lld %lld\n", t, host[(t * 18 + 17) * 8] - t0, host[(t * 18 + 17) * 8 + 1] - t0);
+                for (int w = 0; w < 16; ++w) {
+                    const long long *e = host + (t * 18 + w) * 8;
+                    fprintf(f, "  w%02d %lld %lld %lld %lld %lld %lld\n", w, e[2] - t0, e[3] - t0, e[4] - t0, e[6] - t0, e[7] - t0, e[5] - t0);
+                }
+            }
+            fclose(f);
+        }
+        cudaFree(trace);
+    }
     cudaFree(sa);
     cudaFree(sb);
     cudaFree(ea);

@@ -1,0 +1,19 @@
+// Host build of csrc/oz_transcend.cuh for tests/test_host_logic.py (test infrastructure: the product compiles the same
+// header for the device).  g++ -O2 -ffp-contract=off -shared -fPIC
+#include "oz_transcend.cuh"
+
+extern "C" void ozt_softplus_logistic(const double *z, long n, double *sp, double *sg) {
+    long i = 0;
+    for (; i + 8 <= n; i += 8) {
+        double zz[8], a[8], b[8];
+        for (int j = 0; j < 8; ++j) zz[j] = z[i + j];
+        opl::ozt_softplus_logistic_n<8>(zz, a, b);
+        for (int j = 0; j < 8; ++j) { sp[i + j] = a[j]; sg[i + j] = b[j]; }
+    }
+    for (; i < n; ++i) {
+        double zz[1] = {z[i]}, a[1], b[1];
+        opl::ozt_softplus_logistic_n<1>(zz, a, b);
+        sp[i] = a[0];
+        sg[i] = b[0];
+    }
+}

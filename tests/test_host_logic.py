@@ -170,3 +170,59 @@ def test_train_retries_keep_best_attempt():
     err = m.train(numpy.zeros((1, 1)), numpy.zeros((1, 1)), iterations=2, retries=2)
     assert err == pytest.approx(0.7)     # last attempt's error is returned (base.py:213-221)
     assert m.tag == 0                    # ... but the best attempt (the first) was restored
+
+
+def test_table_driven_softplus_logistic_header_is_accurate(tmp_path):
+    """csrc/oz_transcend.cuh (the FP64 softplus / logistic of the forward GEMM epilogue: table-driven exp and log, ~26 FP64
+    instructions per element) compiled for the HOST and checked against mpmath, the reference's literal form
+    log(1.0 + exp(z)) (calculate.py:128-135) and 1 / (1 + exp(-z)) (:138-141), including the special cases."""
+    import ctypes
+    import os
+    import shutil
+    import subprocess
+    import mpmath
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no host C++ compiler")
+    here = os.path.dirname(os.path.abspath(__file__))
+    csrc = os.path.join(here, "..", "optimal-py-learning_b200", "csrc")
+    so = str(tmp_path / "libozt.so")
+    subprocess.check_call([gxx, "-O2", "-ffp-contract=off", "-std=c++14", "-shared", "-fPIC", "-I", csrc,
+                           os.path.join(here, "ozt_host_check.cpp"), "-o", so])
+    lib = ctypes.CDLL(so)
+    lib.ozt_softplus_logistic.argtypes = [ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p, ctypes.c_void_p]
+
+    def run(z):
+        z = numpy.ascontiguousarray(z, dtype=numpy.float64)
+        sp, sg = numpy.empty_like(z), numpy.empty_like(z)
+        lib.ozt_softplus_logistic(z.ctypes.data, z.size, sp.ctypes.data, sg.ctypes.data)
+        return sp, sg
+
+    rng = numpy.random.default_rng(0)
+    z = numpy.concatenate([rng.uniform(-40, 40, 3000), rng.uniform(-2, 2, 3000), rng.uniform(-750, 750, 500),
+                           rng.normal(0, 1e-3, 500), [0.0, -0.0, 1e-300, -1e-300, 707.9999, -707.9999, 708.0, -708.0,
+                                                      36.7, -36.7, -745.2, 1e300, -1e300]])
+    sp, sg = run(z)
+    mpmath.mp.prec = 200
+    for zi, a, b in zip(z, sp, sg):
+        zm = mpmath.mpf(float(zi))
+        want_sp = mpmath.log1p(mpmath.exp(zm)) if zi < 700 else zm
+        want_sg = 1 / (1 + mpmath.exp(-zm))
+        # 1 + exp(z) is rounded to a double in the reference as well: the allowance is absolute below 1
+        assert abs(mpmath.mpf(float(a)) - want_sp) <= 4.5e-16 * max(1, abs(want_sp)), (zi, a)
+        if zi > -708.0:
+            assert abs(mpmath.mpf(float(b)) - want_sg) <= 6e-16 * want_sg, (zi, b)
+        else:
+            assert b == 0.0          # exp(-708) = 3e-308: flushed instead of going subnormal
+    # the reference's literal NumPy form on the same inputs
+    with numpy.errstate(over='ignore'):
+        lit = numpy.log(1.0 + numpy.exp(z))
+    lit = numpy.where(numpy.isinf(lit), z, lit)
+    assert (numpy.abs(sp - lit) <= 4.5e-16 * numpy.maximum(1, numpy.abs(lit))).all()
+    # special values: NaN propagates, +-inf and the overflow detour (calculate.py:132-135), softplus(0) = ln 2
+    sp, sg = run([numpy.nan, numpy.inf, -numpy.inf, 0.0, 1000.0, -1000.0, 1.0])
+    assert numpy.isnan(sp[0]) and numpy.isnan(sg[0])
+    assert sp[1] == numpy.inf and sg[1] == 1.0 and sp[2] == 0.0 and sg[2] == 0.0
+    assert sp[3] == math.log(2.0) and sg[3] == 0.5
+    assert sp[4] == 1000.0 and sg[4] == 1.0 and sp[5] == 0.0 and sg[5] == 0.0
+    assert abs(sp[6] - 1.3132616875182228) <= 3e-16      # test_calculate.py:223: relu([0, 1]) == [0.6931, 1.3133]

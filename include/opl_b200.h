@@ -248,6 +248,30 @@ int opl_vec_penalty_device(int64_t n, const double *w, int32_t kind, double lamb
 /* host_out[0] = x . y   (deterministic two-stage reduction; synchronises) */
 int opl_vec_dot_device(int64_t n, const double *x, const double *y, double *host_out, void *cuda_stream);
 
+/* =====================================================================================
+ * RBF network front end.  The RBF output layer is an opl_mlp of shape
+ * (clusters, outputs) with a linear transfer fed with the similarity matrix (its flat layout
+ * [bias ; W.ravel()], architecture/rbf.py:229-231, is the MLP layout); these two entry points
+ * are the parts in front of it.
+ * ===================================================================================== */
+/* SOM.activate (architecture/som.py:61-85) for a matrix of patterns, optionally followed by
+ * calculate.gaussian (calculate.py:101-102) and the similarity scaling of RBF.activate
+ * (architecture/rbf.py:139-146):
+ *   mode 0: out[i][j] = sqrt(sum_k (x[i][k] - centers[j][k])^2)
+ *   mode 1: out[i][j] = exp(-(d^2 / variance))
+ *   mode 2: mode 1 divided by its row sum, NaN (0/0) replaced by 1/neurons
+ * x: rows x attrs, centers: neurons x attrs, out: rows x neurons, row-major FP64 device buffers. */
+int opl_rbf_similarity_device(const double *x_dev, int64_t rows, int32_t attrs, const double *centers_dev,
+                              int32_t neurons, int32_t mode, double variance, double *out_dev, void *cuda_stream);
+/* `passes` passes of Model.train_step's per-pattern loop (base.py:289-331) around
+ * SOM._train_increment / _move_neurons (architecture/som.py:87-113): for every pattern in order,
+ * winner = argmin distance, neurons within `neighborhood` of the winner move by
+ * rates[|i - winner|] * (pattern - weights[i]).  rates_dev: neighborhood + 1 doubles
+ * (calculate.gaussian(distance, neighbor_move_rate) * move_rate, computed by the caller);
+ * weights_dev: neurons x attrs, updated in place.  Asynchronous on the stream. */
+int opl_som_train_device(const double *x_dev, int64_t rows, int32_t attrs, double *weights_dev, int32_t neurons,
+                         int64_t passes, const double *rates_dev, int32_t neighborhood, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,8 +15,10 @@ from . import optimize
 from . import validation
 from .architecture.mlp import MLP, DropoutMLP
 from .architecture.regression import LinearRegressionModel, LogisticRegressionModel
+from .architecture.som import SOM
+from .architecture.rbf import RBF
 
 __all__ = ['Transfer', 'LinearTransfer', 'TanhTransfer', 'ReluTransfer', 'GaussianTransfer',
            'SoftmaxTransfer', 'ErrorFunc', 'MeanSquaredError', 'CrossEntropyError', 'L1Penalty', 'L2Penalty', 'Model',
-           'MLP', 'DropoutMLP', 'LinearRegressionModel', 'LogisticRegressionModel',
+           'MLP', 'DropoutMLP', 'LinearRegressionModel', 'LogisticRegressionModel', 'SOM', 'RBF',
            'optimize', 'validation']

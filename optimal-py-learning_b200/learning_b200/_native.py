@@ -68,6 +68,8 @@ SIGNATURES = {
     "opl_vec_scale_device": (ctypes.c_int, [i64, f64, vp, vp, vp]),
     "opl_vec_penalty_device": (ctypes.c_int, [i64, vp, i32, f64, vp, c_double_p, vp]),
     "opl_vec_dot_device": (ctypes.c_int, [i64, vp, vp, c_double_p, vp]),
+    "opl_rbf_similarity_device": (ctypes.c_int, [vp, i64, i32, vp, i32, i32, f64, vp, vp]),
+    "opl_som_train_device": (ctypes.c_int, [vp, i64, i32, vp, i32, i64, vp, i32, vp]),
 }
 
 

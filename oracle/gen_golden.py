@@ -381,6 +381,73 @@ def gen_widening(L, store, meta):
                                        penalty=list(pen) if pen else None, seed=70 + k))
         print("regression %-8s pen=%s obj=%.8g |jac|=%.4g trained err=%.6g" % (kind, pen, obj, numpy.linalg.norm(jac), errors[-1]))
 
+    # ---- SOM + RBF ----
+    from learning.architecture import som as rsom
+    from learning.architecture import rbf as rrbf
+    random.seed(90)
+    numpy.random.seed(90)
+    xs = rng.random((30, 3)) * 2 - 1
+    som = rsom.SOM(3, 5)
+    som.logging = False
+    store["som_w0"] = som._weights.copy()
+    som.train(xs, xs, iterations=25)
+    store["som_x"], store["som_w"] = xs, som._weights.copy()
+    store["som_dist"] = som.activate(xs).copy()
+    store["som_dist_vec"] = som.activate(xs[3]).copy()
+    print("som: 25 passes over 30 patterns, |w| = %.6g" % numpy.linalg.norm(som._weights))
+
+    meta["rbf"] = []
+    for k, (attrs, clusters, outs, rows, scale, variance, incremental, steps) in enumerate([
+            (3, 5, 2, 40, True, None, False, 8), (4, 6, 1, 35, False, 0.7, False, 8), (2, 4, 2, 30, True, None, True, 6)]):
+        x, y = mo.random_regression(rows, attrs, outs, rng)
+        random.seed(95 + k)
+        numpy.random.seed(95 + k)
+        model = rrbf.RBF(attrs, clusters, outs, variance=variance, scale_by_similarity=scale,
+                         cluster_incrementally=incremental)
+        model.logging = False
+        w = (2.0 * rng.random(outs + clusters * outs) - 1.0) * 0.6
+        with numpy.errstate(all='ignore'):
+            model._pre_train(x, y)                      # SOM clustering: 1000 passes (Model.train defaults)
+            centers = model._clustering_model._weights.copy()
+            obj = float(model._get_obj(w.copy(), x, y))
+            obj2, jac = model._get_obj_jac(w.copy(), x, y)
+            out = model.activate(x)
+            sim = model._similarity_tensor.copy()
+            # training trace from the seeded initial weights
+            random.seed(95 + k)
+            numpy.random.seed(95 + k)
+            model = rrbf.RBF(attrs, clusters, outs, variance=variance, scale_by_similarity=scale,
+                             cluster_incrementally=incremental)
+            model.logging = False
+            model._pre_train(x, y)
+            weights, errors = [], []
+            for _ in range(steps):
+                errors.append(float(model.train_step(x, y)))
+                weights.append(rrbf._flatten_weights(model._weight_matrix, model._bias_vec).copy())
+        assert abs(obj - float(obj2)) <= 1e-15 * max(1, abs(obj))
+        key = "rbf%d" % k
+        store[key + "_x"], store[key + "_y"], store[key + "_w"] = x, y, w
+        store[key + "_centers"], store[key + "_obj"], store[key + "_jac"] = centers, numpy.array(obj), jac
+        store[key + "_out"], store[key + "_sim"] = out, sim
+        store[key + "_weights"], store[key + "_errors"] = numpy.array(weights), numpy.array(errors)
+        store[key + "_centers_end"] = model._clustering_model._weights.copy()
+        meta["rbf"].append(dict(key=key, attrs=attrs, clusters=clusters, outs=outs, scale=scale, variance=variance,
+                                incremental=incremental, steps=steps, seed=95 + k))
+        print("rbf %s obj=%.8g |jac|=%.4g trained err=%.6g" % ((attrs, clusters, outs), obj, numpy.linalg.norm(jac), errors[-1]))
+
+    # ---- Model.stochastic_train / select_sample (base.py:39-135) ----
+    tr = numpy.load(os.path.join(GOLDEN, "traces.npz"))
+    random.seed(7)
+    numpy.random.seed(7)
+    model = rmlp.MLP((4, 6, 3), transfers=L.SoftmaxTransfer(), error_func=L.CrossEntropyError())
+    model.logging = False
+    with numpy.errstate(all='ignore'):
+        err = model.stochastic_train(tr["iris_x"], tr["iris_y"], max_iterations=4, train_kwargs={'iterations': 6})
+    store["st_error"] = numpy.array(float(err))
+    store["st_weights"] = rmlp._flatten(model._bias_vec, model._weight_matrices).copy()
+    store["st_iteration"] = numpy.array(model.iteration)
+    print("stochastic_train: 4 x 6 steps on random iris subsets, err=%.6g" % float(err))
+
     # penalty known answers
     w = rng.standard_normal(9)
     store["pen_w"] = w

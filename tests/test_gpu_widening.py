@@ -1,5 +1,5 @@
-"""GPU: SURVEY section 8(f) rows -- DropoutMLP, Linear / Logistic regression with penalties, batched
-validation -- against golden vectors produced by the real reference (oracle/gen_golden.py part E)."""
+"""GPU: SURVEY section 8(f) rows -- DropoutMLP, Linear / Logistic regression with penalties, SOM + RBF network, batched
+validation, stochastic_train -- against golden vectors produced by the real reference (oracle/gen_golden.py part E)."""
 import os
 import random
 
@@ -129,6 +129,118 @@ def test_batched_validation_equals_per_pattern_reference_semantics(L):
     assert rel_err(L.validation.get_error(model, x, y, error_func=L.CrossEntropyError()), per_row_ce) <= 1e-12
     acc = numpy.mean(numpy.argmax(out, axis=1) == numpy.argmax(y, axis=1))
     assert L.validation.get_accuracy(model, x, y) == pytest.approx(acc, abs=0)
+
+
+def test_stochastic_train_matches_reference(L, golden_traces, wide):
+    """Model.stochastic_train + select_sample (base.py:39-135): 4 outer iterations of 6 BFGS steps on random iris
+    subsets (random.sample order from the seeded generator), each mini-batch resident once per inner train."""
+    t = golden_traces
+    random.seed(7)
+    numpy.random.seed(7)
+    model = L.MLP((4, 6, 3), transfers=L.SoftmaxTransfer(), error_func=L.CrossEntropyError())
+    model.logging = False
+    err = model.stochastic_train(t["iris_x"], t["iris_y"], max_iterations=4, train_kwargs={'iterations': 6})
+    got = numpy.hstack([model._bias_vec] + [m.ravel() for m in model._weight_matrices])
+    assert rel_err(err, float(wide["st_error"])) <= 1e-6, (err, float(wide["st_error"]))
+    assert rel_err(got, wide["st_weights"]) <= 1e-6, rel_err(got, wide["st_weights"])
+    assert model.iteration == int(wide["st_iteration"])
+
+
+def test_som_matches_reference(L, wide):
+    """SOM (architecture/som.py:33-113): seeded weights, 25 passes of the competition / move loop as one resident-CTA
+    kernel launch per pass, batched and single-pattern distances."""
+    random.seed(90)
+    numpy.random.seed(90)
+    xs = wide["som_x"]
+    som = L.SOM(3, 5)
+    som.logging = False
+    assert numpy.array_equal(som._weights, wide["som_w0"])
+    assert som.train(xs, xs, iterations=25) is None          # the SOM reports no error
+    assert rel_err(som._weights, wide["som_w"]) <= 1e-12, rel_err(som._weights, wide["som_w"])
+    assert rel_err(som.activate(xs), wide["som_dist"]) <= 1e-12
+    assert rel_err(som.activate(xs[3]), wide["som_dist_vec"]) <= 1e-12
+    assert som.activate(xs[3]).shape == (5,)
+    # the per-pattern path (post_pattern_callback) is the same arithmetic
+    random.seed(90)
+    numpy.random.seed(90)
+    som2 = L.SOM(3, 5)
+    som2.logging = False
+    seen = []
+    som2.train(xs, xs, iterations=2, post_pattern_callback=lambda model, a, b: seen.append(1))
+    random.seed(90)
+    numpy.random.seed(90)
+    som3 = L.SOM(3, 5)
+    som3.logging = False
+    som3.train(xs, xs, iterations=2)
+    assert len(seen) == 60 and numpy.array_equal(som2._weights, som3._weights)
+    with pytest.raises(ValueError):
+        som.activate(numpy.zeros((2, 2, 3)))
+
+
+def test_rbf_matches_reference(L, golden_meta, wide):
+    """RBF (architecture/rbf.py:36-231): SOM clustering (1000 passes), Gaussian similarity (+ scaling by the row sum),
+    objective / Jacobian of the linear output layer, training traces incl. cluster_incrementally."""
+    for case in golden_meta["rbf"]:
+        k = case["key"]
+        x, y, w = wide[k + "_x"], wide[k + "_y"], wide[k + "_w"]
+
+        def make():
+            random.seed(case["seed"])
+            numpy.random.seed(case["seed"])
+            m = L.RBF(case["attrs"], case["clusters"], case["outs"], variance=case["variance"],
+                      scale_by_similarity=case["scale"], cluster_incrementally=case["incremental"])
+            m.logging = False
+            return m
+        model = make()
+        model._pre_train(x, y)
+        assert rel_err(model._clustering_model._weights, wide[k + "_centers"]) <= 1e-11, case
+        obj = model._get_obj(w.copy(), x, y)
+        obj2, jac = model._get_obj_jac(w.copy(), x, y)
+        assert rel_err(obj, wide[k + "_obj"]) <= 1e-10 and rel_err(obj2, wide[k + "_obj"]) <= 1e-10, case
+        assert rel_err(jac, wide[k + "_jac"]) <= 1e-10, (case, rel_err(jac, wide[k + "_jac"]))
+        assert rel_err(model.activate(x), wide[k + "_out"]) <= 1e-10, case
+        assert rel_err(model._similarity_tensor, wide[k + "_sim"]) <= 1e-11, case
+        assert rel_err(model.activate(x[2]), wide[k + "_out"][2]) <= 1e-10
+        model = make()
+        model._pre_train(x, y)
+        for step in range(case["steps"]):
+            err = model.train_step(x, y)
+            got = numpy.hstack([model._bias_vec, model._weight_matrix.ravel()])
+            assert rel_err(err, wide[k + "_errors"][step]) <= 1e-7, (case, step)
+            assert rel_err(got, wide[k + "_weights"][step]) <= 1e-7, (case, step, rel_err(got, wide[k + "_weights"][step]))
+        assert rel_err(model._clustering_model._weights, wide[k + "_centers_end"]) <= 1e-11, case
+    with pytest.raises(TypeError):
+        L.RBF(2, 3, 1, clustering_model=object())
+
+
+def test_rbf_far_pattern_gets_uniform_similarity(L):
+    """reference tests/architecture/test_rbf.py:36-60: a pattern far from every cluster has all similarities underflow;
+    0/0 is replaced by the uniform vector instead of NaN."""
+    random.seed(0)
+    numpy.random.seed(0)
+    clustering_model = L.SOM(1, 2, neighborhood=0)
+    clustering_model.logging = False
+    model = L.RBF(1, 2, 1, variance=1.0, scale_by_similarity=True, clustering_model=clustering_model)
+    model._pre_train(numpy.array([[0.], [1.]]), numpy.array([[0.], [1.]]))
+    assert numpy.allclose(model._clustering_model.activate([0]), [0, 1], atol=1e-3)
+    assert not numpy.isnan(model.activate(numpy.array([1000.]))).any()
+    assert numpy.allclose(model._similarity_tensor, [0.5, 0.5], atol=1e-3)
+    assert not numpy.isnan(model.activate(numpy.array([[0.], [1000.]]))).any()
+    assert numpy.allclose(model._similarity_tensor, [[0.73105858, 0.26894142], [0.5, 0.5]], atol=1e-3)
+
+
+def test_rbf_trains(L):
+    """reference tests/architecture/test_rbf.py:92-100: error decreases over a short train call."""
+    rng = numpy.random.default_rng(1)
+    x = rng.random((60, 2)) * 2 - 1
+    y = numpy.stack([numpy.sin(2 * x[:, 0]), x[:, 0] * x[:, 1]], axis=1)
+    random.seed(3)
+    numpy.random.seed(3)
+    model = L.RBF(2, 6, 2, scale_by_similarity=True)
+    model.logging = False
+    before = L.validation.get_error(model, x, y)
+    model.train(x, y, iterations=12)
+    assert L.validation.get_error(model, x, y) < before
 
 
 def test_stochastic_train_runs_on_device(L, golden_traces):

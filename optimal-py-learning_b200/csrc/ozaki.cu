@@ -226,6 +226,22 @@ __device__ __forceinline__ void oz_store_chunk(double *patch, const double (&v)[
     for (int j = 0; j < 4; ++j) pw[j ^ ((lane >> 1) & 3)] = make_double2(v[2 * j], v[2 * j + 1]);
     __syncwarp();
     const int pc = lane & 3, gcol = col0 + 2 * pc;
+    if (vec && row0 + 32 <= M && col0 + 8 <= N) {      // interior patch: nothing to check, one address per thread
+        const int64_t off = (int64_t)(row0 + (lane >> 2)) * ld + gcol;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int prow = (lane >> 2) + 8 * i;
+            double2 q = *reinterpret_cast<const double2 *>(patch + prow * 8 + 2 * (pc ^ ((prow >> 1) & 3)));
+            if (MUL != 0) {
+                const double2 m = *reinterpret_cast<const double2 *>(mul + off + (int64_t)8 * i * ld);
+                q.x *= MUL == 1 ? m.x : 1.0 - m.x * m.x;
+                q.y *= MUL == 1 ? m.y : 1.0 - m.y * m.y;
+            }
+            *reinterpret_cast<double2 *>(base + off + (int64_t)8 * i * ld) = q;
+        }
+        __syncwarp();
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int prow = (lane >> 2) + 8 * i, grow = row0 + prow;
@@ -473,21 +489,37 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 double r[8], x[8], zz[8], mk[8], zc[8];
                 oz_tmem_ld_f64x8(stage_addr + 16 * ch, zc);
                 if (tracer && ch == 0) tr[6] = clock64();
+                // column scale (+ bias).  Interior tiles without bias / mask skip the predicates and the loads (the finish phase
+                // is bound by its instruction count, see the header)
+                const bool inner = col0 + 8 <= p.N;
+                const bool masked = p.colmask != nullptr;
+                if (inner && !masked) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int col = col0 + j;
-                    const bool ok = col < p.N;
-                    const double eb = ok ? __ldg(p.scale_b + col) : 0.0;
-                    const double bi = (p.bias && ok) ? __ldg(p.bias + col) : 0.0;
-                    mk[j] = (p.colmask && ok) ? __ldg(p.colmask + col) : 1.0;
-                    zz[j] = zc[j] * eb + bi;
-                    x[j] = 0.0;
+                    for (int j = 0; j < 8; ++j) {
+                        const double eb = __ldg(p.scale_b + col0 + j);
+                        zz[j] = p.bias ? fma(zc[j], eb, __ldg(p.bias + col0 + j)) : zc[j] * eb;
+                        mk[j] = 1.0;
+                        x[j] = 0.0;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int col = col0 + j;
+                        const bool ok = col < p.N;
+                        const double eb = ok ? __ldg(p.scale_b + col) : 0.0;
+                        const double bi = (p.bias && ok) ? __ldg(p.bias + col) : 0.0;
+                        mk[j] = (masked && ok) ? __ldg(p.colmask + col) : 1.0;
+                        zz[j] = zc[j] * eb + bi;
+                        x[j] = 0.0;
+                    }
                 }
                 // the transfer function of all 8 columns in ONE basic block, so the FP64 chains interleave
                 if (EPI == OZ_EPI_SOFTPLUS) {
                     ozt_softplus_logistic_n<8>(zz, r, x);
+                    if (masked) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) r[j] *= mk[j];
+                        for (int j = 0; j < 8; ++j) r[j] *= mk[j];
+                    }
                 } else if (EPI == OZ_EPI_TANH) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) r[j] = tanh(zz[j]) * mk[j];
@@ -497,9 +529,12 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         r[j] = exp(-(zz[j] * zz[j] / p.tparam)) * mk[j];
                         x[j] = -2.0 * zz[j] * r[j] / p.tparam;   // derivative uses the masked output, as the reference does
                     }
-                } else {
+                } else if (masked) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) r[j] = zz[j] * mk[j];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) r[j] = zz[j];
                 }
                 constexpr int MUL = EPI == OZ_EPI_MUL_AUX ? 1 : (EPI == OZ_EPI_MUL_DTANH ? 2 : 0);
                 if (tracer && ch == 0) tr[7] = clock64();

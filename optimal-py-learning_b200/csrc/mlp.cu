@@ -21,6 +21,7 @@
 #include "gemm_f64.cuh"
 #include "gemm_tf32.cuh"
 #include "ozaki.cuh"
+#include "oz_transcend.cuh"
 
 namespace opl {
 
@@ -324,7 +325,9 @@ struct HeadArgsT {
     double tparam;
     int eid;
     double ce_div, mse_mul;
+    double ce_rdiv;         // 1 / ce_div
     int *flag;
+    long long *trace;       // tools only (OPL_HEAD_TRACE): CTA 0 writes 8 clock64() stamps per step
 };
 using HeadArgs = HeadArgsT<double>;
 
@@ -354,6 +357,11 @@ __device__ __forceinline__ double2 head_store2(float *p, double a, double b) {
 // The row stage (softmax / error / delta_L) runs one pattern per half-warp, lane = class.
 // Two shapes: R = 32 patterns per step with 16 warps (one CTA per SM) or R = 16 with 8 warps (two CTAs per SM, whose
 // latency-bound row stages and DMMA phases overlap each other).
+// tools only (OPL_HEAD_TRACE): phase stamps of CTA 0, thread 0; evaluated in place so that nothing stays live
+#define HEAD_STAMP(k)                                                                       \
+    do {                                                                                    \
+        if (p.trace && blockIdx.x == 0 && threadIdx.x == 0 && step_no < 16) p.trace[step_no * 8 + (k)] = clock64(); \
+    } while (0)
 template <typename T, int MT, int R, int HEAD_WARPS, bool CSUM>    // MT = hidden tiles (8 units) per warp: H <= 8 MT HEAD_WARPS
 __global__ void __launch_bounds__(HEAD_WARPS * 32, R == 16 ? 2 : 1) narrow_head_kernel(const HeadArgsT<T> p) {
     extern __shared__ double hsm[];
@@ -400,8 +408,9 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, R == 16 ? 2 : 1) narrow_head_
 #pragma unroll
         for (int n = 0; n < 2; ++n) dw[i][n][0] = dw[i][n][1] = 0.0;
     }
-    int buf = 0;
-    for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x, buf ^= 1) {
+    int buf = 0, step_no = 0;
+    for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x, buf ^= 1, ++step_no) {
+        HEAD_STAMP(0);
         const int64_t r0 = blk * R;
         const int nr = (int)min((int64_t)R, p.rows - r0);
         const T *As = As0 + (size_t)buf * R * ldA;
@@ -418,14 +427,24 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, R == 16 ? 2 : 1) narrow_head_
                 }
             }
         }
+        // this thread's target value for the row stage (one pattern per half-warp, lane = class): requested now, so the
+        // row stage does not wait for DRAM
+        double y_mine = 0.0;
+        {
+            const int r = warp * 2 + (lane >> 4), cl = lane & 15;
+            if (sizeof(T) == 8 && r < nr && cl < C) y_mine = p.Y[(r0 + r) * C + cl];
+        }
         for (int i = threadIdx.x; i < R * 16; i += HEAD_THREADS) Zs[(i >> 4) * ldD + (i & 15)] = 0.0;
         cp_async_wait<0>();
         __syncthreads();                       // tile `buf` landed, Zs cleared, previous step done with the other buffer
+        HEAD_STAMP(1);
         if (blk + gridDim.x < nblocks) fetch(blk + gridDim.x, buf ^ 1);
         // ---- logits: warp -> (row tile, class tile, K half); the two halves add up in Zs ----
         {
             const int mt = warp % RM, nt = (warp / RM) & 1, kh = warp / (2 * RM);
-            double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;       // two independent accumulation chains
+            // two independent accumulation chains (four or eight measure the same: the phase is bound by the FP64 pipe
+            // the two resident CTAs share, 3.9 cycles per DMMA per SM, not by the chain latency)
+            double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
             const int kq = H >> 3;                                // DMMA steps per half
             const T *ap = As + (size_t)(8 * mt + g) * ldA + 4 * kh * kq + t;
             const double *bp = Ws + (size_t)(4 * kh * kq + t) * ldW + 8 * nt + g;
@@ -435,11 +454,15 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, R == 16 ? 2 : 1) narrow_head_
                 dmma_8x8x4(e0, e1, (double)ap[4 * k + 4], bp[(4 * k + 4) * ldW]);
             }
             if (k < kq) dmma_8x8x4(c0, c1, (double)ap[4 * k], bp[4 * k * ldW]);
+            c0 += e0;
+            c1 += e1;
             double *zp = Zs + (8 * mt + g) * ldD + 8 * nt + 2 * t;
-            atomicAdd(zp, c0 + e0);             // 0 + a + b == 0 + b + a: the order of the two halves does not matter
-            atomicAdd(zp + 1, c1 + e1);
+            atomicAdd(zp, c0);                  // 0 + a + b == 0 + b + a: the order of the two halves does not matter
+            atomicAdd(zp + 1, c1);
         }
+        HEAD_STAMP(2);
         __syncthreads();
+        HEAD_STAMP(3);
         // ---- output transfer + error + delta_L: one pattern per half-warp, lane = class ----
         {
             static_assert(HEAD_WARPS * 2 == R && 4 * RM == HEAD_WARPS, "one pattern per half-warp, two K halves per logits tile");
@@ -478,6 +501,30 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, R == 16 ? 2 : 1) narrow_head_
                 if (!backward) continue;
                 goto head_backward;
             }
+            if (sizeof(T) == 8 && softmax && p.eid == OPL_ERROR_CROSS_ENTROPY) {
+                // parity mode, classification head.  The row stage is one dependent FP64 chain per pattern (~36 cycles per
+                // link), so exp / log / reciprocal are the short table-driven forms of oz_transcend.cuh (~35 links instead
+                // of ~110 for the library routines; ~1 ulp each).  Same formulas and the same numpy.nan_to_num rules as
+                // error.py:89-116: log(0) -> -DBL_MAX, y/0 -> +-DBL_MAX, 0/0 and NaN -> 0.
+                const double mx = group_max(live ? z : -INFINITY, 16);
+                const double e = live ? ozt_exp_nonpos(z - mx) : 0.0;
+                const double den = group_sum(e, 16);                         // in [1, 16] (or NaN)
+                a_out = e * ozt_rcp(den);
+                double gq = 0.0;
+                if (live) {
+                    const bool regular = a_out >= 9.332636185032189e-302;  // 2^-1000: normal, reciprocal finite
+                    const double lg = regular ? ozt_log_pos(a_out) : (a_out > 0.0 ? log(a_out) : (a_out == 0.0 ? -kBig : 0.0));
+                    loss += lg * y_mine;
+                    const double q = regular ? y_mine * ozt_rcp(a_out) : nan_to_num(y_mine / a_out);
+                    gq = q * p.ce_rdiv;
+                }
+                const double tt = group_sum(live ? gq * a_out : 0.0, 16);
+                if (backward) Zs[r * ldD + cl] = live ? a_out * (gq - tt) : 0.0;
+                HEAD_STAMP(4);
+                __syncthreads();
+                if (!backward) continue;
+                goto head_backward;
+            }
             if (softmax) {   // calculate.py:152-153
                 const double mx = group_max(live ? z : -INFINITY, 16);
                 const double e = live ? exp(z - mx) : 0.0;
@@ -486,7 +533,7 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, R == 16 ? 2 : 1) narrow_head_
                 a_out = live ? transfer_value(p.tid, p.tparam, z) : 0.0;
             }
             double gq = 0.0;
-            if (live) gq = error_term(ra, a_out, p.Y[(r0 + r) * C + cl], loss, bad);
+            if (live) gq = error_term(ra, a_out, sizeof(T) == 8 ? y_mine : p.Y[(r0 + r) * C + cl], loss, bad);
             double d;
             if (softmax) {   // delta_k = a_k (g_k - sum_j g_j a_j): dsoftmax contracted (mlp.py:295)
                 const double tt = group_sum(live ? gq * a_out : 0.0, 16);
@@ -496,9 +543,11 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, R == 16 ? 2 : 1) narrow_head_
             }
             if (backward) Zs[r * ldD + cl] = live ? d : 0.0;
         }
+        HEAD_STAMP(4);
         __syncthreads();
         if (!backward) continue;
     head_backward:
+        HEAD_STAMP(5);
         // ---- delta_prev = (delta_L W^T) o slope ----
 #pragma unroll
         for (int i = 0; i < MT; ++i) {
@@ -534,6 +583,7 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, R == 16 ? 2 : 1) narrow_head_
                 }
             }
         }
+        HEAD_STAMP(6);
         // ---- dW += A^T delta_L ----
 #pragma unroll
         for (int i = 0; i < MT; ++i) {
@@ -548,6 +598,7 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, R == 16 ? 2 : 1) narrow_head_
                     dmma_8x8x4(dw[i][n][0], dw[i][n][1], (double)ap[(size_t)4 * k * ldA], bp[4 * k * ldD]);
             }
         }
+        HEAD_STAMP(7);
         __syncthreads();                       // Zs / this A buffer are free again
     }
     cp_async_wait<0>();
@@ -1080,6 +1131,7 @@ int fused_head(opl_mlp *ws, const double *w, const double *y, int64_t rows, bool
     a.tparam = ws->tparam[L - 1];
     a.eid = ws->error_id;
     a.ce_div = -(double)ws->norm_rows;
+    a.ce_rdiv = 1.0 / a.ce_div;
     a.mse_mul = 2.0 / ((double)ws->norm_rows * (double)C);
     a.flag = ws->flag;
     a.loss_partial = ws->loss_partial;
@@ -1097,12 +1149,32 @@ int fused_head(opl_mlp *ws, const double *w, const double *y, int64_t rows, bool
         OPL_CUDA(cudaFuncSetAttribute(narrow_head_kernel<double, 4, 16, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_smem(256, 16)));
         configured = true;
     }
+    static long long *head_trace = nullptr;
+    const char *trace_path = getenv("OPL_HEAD_TRACE");
+    if (trace_path && !head_trace) {
+        OPL_CUDA(cudaMalloc(&head_trace, sizeof(long long) * 128));
+        OPL_CUDA(cudaMemset(head_trace, 0, sizeof(long long) * 128));
+    }
+    a.trace = trace_path ? head_trace : nullptr;
     mark(ws, STAGE_HEAD * 100 + L - 1);
     if (R == 32)
         narrow_head_kernel<double, 2, 32, 16, false><<<grid, 512, smem, ws->stream>>>(a);
     else
         narrow_head_kernel<double, 4, 16, 8, false><<<grid, 256, smem, ws->stream>>>(a);
     OPL_LAUNCH_CHECK();
+    if (trace_path) {     // tools only: per-step phase stamps of CTA 0, thread 0 (synchronises)
+        long long host[128];
+        OPL_CUDA(cudaStreamSynchronize(ws->stream));
+        OPL_CUDA(cudaMemcpy(host, head_trace, sizeof(host), cudaMemcpyDeviceToHost));
+        if (FILE *f = fopen(trace_path, "w")) {
+            fprintf(f, "# narrow_head_kernel, CTA 0 thread 0, cycles since the first stamp: step_begin tile_landed logits_done sync row_stage_done sync dA_done dW_done\n");
+            for (int i = 0; i < 16 && host[8 * i + 1]; ++i) {
+                for (int k = 0; k < 8; ++k) fprintf(f, "%lld ", host[8 * i + k] - host[0]);
+                fprintf(f, "\n");
+            }
+            fclose(f);
+        }
+    }
     ++ws->launches;
     mark(ws, STAGE_LOSS * 100);
     loss_final_kernel<<<1, 256, 0, ws->stream>>>(ws->loss_partial, grid, ws->error_id, (double)ws->norm_rows, (double)C, obj_out);

@@ -49,6 +49,11 @@ OZT_FN void ozt_log_tab(int i, double &rc, double &L) {
     rc = __longlong_as_double((long long)v.x);
     L = __longlong_as_double((long long)v.y);
 }
+OZT_FN void ozt_logh_tab(int i, double &rc, double &L) {
+    const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2 *>(&OZT_LOGH_BITS[i][0]));
+    rc = __longlong_as_double((long long)v.x);
+    L = __longlong_as_double((long long)v.y);
+}
 #else
 OZT_FN int ozt_hi(double x) { uint64_t b; memcpy(&b, &x, 8); return (int)(uint32_t)(b >> 32); }
 OZT_FN int ozt_lo(double x) { uint64_t b; memcpy(&b, &x, 8); return (int)(uint32_t)b; }
@@ -63,7 +68,65 @@ OZT_FN double ozt_fma(double a, double b, double c) { return fma(a, b, c); }
 OZT_FN double ozt_rcp_seed(double x) { return ozt_make(ozt_hi(1.0 / ozt_make(ozt_hi(x), 0)), 0); }
 OZT_FN double ozt_exp_tab(int j) { double x; memcpy(&x, &OZT_EXP_BITS[j], 8); return x; }
 OZT_FN void ozt_log_tab(int i, double &rc, double &L) { memcpy(&rc, &OZT_LOG_BITS[i][0], 8); memcpy(&L, &OZT_LOG_BITS[i][1], 8); }
+OZT_FN void ozt_logh_tab(int i, double &rc, double &L) { memcpy(&rc, &OZT_LOGH_BITS[i][0], 8); memcpy(&L, &OZT_LOGH_BITS[i][1], 8); }
 #endif
+
+// ---- single-value forms for latency-bound row stages (fused head: softmax + cross entropy) ---------------------------
+// Short dependency chains are the point there: ~11 dependent FP64 operations for exp, ~10 for log, 3 for 1/x, against
+// ~40 / ~45 / ~12 for the library routines (a dependent FP64 operation costs ~36 cycles on this part).
+
+// exp(x) for x <= 0 (softmax: logit minus the row maximum), -inf -> 0, NaN -> NaN; subnormal results are rounded by the
+// hardware (two-step scaling), as the reference's exp does
+OZT_FN double ozt_exp_nonpos(double x) {
+    const double t = ozt_fma(x, 92.332482616893656877, 6755399441055744.0);
+    const double nd = t - 6755399441055744.0;
+    double r = ozt_fma(nd, -6.93147180369123816490e-01 / 64.0, x);
+    r = ozt_fma(nd, -1.90821492927058770002e-10 / 64.0, r);
+    const double r2 = r * r;
+    double p = ozt_fma(r, 8.3333333333333332e-03, 4.1666666666666664e-02);
+    p = ozt_fma(p, r, 1.6666666666666666e-01);
+    p = ozt_fma(p, r, 0.5);
+    const double s = ozt_fma(r2, p, r);
+    const int n = ozt_lo(t), k = n >> 6;
+    const double T = ozt_exp_tab(n & 63);
+    const double q = ozt_fma(T, s, T);
+    const bool sub = k < -1000;
+    const double v = ozt_make(ozt_hi(q) + ((k + (sub ? 128 : 0)) << 20), ozt_lo(q)) * (sub ? 2.938735877055719e-39 : 1.0);   // 2^-128
+    const uint32_t ax = (uint32_t)(ozt_hi(x) & 0x7fffffff);
+    const bool isnan = (ax | (ozt_lo(x) != 0 ? 1u : 0u)) > 0x7ff00000u;
+    return isnan ? x : (ax >= 0x40875000u ? 0.0 : v);       // |x| >= 746: below the smallest subnormal
+}
+
+// 1/a for a normal a whose reciprocal is finite: MUFU seed (2^-20) + one cubic Newton step, ~1 ulp
+OZT_FN double ozt_rcp(double a) {
+    const double y = ozt_rcp_seed(a);
+    const double e = ozt_fma(-a, y, 1.0);
+    return ozt_fma(y, ozt_fma(e, e, e), y);
+}
+
+// log(a) for a positive finite a (normal or subnormal): a = u 2^(kk-1), u in [1, 2); log a = kk ln2 + (log u - ln2) with the
+// bracket from the table centred on a = 1 (relative accuracy kept for a -> 1-, where cross entropy lives)
+OZT_FN double ozt_log_pos(double a) {
+    int hi = ozt_hi(a), adj = 0;
+    if (hi < 0x00100000) {                 // subnormal: rare
+        a *= 18014398509481984.0;          // 2^54
+        hi = ozt_hi(a);
+        adj = -54;
+    }
+    const int kk = (hi >> 20) - 1022 + adj;
+    const double u = ozt_make((hi & 0x000fffff) | 0x3ff00000, ozt_lo(a));
+    double rc, L;
+    ozt_logh_tab((hi >> 12) & 0xff, rc, L);
+    const double w = ozt_fma(u, rc, -1.0), w2 = w * w;
+    double p = ozt_fma(w, 1.4285714285714285e-01, -1.6666666666666666e-01);
+    p = ozt_fma(p, w, 0.2);
+    p = ozt_fma(p, w, -0.25);
+    p = ozt_fma(p, w, 3.3333333333333331e-01);
+    p = ozt_fma(p, w, -0.5);
+    const double lw = ozt_fma(w2, p, w);
+    const double kd = (double)kk;
+    return ozt_fma(kd, 6.93147180369123816490e-01, L + ozt_fma(kd, 1.90821492927058770002e-10, lw));
+}
 
 // W elements advance in lockstep through every step, so W independent FP64 chains are adjacent in program order
 // (a dependent DFMA has ~36 cycles of latency on this part).

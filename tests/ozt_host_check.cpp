@@ -17,3 +17,11 @@ extern "C" void ozt_softplus_logistic(const double *z, long n, double *sp, doubl
         sg[i] = b[0];
     }
 }
+
+extern "C" void ozt_scalar_forms(const double *x, long n, double *e, double *l, double *r) {
+    for (long i = 0; i < n; ++i) {
+        e[i] = opl::ozt_exp_nonpos(-(x[i] < 0 ? -x[i] : x[i]));      // exp(-|x|)
+        l[i] = opl::ozt_log_pos(x[i] < 0 ? -x[i] : x[i]);            // log |x|
+        r[i] = opl::ozt_rcp(x[i]);
+    }
+}

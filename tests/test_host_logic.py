@@ -226,3 +226,47 @@ def test_table_driven_softplus_logistic_header_is_accurate(tmp_path):
     assert sp[3] == math.log(2.0) and sg[3] == 0.5
     assert sp[4] == 1000.0 and sg[4] == 1.0 and sp[5] == 0.0 and sg[5] == 0.0
     assert abs(sp[6] - 1.3132616875182228) <= 3e-16      # test_calculate.py:223: relu([0, 1]) == [0.6931, 1.3133]
+
+
+def test_scalar_exp_log_rcp_forms_of_the_head(tmp_path):
+    """The single-value forms used by the fused head's softmax + cross-entropy row stage (csrc/oz_transcend.cuh:
+    ozt_exp_nonpos, ozt_log_pos, ozt_rcp), host build against mpmath: exp incl. the subnormal range and the underflow
+    point, log on (0, 1] incl. subnormals and a -> 1 (relative accuracy), reciprocal."""
+    import ctypes
+    import os
+    import shutil
+    import subprocess
+    import mpmath
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no host C++ compiler")
+    here = os.path.dirname(os.path.abspath(__file__))
+    csrc = os.path.join(here, "..", "optimal-py-learning_b200", "csrc")
+    so = str(tmp_path / "libozt.so")
+    subprocess.check_call([gxx, "-O2", "-ffp-contract=off", "-std=c++14", "-shared", "-fPIC", "-I", csrc,
+                           os.path.join(here, "ozt_host_check.cpp"), "-o", so])
+    lib = ctypes.CDLL(so)
+    lib.ozt_scalar_forms.argtypes = [ctypes.c_void_p, ctypes.c_long] + [ctypes.c_void_p] * 3
+    rng = numpy.random.default_rng(1)
+    x = numpy.concatenate([rng.uniform(0, 50, 1500), rng.uniform(0, 1, 1500), 1 - 10.0 ** rng.uniform(-16, -1, 1000),
+                           10.0 ** rng.uniform(-320, 0, 1500), rng.uniform(700, 750, 300),
+                           [1.0, 0.5, 4.9e-324, 2.2250738585072014e-308, 1e-310, 745.13, 745.2, 746.0, 1000.0, numpy.inf]])
+    e, l, r = numpy.empty_like(x), numpy.empty_like(x), numpy.empty_like(x)
+    lib.ozt_scalar_forms(x.ctypes.data, x.size, e.ctypes.data, l.ctypes.data, r.ctypes.data)
+    mpmath.mp.prec = 200
+    for xi, ei, li, ri in zip(x, e, l, r):
+        if numpy.isinf(xi):
+            assert ei == 0.0
+            continue
+        xm = mpmath.mpf(float(xi))
+        want = mpmath.exp(-xm)
+        if want > mpmath.mpf(2) ** -1022:
+            assert abs(mpmath.mpf(float(ei)) - want) <= 4e-16 * want, (xi, ei)
+        else:                                   # subnormal results: within one spacing, 0 below the smallest one
+            assert abs(mpmath.mpf(float(ei)) - want) <= mpmath.mpf(2) ** -1074, (xi, ei)
+        if 0 < xi <= 1:
+            lg = mpmath.log(xm)
+            assert abs(mpmath.mpf(float(li)) - lg) <= 4e-16 * abs(lg), (xi, li)
+        if 1e-300 < xi < 1e300:
+            assert abs(mpmath.mpf(float(ri)) * xm - 1) <= 3e-16, (xi, ri)
+    assert l[list(x).index(1.0)] == 0.0 and l[list(x).index(0.5)] == -math.log(2.0)

@@ -253,9 +253,16 @@ def run_gpu(args):
     wd = dev.to_device(w)
     out = torch.empty(n + 1, dtype=torch.float64, device="cuda")
 
+    # N > 1: this rank's [gradient ; objective] is written into peer-mapped memory and one kernel pulls and adds every rank's
+    # vector over NVLink (csrc/collective.cu), exactly what MLP._probe does; NCCL if symmetric memory is unavailable
+    peer = model._peer_allreduce(ws, n + 1) if world > 1 else None
+
     def device_step():
-        nat.check(nat.lib.opl_mlp_eval_device(ws.pointer, dev.ptr(wd), 0.0, None, 1, dev.ptr(out)))
-        if world > 1:
+        mine = peer.next_slot() if peer is not None else out
+        nat.check(nat.lib.opl_mlp_eval_device(ws.pointer, dev.ptr(wd), 0.0, None, 1, dev.ptr(mine)))
+        if peer is not None:
+            peer.reduce(out)
+        elif world > 1:
             dist.all_reduce(out)
 
     for _ in range(args.warmup):
@@ -367,9 +374,9 @@ def run_gpu(args):
                                "entropy, FP64 parity mode (large GEMMs: exact INT8 digit products on tcgen05, FP64 recombination), one full-batch "
                                "obj+grad evaluation per step",
                    "rows_per_gpu": ROWS, "shape": list(SHAPE), "n_weights": int(n),
-                   "parallelism": "batch rows sharded x%d, NCCL all-reduce of [grad;obj]" % world if world > 1 else "single GPU",
+                   "parallelism": ("batch rows sharded x%d, all-reduce of [grad;obj] %s" % (world, ("in one kernel over NVLink peer memory (%s)" % {"nvls": "NVSwitch multicast: multimem.ld_reduce + multimem.st", "pull": "rank-ordered pull"}[peer.mode]) if peer is not None else "by NCCL")) if world > 1 else "single GPU",
                    "l2": "inputs larger than L2 (X shard 376 MB, activations 3 x 123 MB vs 126 MB L2)"},
-        "gpu_launches": int(launches + bfgs.get("launches", 0)),
+        "gpu_launches": int(launches + bfgs.get("launches", 0) + (args.steps if peer is not None else 0)),
         "clocks": clocks,
         "bfgs": bfgs,
     }

@@ -272,6 +272,30 @@ int opl_rbf_similarity_device(const double *x_dev, int64_t rows, int32_t attrs, 
 int opl_som_train_device(const double *x_dev, int64_t rows, int32_t attrs, double *weights_dev, int32_t neurons,
                          int64_t passes, const double *rates_dev, int32_t neighborhood, void *cuda_stream);
 
+/* =====================================================================================
+ * Multi-GPU: the all-reduce of the batch-sharded evaluation as one kernel over
+ * NVLink peer memory.  The reference has no counterpart (single process); it completes what
+ * mlp.py:269-276 sums over ALL patterns when the patterns are sharded over ranks.
+ * ===================================================================================== */
+/* out[i] = sum over ranks r = 0..world-1 (in that order, so every rank gets the bit-identical
+ * result) of buffer_r[i], i < count.  buffer_ptrs[r] / flag_ptrs[r]: this process's peer-mapped
+ * device addresses of rank r's vector and of rank r's flag array (32 x uint32, zero-initialised
+ * once); host arrays of `world` entries.  `seq` must increase by one per call on every rank and the
+ * caller alternates between two buffers by its parity (see csrc/collective.cu).  Asynchronous on
+ * the stream; the vector of this rank must have been produced by earlier work on the same stream. */
+int opl_allreduce_sum_device(int32_t world, int32_t rank, const uint64_t *buffer_ptrs, const uint64_t *flag_ptrs,
+                             int64_t count, uint32_t seq, double *out_dev, void *cuda_stream);
+
+/* The same sum on an NVSwitch system with multicast (NVLS): rank r reduces its 1/world slice in the
+ * switch (multimem.ld_reduce), broadcasts it into every rank's result buffer (multimem.st), and after
+ * a second flag round every rank copies the complete result to out_dev.  mc_in / mc_res: multicast
+ * addresses of this call's input / result buffers; res_local: this rank's result buffer;
+ * flag_ptrs[r]: peer-mapped address of rank r's 32 x uint32 flag array (zero-initialised once);
+ * counter_dev: one zero-initialised uint32 in local device memory.  seq / parity rules as above. */
+int opl_allreduce_sum_nvls_device(int32_t world, int32_t rank, uint64_t mc_in, uint64_t mc_res, const double *res_local,
+                                  const uint64_t *flag_ptrs, int64_t count, uint32_t seq, double *out_dev,
+                                  uint32_t *counter_dev, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,7 +21,7 @@ OUT_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(OUT_DIR, "libopl_b200.so")
 OBJ_DIR = os.path.join(HERE, "build")
 
-SOURCES = ["common.cu", "gemm_f64.cu", "gemm_tf32.cu", "ozaki.cu", "mlp.cu", "bfgs.cu", "lbfgs.cu", "rbf.cu"]
+SOURCES = ["common.cu", "gemm_f64.cu", "gemm_tf32.cu", "ozaki.cu", "mlp.cu", "bfgs.cu", "lbfgs.cu", "rbf.cu", "collective.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

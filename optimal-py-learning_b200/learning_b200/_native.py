@@ -70,6 +70,8 @@ SIGNATURES = {
     "opl_vec_dot_device": (ctypes.c_int, [i64, vp, vp, c_double_p, vp]),
     "opl_rbf_similarity_device": (ctypes.c_int, [vp, i64, i32, vp, i32, i32, f64, vp, vp]),
     "opl_som_train_device": (ctypes.c_int, [vp, i64, i32, vp, i32, i64, vp, i32, vp]),
+    "opl_allreduce_sum_device": (ctypes.c_int, [i32, i32, ctypes.POINTER(u64), ctypes.POINTER(u64), i64, ctypes.c_uint32, vp, vp]),
+    "opl_allreduce_sum_nvls_device": (ctypes.c_int, [i32, i32, u64, u64, vp, ctypes.POINTER(u64), i64, ctypes.c_uint32, vp, vp, vp]),
 }
 
 

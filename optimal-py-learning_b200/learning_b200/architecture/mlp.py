@@ -208,17 +208,32 @@ class _KernelModel(Model):
         """Evaluate at x + alpha*direction on the device.  Returns (obj, slope, grad tensor | None)."""
         n = x_dev.numel()
         out = torch.empty(n + 1, dtype=torch.float64, device=x_dev.device)
+        sharded = getattr(ws, 'sharded', False)
+        peer = self._peer_allreduce(ws, n + 1) if sharded and want_grad else None
+        mine = peer.next_slot() if peer is not None else out
         nat.check(nat.lib.opl_mlp_eval_device(ws.pointer, dev.ptr(x_dev), float(alpha), dev.ptr(direction),
-                                              1 if want_grad else 0, dev.ptr(out)))
-        if getattr(ws, 'sharded', False):
-            # batch-sharded ranks hold partial sums of [gradient ; objective]: one NCCL all-reduce
-            torch.distributed.all_reduce(out if want_grad else out[n:])
+                                              1 if want_grad else 0, dev.ptr(mine)))
+        if peer is not None:
+            # batch-sharded ranks hold partial sums of [gradient ; objective]: the evaluation wrote this rank's vector
+            # into peer-mapped memory, one kernel pulls every rank's vector over NVLink and adds them in rank order
+            peer.reduce(out)
+        elif sharded:
+            torch.distributed.all_reduce(out if want_grad else out[n:])     # objective only / no peer memory: NCCL
         scalars = (ctypes.c_double * 3)()
         nat.check(nat.lib.opl_mlp_probe_scalars(ws.pointer, dev.ptr(out), dev.ptr(direction),
                                                 1 if want_grad else 0, scalars))
         self.obj_jac_evaluations += 1
         self._last_grad_norm = float(numpy.sqrt(scalars[2])) if want_grad else None
         return scalars[0], scalars[1], (out[:n] if want_grad else None)
+
+    def _peer_allreduce(self, ws, count):
+        """The workspace's peer-memory all-reduce for vectors of ``count`` doubles (None: use NCCL)."""
+        state = getattr(ws, 'peer_allreduce', False)
+        if state is False or (state is not None and state.count != count):
+            from .. import _collective
+            state = _collective.make(count)
+            ws.peer_allreduce = state
+        return state
 
     def _objective(self, parameter_vec, input_matrix, target_matrix, want_grad):
         """Shared body of _get_obj / _get_obj_jac: NumPy in -> host-buffer C-ABI call, device in -> device call."""

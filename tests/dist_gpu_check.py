@@ -58,9 +58,31 @@ def main():
     h_local = model._optimizer.inverse_hessian()
     begin, end, _ = model._optimizer._row_range(w.size)
     assert rel_err(h_local, ref.h[begin:end]) <= 1e-7, rel_err(h_local, ref.h[begin:end])
+    # the peer-memory all-reduce kernel on its own: equal to NCCL's sum, bit-identical on every rank, over several rounds
+    # (double buffering / monotonic flags), odd and even lengths
+    from learning_b200 import _collective
+    used_peer = getattr(model._workspace, "peer_allreduce", None) is not None
+    for count in (203521, 7):
+        ar = _collective.make(count)
+        if ar is None:
+            assert not used_peer
+            break
+        g = torch.Generator(device="cuda").manual_seed(100 + rank)
+        for rnd in range(5):
+            mine = torch.randn(count, dtype=torch.float64, device="cuda", generator=g) * (10.0 ** (rnd - 2))
+            ar.next_slot().copy_(mine)
+            out = torch.empty(count, dtype=torch.float64, device="cuda")
+            ar.reduce(out)
+            want = mine.clone()
+            dist.all_reduce(want)
+            assert float((out - want).abs().max()) <= 1e-13 * float(want.abs().max()), (count, rnd)
+            gathered = [torch.empty_like(out) for _ in range(world)]
+            dist.all_gather(gathered, out)
+            assert all(torch.equal(gathered[0], t) for t in gathered), "ranks disagree bitwise"
     dist.barrier()
     if rank == 0:
-        print("dist_gpu_check ok: world=%d, sharded obj/grad + 12 row-sharded BFGS steps match the oracle" % world)
+        print("dist_gpu_check ok: world=%d, sharded obj/grad + 12 row-sharded BFGS steps match the oracle; gradient all-reduce: %s"
+              % (world, "peer-memory kernel (%s)" % model._workspace.peer_allreduce.mode if used_peer else "NCCL"))
     dist.destroy_process_group()
 
 

@@ -56,21 +56,48 @@ __global__ void reduce_unpad_kernel(const float *__restrict__ partial, int split
     }
 }
 
-__global__ void colsum32_partial_kernel(const float *__restrict__ D, int64_t rows, int64_t ld, int cols,
-                                        int64_t rows_per_block, double *__restrict__ partial) {
-    __shared__ double tile[8][33];
-    const int col = blockIdx.x * 32 + threadIdx.x;
+// column sums of a rows x cols FP32 matrix (row pitch ld, a multiple of 32 with zero padding), stage 1:
+// partial[blockIdx.y][col].  HBM-bound: a thread owns four adjacent columns (one 16-byte load per row) and four rows are in
+// flight per thread; block = 32 x 8 threads = 128 columns x 8 row phases.
+__global__ void __launch_bounds__(256) colsum32_partial_kernel(const float *__restrict__ D, int64_t rows, int64_t ld, int cols,
+                                                               int64_t rows_per_block, double *__restrict__ partial) {
+    __shared__ double tile[8][32][5];
+    const int c4 = (blockIdx.x * 32 + threadIdx.x) * 4;
     const int64_t r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
-    double s = 0.0;
-    if (col < cols)
-        for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) s += (double)D[r * ld + col];
-    tile[threadIdx.y][threadIdx.x] = s;
-    __syncthreads();
-    if (threadIdx.y == 0 && col < cols) {
-        double tot = 0.0;
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    if (c4 < ld) {
+        int64_t r = r0 + threadIdx.y;
+        for (; r + 24 < r1; r += 32) {
+            float4 v[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) tot += tile[k][threadIdx.x];
-        partial[(int64_t)blockIdx.y * cols + col] = tot;
+            for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4 *>(D + (r + 8 * u) * ld + c4);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                s[0] += (double)v[u].x;
+                s[1] += (double)v[u].y;
+                s[2] += (double)v[u].z;
+                s[3] += (double)v[u].w;
+            }
+        }
+        for (; r < r1; r += 8) {
+            const float4 v = *reinterpret_cast<const float4 *>(D + r * ld + c4);
+            s[0] += (double)v.x;
+            s[1] += (double)v.y;
+            s[2] += (double)v.z;
+            s[3] += (double)v.w;
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) tile[threadIdx.y][threadIdx.x][e] = s[e];
+    __syncthreads();
+    if (threadIdx.y < 4) {                       // row phase y folds component y of every thread column (fixed order)
+        const int col = c4 + threadIdx.y;
+        if (col < cols) {
+            double tot = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) tot += tile[k][threadIdx.x][threadIdx.y];
+            partial[(int64_t)blockIdx.y * cols + col] = tot;
+        }
     }
 }
 
@@ -325,11 +352,12 @@ int fast_backward(opl_mlp *ws, const float *x32, int64_t rows, double *grad, int
     }
     if (!have_bias_grad) {   // db = column sums of delta_0
         const int cols = (int)ws->width[1];
-        int64_t nblk = std::max<int64_t>(1, std::min<int64_t>(ceil_div(rows, 64), (2 * (int64_t)sm_count()) / ceil_div(cols, 32) + 1));
+        const int64_t gx = ceil_div(f->pw[1], 128);
+        int64_t nblk = std::max<int64_t>(1, std::min<int64_t>(ceil_div(rows, 64), (8 * (int64_t)sm_count()) / gx + 1));
         if (nblk * cols > ws->partials_len) nblk = std::max<int64_t>(1, ws->partials_len / cols);
         const int64_t rpb = ceil_div(rows, nblk);
         nblk = ceil_div(rows, rpb);
-        dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)nblk);
+        dim3 grid((unsigned)gx, (unsigned)nblk);
         mark(ws, STAGE_BIAS * 100);
         colsum32_partial_kernel<<<grid, dim3(32, 8), 0, ws->stream>>>(f->delta[0], rows, f->pw[1], cols, rpb, ws->partials);
         OPL_LAUNCH_CHECK();

@@ -472,8 +472,8 @@ def run_fast_mode(args, torch, L, nat, dev, xd, yd, wd, obj_f64, grad_f64):
     for i in range(count.value):
         stage[int(kinds[i])] = stage.get(int(kinds[i]), 0.0) + float(tms[i]) / args.steps
     names = {1: "forward GEMM", 2: "row kernel", 3: "dW GEMM", 4: "dW reduce", 5: "dA GEMM", 6: "bias colsum", 7: "loss",
-             0: "trial point + weight convert"}
-    gemm_ms = sum(v for k, v in stage.items() if k // 100 in (1, 3, 5))
+             10: "fused head", 0: "trial point + weight convert"}
+    gemm_ms = sum(v for k, v in stage.items() if k // 100 in (1, 3, 5, 10))
     flops = algorithmic_flops(SHAPE, ROWS)
     g64 = grad_f64[:n]
     rel_grad = float(((out[:n] - g64).norm() / g64.norm()).item())

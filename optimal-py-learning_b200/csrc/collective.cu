@@ -53,6 +53,25 @@ __device__ __forceinline__ double ld_peer1(const double *p) {
     return v;
 }
 
+__device__ __forceinline__ unsigned long long ar_now_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Wait until the flag reaches `seq` (monotonic counters; the signed difference handles wrap-around).  Ranks may be far apart
+// in host time (one of them logging, checkpointing, timing a CPU baseline), so the wait is patient: fast polls first, then
+// sleeping polls, and a trap only after ten minutes -- a dead peer must not hang the GPU for good.
+__device__ __forceinline__ void wait_flags(const uint32_t *mine, uint32_t seq) {
+    unsigned int spins = 0;
+    unsigned long long start = 0;
+    while ((int32_t)(ld_acquire_sys(mine) - seq) < 0) {
+        if (++spins < 4096) continue;
+        if (start == 0) start = ar_now_ns();
+        __nanosleep(1000);
+        if ((spins & 4095u) == 0 && ar_now_ns() - start > 600ull * 1000000000ull) __trap();
+    }
+}
+
 __global__ void __launch_bounds__(256) allreduce_pull_kernel(const AllReduceArgs p) {
     // (1) my vector was written by earlier kernels of this stream: complete and visible at kernel start
     if (blockIdx.x == 0 && threadIdx.x < p.world) {
@@ -60,14 +79,7 @@ __global__ void __launch_bounds__(256) allreduce_pull_kernel(const AllReduceArgs
         st_release_sys(p.flag[threadIdx.x] + p.rank, p.seq);
     }
     // (2) every CTA waits for every rank's announcement (flags are monotonic; the difference handles wrap-around)
-    if (threadIdx.x < p.world) {
-        const uint32_t *mine = p.flag[p.rank] + threadIdx.x;
-        unsigned long long spins = 0;
-        while ((int32_t)(ld_acquire_sys(mine) - p.seq) < 0) {
-            __nanosleep(64);
-            if (++spins > (1ull << 26)) __trap();      // a peer never arrived (~10 s): trap instead of hanging the GPU
-        }
-    }
+    if (threadIdx.x < p.world) wait_flags(p.flag[p.rank] + threadIdx.x, p.seq);
     __syncthreads();
     // (3) rank-ordered sum.  All peers' loads of an element pair are issued before the first addition (NVLink latency is
     // ~2 us: dependent load -> add -> load chains made this kernel slower than NCCL); two pairs per thread and step.
@@ -117,14 +129,6 @@ struct NvlsArgs {
     double *out;
     unsigned int *counter;                // local, zero between launches: CTAs done with their part of the slice
 };
-
-__device__ __forceinline__ void wait_flags(const uint32_t *mine, uint32_t seq) {
-    unsigned long long spins = 0;
-    while ((int32_t)(ld_acquire_sys(mine) - seq) < 0) {
-        __nanosleep(64);
-        if (++spins > (1ull << 26)) __trap();
-    }
-}
 
 __global__ void __launch_bounds__(256) allreduce_nvls_kernel(const NvlsArgs p) {
     // (A) inputs ready everywhere

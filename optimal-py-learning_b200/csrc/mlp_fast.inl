@@ -371,6 +371,287 @@ int fast_backward(opl_mlp *ws, const float *x32, int64_t rows, double *grad, int
 // The fused narrow head on FP32 (TF32-rounded) activations: same kernel as the parity mode, FP64 arithmetic inside (the
 // head is streaming, not tensor work), FP32 loads / TF32-rounded stores.  When the head's delta_prev is delta_0 (two-layer
 // networks) its per-CTA column sums are the bias gradient and the separate column-sum pass disappears.
+// ---------------------------------------------------------------------------------------
+// The fused narrow head of the fast mode on the TF32 tensor path.  Same streaming structure as narrow_head_kernel (one
+// pass over the hidden activations: logits, output transfer + error, delta_L, dW += A^T delta_L, delta_prev =
+// (delta_L W^T) o slope), but the three small products are mma.sync.m16n8k8 TF32 with FP32 accumulation instead of FP64
+// DMMA: the operands are TF32-rounded FP32 already, a 16-pattern step is exactly one M = 16 tile, and the FP64 pipe (one
+// DMMA per 3.9 cycles per SM, shared with every FP64 instruction) that bounds the FP64 head is not touched.  R = 16
+// patterns per step, 8 warps, 51-56 KB of shared memory: three to four CTAs per SM.
+//   logits  Z[16 x 16]   = As[16 x H] . W[H x 16]          warp -> (class tile, K quarter); quarters folded in fixed order
+//   dA      D[16 x H]    = dL[16 x 16] . W^T[16 x H]        warp -> hidden tiles w, w+8, ..; epilogue x slope, TF32 round, store
+//   dW      G[H x 16]   += As^T[H x 16] . dL[16 x 16]       warp -> 16-row hidden tiles w, w+8; FP32 accumulators in registers
+// W is kept once, transposed (Wt[class][hidden], pitch H+4); As pitch H+4; both conflict-free for the logits fragments.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                                uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+constexpr int FH_R = 16, FH_THREADS = 256, FH_LDZ = 24;
+size_t fast_head_smem(int H) {
+    return sizeof(float) * ((size_t)16 * (H + 4) + 16 * FH_LDZ + 4 * 256 + 2 * (size_t)FH_R * (H + 4));
+}
+
+__global__ void __launch_bounds__(FH_THREADS, 3) narrow_head_tf32_kernel(const HeadArgsT<float> p) {
+    extern __shared__ float fsm[];
+    __shared__ double scratch[33];
+    const int H = p.H, C = p.C;
+    const int ldT = H + 4, ldA = H + 4;
+    float *Wt = fsm;                          // 16 x ldT, classes >= C are zero rows
+    float *Zs = Wt + 16 * ldT;                // 16 x 24: delta_L (TF32-rounded)
+    float *Zp = Zs + 16 * FH_LDZ;             // 4 x 16 x 16: partial logits of the four K quarters
+    float *As0 = Zp + 4 * 256;                // 2 x 16 x ldA
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    const bool softmax = p.tid == OPL_TRANSFER_SOFTMAX;
+    const bool backward = p.delta_prev != nullptr;
+    const int h4 = H >> 2;                    // 16-byte chunks per row
+    const int64_t nblocks = (p.rows + FH_R - 1) / FH_R;
+    auto fetch = [&](int64_t blk, int buf) {
+        const int64_t r0 = blk * FH_R;
+        float *dst = As0 + (size_t)buf * FH_R * ldA;
+        for (int i = threadIdx.x; i < FH_R * h4; i += FH_THREADS) {
+            const int r = i / h4, c4 = i - r * h4;
+            const bool ok = r0 + r < p.rows;
+            cp_async16(dst + (size_t)r * ldA + 4 * c4, p.A + (ok ? (r0 + r) * p.ld + 4 * c4 : 0), ok);
+        }
+        cp_async_commit();
+    };
+    if ((int64_t)blockIdx.x < nblocks) fetch(blockIdx.x, 0);
+    for (int i = threadIdx.x; i < H * 16; i += FH_THREADS) {
+        const int h = i >> 4, c = i & 15;
+        Wt[c * ldT + h] = c < C ? round_tf32((float)p.W[h * C + c]) : 0.f;
+    }
+    RowArgs ra = {};
+    ra.eid = p.eid;
+    ra.ce_div = p.ce_div;
+    ra.mse_mul = p.mse_mul;
+    double loss = 0.0;
+    bool bad = false;
+    float dw[2][2][4];                        // [hidden 16-tile j][class tile][fragment]
+    float csum[4][2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int n = 0; n < 2; ++n)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) dw[j][n][e] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) csum[i][0] = csum[i][1] = 0.f;
+    const int ksteps = H >> 3;
+    const bool two_class_steps = C > 8;
+    int buf = 0;
+    for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x, buf ^= 1) {
+        const int64_t r0 = blk * FH_R;
+        const int nr = (int)min((int64_t)FH_R, p.rows - r0);
+        const float *As = As0 + (size_t)buf * FH_R * ldA;
+        // slope values of this step's delta_prev fragments and this thread's target value: requested now
+        float2 x[4][2];
+        if (backward && p.mode != 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int col = 8 * (warp + 8 * i) + 2 * t;
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    const int row = g + 8 * hf;
+                    x[i][hf] = (col < H && row < nr) ? *reinterpret_cast<const float2 *>(p.aux + (r0 + row) * p.ld + col)
+                                                     : make_float2(1.f, 1.f);
+                }
+            }
+        }
+        double y_mine = 0.0;
+        {
+            const int r = warp * 2 + (lane >> 4), cl = lane & 15;
+            if (r < nr && cl < C) y_mine = p.Y[(r0 + r) * C + cl];
+        }
+        cp_async_wait<0>();
+        __syncthreads();                       // tile `buf` landed; the previous step is done with the other buffer, Zs and Zp
+        if (blk + gridDim.x < nblocks) fetch(blk + gridDim.x, buf ^ 1);
+        // ---- logits: warp -> (class tile nt, K quarter kq); k-steps kq, kq + 4, .. ----
+        {
+            const int nt = warp & 1, kq = warp >> 1;
+            float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+            const float *a_lo = As + (size_t)g * ldA + t, *a_hi = As + (size_t)(g + 8) * ldA + t;
+            const float *b = Wt + (size_t)(8 * nt + g) * ldT + t;
+            int ks = kq;
+            for (; ks + 4 < ksteps; ks += 8) {
+                mma_tf32_16x8x8(c0, __float_as_uint(a_lo[8 * ks]), __float_as_uint(a_hi[8 * ks]), __float_as_uint(a_lo[8 * ks + 4]),
+                                __float_as_uint(a_hi[8 * ks + 4]), __float_as_uint(b[8 * ks]), __float_as_uint(b[8 * ks + 4]));
+                const int k2 = ks + 4;
+                mma_tf32_16x8x8(c1, __float_as_uint(a_lo[8 * k2]), __float_as_uint(a_hi[8 * k2]), __float_as_uint(a_lo[8 * k2 + 4]),
+                                __float_as_uint(a_hi[8 * k2 + 4]), __float_as_uint(b[8 * k2]), __float_as_uint(b[8 * k2 + 4]));
+            }
+            if (ks < ksteps)
+                mma_tf32_16x8x8(c0, __float_as_uint(a_lo[8 * ks]), __float_as_uint(a_hi[8 * ks]), __float_as_uint(a_lo[8 * ks + 4]),
+                                __float_as_uint(a_hi[8 * ks + 4]), __float_as_uint(b[8 * ks]), __float_as_uint(b[8 * ks + 4]));
+            float *zp = Zp + kq * 256 + g * 16 + 8 * nt + 2 * t;
+            *reinterpret_cast<float2 *>(zp) = make_float2(c0[0] + c1[0], c0[1] + c1[1]);
+            *reinterpret_cast<float2 *>(zp + 8 * 16) = make_float2(c0[2] + c1[2], c0[3] + c1[3]);
+        }
+        __syncthreads();
+        // ---- output transfer + error + delta_L: one pattern per half-warp, lane = class ----
+        {
+            const int hw = lane >> 4, cl = lane & 15;
+            const int r = warp * 2 + hw;
+            const bool live = r < nr && cl < C;
+            const float zf = (Zp[r * 16 + cl] + Zp[256 + r * 16 + cl]) + (Zp[512 + r * 16 + cl] + Zp[768 + r * 16 + cl]);
+            float d_out = 0.f;
+            if (softmax && p.eid == OPL_ERROR_CROSS_ENTROPY) {
+                // the classification head in FP32: same formulas, FLT_MAX where the FP64 path has DBL_MAX
+                float mx = live ? zf : -INFINITY;
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                const float e = live ? expf(zf - mx) : 0.f;
+                float den = e;
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) den += __shfl_xor_sync(0xffffffffu, den, o);
+                const float a = e / den;
+                float gq = 0.f;
+                if (live) {
+                    const float y = (float)y_mine;
+                    float lg = logf(a);
+                    lg = isnan(lg) ? 0.f : (isinf(lg) ? (lg > 0 ? 3.4028234664e38f : -3.4028234664e38f) : lg);
+                    loss += (double)(lg * y);
+                    float q = y / a;
+                    q = isnan(q) ? 0.f : (isinf(q) ? (q > 0 ? 3.4028234664e38f : -3.4028234664e38f) : q);
+                    gq = q / (float)p.ce_div;
+                }
+                float tt = live ? gq * a : 0.f;
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) tt += __shfl_xor_sync(0xffffffffu, tt, o);
+                d_out = live ? a * (gq - tt) : 0.f;
+            } else {
+                const double z = (double)zf;
+                double a_out;
+                if (softmax) {
+                    const double mx = group_max(live ? z : -INFINITY, 16);
+                    const double e = live ? exp(z - mx) : 0.0;
+                    a_out = e / group_sum(e, 16);
+                } else {
+                    a_out = live ? transfer_value(p.tid, p.tparam, z) : 0.0;
+                }
+                double gq = 0.0;
+                if (live) gq = error_term(ra, a_out, y_mine, loss, bad);
+                double d;
+                if (softmax) {
+                    const double tt = group_sum(live ? gq * a_out : 0.0, 16);
+                    d = a_out * (gq - tt);
+                } else {
+                    d = live ? gq * transfer_slope(p.tid, p.tparam, z, a_out) : 0.0;
+                }
+                d_out = live ? (float)d : 0.f;
+            }
+            if (backward) Zs[r * FH_LDZ + cl] = round_tf32(d_out);
+        }
+        __syncthreads();
+        if (!backward) continue;
+        // ---- delta_prev = (delta_L W^T) o slope: warp -> hidden tiles w, w + 8, .. ----
+        {
+            const uint32_t a0 = __float_as_uint(Zs[g * FH_LDZ + t]), a1 = __float_as_uint(Zs[(g + 8) * FH_LDZ + t]);
+            const uint32_t a2 = __float_as_uint(Zs[g * FH_LDZ + t + 4]), a3 = __float_as_uint(Zs[(g + 8) * FH_LDZ + t + 4]);
+            uint32_t e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+            if (two_class_steps) {
+                e0 = __float_as_uint(Zs[g * FH_LDZ + 8 + t]);
+                e1 = __float_as_uint(Zs[(g + 8) * FH_LDZ + 8 + t]);
+                e2 = __float_as_uint(Zs[g * FH_LDZ + 12 + t]);
+                e3 = __float_as_uint(Zs[(g + 8) * FH_LDZ + 12 + t]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int nt = warp + 8 * i;
+                if (8 * nt >= H) break;
+                float c[4] = {0.f, 0.f, 0.f, 0.f};
+                const float *b = Wt + (size_t)t * ldT + 8 * nt + g;
+                mma_tf32_16x8x8(c, a0, a1, a2, a3, __float_as_uint(b[0]), __float_as_uint(b[4 * ldT]));
+                if (two_class_steps) mma_tf32_16x8x8(c, e0, e1, e2, e3, __float_as_uint(b[8 * ldT]), __float_as_uint(b[12 * ldT]));
+                const int col = 8 * nt + 2 * t;
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    const int row = g + 8 * hf;
+                    if (row < nr) {
+                        float o0 = c[2 * hf], o1 = c[2 * hf + 1];
+                        if (p.mode == 1) {
+                            o0 *= x[i][hf].x;
+                            o1 *= x[i][hf].y;
+                        } else if (p.mode == 2) {
+                            o0 *= 1.f - x[i][hf].x * x[i][hf].x;
+                            o1 *= 1.f - x[i][hf].y * x[i][hf].y;
+                        }
+                        const float2 st = make_float2(round_tf32(o0), round_tf32(o1));
+                        *reinterpret_cast<float2 *>(p.delta_prev + (r0 + row) * p.ld + col) = st;
+                        csum[i][0] += st.x;
+                        csum[i][1] += st.y;
+                    }
+                }
+            }
+        }
+        // ---- dW += A^T delta_L: warp -> hidden 16-tiles w, w + 8 ----
+        {
+            uint32_t b[2][2][2];              // [row step][class tile][b0, b1]
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+                for (int n = 0; n < 2; ++n) {
+                    b[ks][n][0] = __float_as_uint(Zs[(8 * ks + t) * FH_LDZ + 8 * n + g]);
+                    b[ks][n][1] = __float_as_uint(Zs[(8 * ks + t + 4) * FH_LDZ + 8 * n + g]);
+                }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int m0 = 16 * (warp + 8 * j);
+                if (m0 >= H) break;
+                const bool hi_ok = m0 + 8 < H;           // H is a multiple of 8: the upper half of the last tile may be absent
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                    const float *a = As + (size_t)(8 * ks + t) * ldA + m0 + g;
+                    const uint32_t a0 = __float_as_uint(a[0]), a1 = hi_ok ? __float_as_uint(a[8]) : 0u;
+                    const uint32_t a2 = __float_as_uint(a[4 * ldA]), a3 = hi_ok ? __float_as_uint(a[4 * ldA + 8]) : 0u;
+                    mma_tf32_16x8x8(dw[j][0], a0, a1, a2, a3, b[ks][0][0], b[ks][0][1]);
+                    if (two_class_steps) mma_tf32_16x8x8(dw[j][1], a0, a1, a2, a3, b[ks][1][0], b[ks][1][1]);
+                }
+            }
+        }
+        __syncthreads();                       // Zs / Zp / this A buffer are free again
+    }
+    cp_async_wait<0>();
+    if (bad) *p.flag = 1;
+    if (backward) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int m0 = 16 * (warp + 8 * j);
+            if (m0 >= H) break;
+#pragma unroll
+            for (int n = 0; n < 2; ++n)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int m = m0 + g + 8 * (e >> 1), c = 8 * n + 2 * t + (e & 1);
+                    if (m < H && c < C) p.dw_partial[(size_t)blockIdx.x * H * C + (size_t)m * C + c] = (double)dw[j][n][e];
+                }
+        }
+        if (p.colsum_partial) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int nt = warp + 8 * i;
+                if (8 * nt >= H) break;
+                float s0 = csum[i][0], s1 = csum[i][1];
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                }
+                if (g == 0) {
+                    p.colsum_partial[(size_t)blockIdx.x * H + 8 * nt + 2 * t] = (double)s0;
+                    p.colsum_partial[(size_t)blockIdx.x * H + 8 * nt + 2 * t + 1] = (double)s1;
+                }
+            }
+        }
+    }
+    loss = block_sum(loss, scratch);
+    if (threadIdx.x == 0) p.loss_partial[blockIdx.x] = loss;
+}
+
 bool fast_head_ok(const opl_mlp *ws) {
     const int L = ws->layers;
     if (L < 2 || !ws->fused_head) return false;
@@ -384,8 +665,8 @@ int fast_fused_head(opl_mlp *ws, bool want_grad, double *grad, double *obj_out) 
     const int L = ws->layers;
     const int H = (int)ws->width[L - 1], C = (int)ws->width[L];
     constexpr int R = 16;
-    const size_t smem = head_smem(H, R, sizeof(float));
-    int grid = (int)std::min<int64_t>(ceil_div(ws->rows, R), 2 * (int64_t)sm_count());
+    const size_t smem = fast_head_smem(H);
+    int grid = (int)std::min<int64_t>(ceil_div(ws->rows, R), 3 * (int64_t)sm_count());
     grid = std::min(grid, ws->loss_blocks);
     if (want_grad) grid = (int)std::min<int64_t>(grid, ws->partials_len / ((int64_t)H * (C + 1)));
     if (grid < 1) return fail(OPL_E_STATE, "fused head (fast mode): scratch too small");
@@ -416,12 +697,12 @@ int fast_fused_head(opl_mlp *ws, bool want_grad, double *grad, double *obj_out) 
     }
     static bool configured = false;
     if (!configured) {
-        OPL_CUDA(cudaFuncSetAttribute(narrow_head_kernel<float, 4, 16, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)head_smem(256, R, sizeof(float))));
+        OPL_CUDA(cudaFuncSetAttribute(narrow_head_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)fast_head_smem(256)));
         configured = true;
     }
     mark(ws, STAGE_HEAD * 100 + L - 1);
-    narrow_head_kernel<float, 4, 16, 8, true><<<grid, 256, smem, ws->stream>>>(a);
+    narrow_head_tf32_kernel<<<grid, FH_THREADS, smem, ws->stream>>>(a);
     OPL_LAUNCH_CHECK();
     ++ws->launches;
     mark(ws, STAGE_LOSS * 100);

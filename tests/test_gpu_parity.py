@@ -647,6 +647,10 @@ def test_fast_mode_golden_cases(L, golden_meta, golden_objgrad):
     ((512, 128, 128, 10), [(2, 0), (2, 0), (4, 0)], 1, 2048),
     ((256, 192, 160, 10), [(1, 0), (3, 1.5), (0, 0)], 0, 1000),
     ((40, 70, 33, 65), [(4, 0), (2, 0), (2, 0)], 0, 517),
+    # TF32 tensor-path head: last 16-row hidden tile half empty (H % 16 == 8), odd k-step count, <= 8 classes, tanh slope,
+    # a partial last step; then 16 classes, tanh output + MSE through the generic row stage
+    ((64, 40, 5), [(1, 0), (4, 0)], 1, 1003),
+    ((96, 72, 16), [(2, 0), (1, 0)], 0, 333),
 ])
 def test_fast_mode_against_oracle_at_size(L, shape, transfers, eid, rows):
     rng = numpy.random.default_rng(hash(shape) % 1000 + 1)

@@ -224,7 +224,11 @@ class _KernelModel(Model):
                                                 1 if want_grad else 0, scalars))
         self.obj_jac_evaluations += 1
         self._last_grad_norm = float(numpy.sqrt(scalars[2])) if want_grad else None
-        return scalars[0], scalars[1], (out[:n] if want_grad else None)
+        grad = None
+        if want_grad:
+            grad = out[:n]
+            grad.opl_norm = self._last_grad_norm      # ||g|| came back with the probe scalars: train_step needs no extra reduction
+        return scalars[0], scalars[1], grad
 
     def _peer_allreduce(self, ws, count):
         """The workspace's peer-memory all-reduce for vectors of ``count`` doubles (None: use NCCL)."""
@@ -267,6 +271,7 @@ class _KernelModel(Model):
     def __getstate__(self):
         state = dict(self.__dict__)
         state['_workspace'] = None       # device buffers are rebuilt on demand
+        state.pop('_flat_stage', None)
         return state
 
 
@@ -353,7 +358,7 @@ class MLP(_KernelModel):
         problem.ray_obj_jac = lambda xk, alpha, direction: self._probe(ws, xk, alpha, direction, True)[:2]
         problem.ray_obj = lambda xk, alpha, direction: self._probe(ws, xk, alpha, direction, False)[0]
 
-        flat = dev.to_device(_flatten(self._bias_vec, self._weight_matrices))
+        flat = self._flat_params_to_device()
         error, flat_next = self._optimizer.next(problem, flat)
         self._bias_vec, self._weight_matrices = _unflatten_weights(dev.to_host(flat_next), self._shape)
 
@@ -361,9 +366,25 @@ class MLP(_KernelModel):
         if jacobian is None:
             self.converged = False
         else:
-            norm = dev.norm(jacobian) if dev.is_device_vector(jacobian) else float(numpy.linalg.norm(jacobian))
+            norm = getattr(jacobian, 'opl_norm', None)
+            if norm is None:
+                norm = dev.norm(jacobian) if dev.is_device_vector(jacobian) else float(numpy.linalg.norm(jacobian))
             self.converged = norm < self._jacobian_norm_break
         return error
+
+    def _flat_params_to_device(self):
+        """[bias ; W0 ; W1 ; ..] (mlp.py:313-315) assembled in a page-locked staging buffer and uploaded from there (the
+        reference keeps the weights as host arrays, so every step starts with this upload)."""
+        parts = [numpy.asarray(self._bias_vec, dtype=float).ravel()] + [numpy.asarray(m, dtype=float).ravel()
+                                                                        for m in self._weight_matrices]
+        n = sum(p.size for p in parts)
+        stage = getattr(self, '_flat_stage', None)
+        if stage is None or stage.numel() != n:
+            stage = torch.empty(n, dtype=torch.float64, pin_memory=True)
+            self._flat_stage = stage
+        torch.cuda.current_stream().synchronize()        # an earlier upload from this buffer has been consumed
+        numpy.concatenate(parts, out=stage.numpy())
+        return stage.cuda(non_blocking=True)
 
     def _post_train(self, input_matrix, target_matrix):
         """Reset optimizer: the problem may change on the next train call (mlp.py:184-190)."""

@@ -305,7 +305,8 @@ __global__ void __launch_bounds__(256) narrow_backprop_kernel(const double *__re
 // accumulation, so the result is bit-reproducible; per-CTA dW partials are folded by the split-K reduce kernel.
 // mode (slope of the hidden transfer): 0 none, 1 aux = f' stored by the forward GEMM, 2 aux = tanh activation.
 // ---------------------------------------------------------------------------------------
-// T = storage type of the activation-side matrices: double (parity mode) or float (fast mode: TF32-rounded operands)
+// T = storage type of the activation-side matrices: double (parity mode, narrow_head_kernel below) or float (fast mode:
+// TF32-rounded operands, narrow_head_tf32_kernel in mlp_fast.inl)
 template <typename T>
 struct HeadArgsT {
     const T *A;             // rows x H hidden activations, row stride ld
@@ -432,7 +433,7 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, R == 16 ? 2 : 1) narrow_head_
         double y_mine = 0.0;
         {
             const int r = warp * 2 + (lane >> 4), cl = lane & 15;
-            if (sizeof(T) == 8 && r < nr && cl < C) y_mine = p.Y[(r0 + r) * C + cl];
+            if (r < nr && cl < C) y_mine = p.Y[(r0 + r) * C + cl];
         }
         for (int i = threadIdx.x; i < R * 16; i += HEAD_THREADS) Zs[(i >> 4) * ldD + (i & 15)] = 0.0;
         cp_async_wait<0>();
@@ -471,37 +472,7 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, R == 16 ? 2 : 1) narrow_head_
             const bool live = r < nr && cl < C;
             const double z = Zs[r * ldD + cl];
             double a_out;
-            if (sizeof(T) == 4 && softmax && p.eid == OPL_ERROR_CROSS_ENTROPY) {
-                // fast mode, classification head: the row stage in FP32 (a dependent FP64 operation costs ~36 cycles here,
-                // an FP32 one 4); same formulas, FLT_MAX where the FP64 path has DBL_MAX
-                const float zf = (float)z;
-                float mx = live ? zf : -INFINITY;
-#pragma unroll
-                for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                const float e = live ? expf(zf - mx) : 0.f;
-                float den = e;
-#pragma unroll
-                for (int o = 8; o > 0; o >>= 1) den += __shfl_xor_sync(0xffffffffu, den, o);
-                const float a = e / den;
-                float gq = 0.f;
-                if (live) {
-                    const float y = (float)p.Y[(r0 + r) * C + cl];
-                    float lg = logf(a);
-                    lg = isnan(lg) ? 0.f : (isinf(lg) ? (lg > 0 ? 3.4028234664e38f : -3.4028234664e38f) : lg);
-                    loss += (double)(lg * y);
-                    float q = y / a;
-                    q = isnan(q) ? 0.f : (isinf(q) ? (q > 0 ? 3.4028234664e38f : -3.4028234664e38f) : q);
-                    gq = q / (float)p.ce_div;
-                }
-                float tt = live ? gq * a : 0.f;
-#pragma unroll
-                for (int o = 8; o > 0; o >>= 1) tt += __shfl_xor_sync(0xffffffffu, tt, o);
-                if (backward) Zs[r * ldD + cl] = live ? (double)(a * (gq - tt)) : 0.0;
-                __syncthreads();
-                if (!backward) continue;
-                goto head_backward;
-            }
-            if (sizeof(T) == 8 && softmax && p.eid == OPL_ERROR_CROSS_ENTROPY) {
+            if (softmax && p.eid == OPL_ERROR_CROSS_ENTROPY) {
                 // parity mode, classification head.  The row stage is one dependent FP64 chain per pattern (~36 cycles per
                 // link), so exp / log / reciprocal are the short table-driven forms of oz_transcend.cuh (~35 links instead
                 // of ~110 for the library routines; ~1 ulp each).  Same formulas and the same numpy.nan_to_num rules as
@@ -533,7 +504,7 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, R == 16 ? 2 : 1) narrow_head_
                 a_out = live ? transfer_value(p.tid, p.tparam, z) : 0.0;
             }
             double gq = 0.0;
-            if (live) gq = error_term(ra, a_out, sizeof(T) == 8 ? y_mine : p.Y[(r0 + r) * C + cl], loss, bad);
+            if (live) gq = error_term(ra, a_out, y_mine, loss, bad);
             double d;
             if (softmax) {   // delta_k = a_k (g_k - sum_j g_j a_j): dsoftmax contracted (mlp.py:295)
                 const double tt = group_sum(live ? gq * a_out : 0.0, 16);

@@ -209,6 +209,7 @@ int int8_forward_layer(opl_mlp *ws, int l, const double *w, const double *in, in
     g.M = (int)rows;
     g.N = (int)dout;
     g.K = (int)kp;
+    g.k_valid = (int)din;
     g.k_per_split = (int)kp;
     g.splits = 1;
     g.scale_a = a_scale;
@@ -249,6 +250,7 @@ int int8_da_layer(opl_mlp *ws, int l, const double *w, int64_t rows) {
     g.M = (int)rows;
     g.N = (int)din;
     g.K = (int)kp;
+    g.k_valid = (int)dout;
     g.k_per_split = (int)kp;
     g.splits = 1;
     g.scale_a = s->a_scale;
@@ -304,6 +306,7 @@ int int8_dw_layer(opl_mlp *ws, int l, const double *in, int64_t rows, double *gr
     g.M = (int)m;
     g.N = (int)dout;
     g.K = (int)kp;
+    g.k_valid = (int)rows;
     g.k_per_split = plan.k_per_split;
     g.splits = plan.splits;
     g.split_stride = count;

@@ -394,6 +394,9 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const uint64_t *a_full_k = a_full + set * OZ_S;
                 const uint32_t b_lo = b_lo0 + bs * (uint32_t)((OZ_S * OZ_B_BYTES) >> 4);
                 const uint32_t first = kb > 0 ? 1u : 0u;
+                // K = 32 steps of this k-block that hold data (the rest is zero padding of the contraction index)
+                const int k_left = (p.k_valid > 0 ? p.k_valid : p.K) - (tl.k_begin + kb * 128);
+                const int live = k_left >= 128 ? 4 : (k_left + 31) >> 5;
                 oz_wait(&b_full[set], par);
 #pragma unroll
                 for (int pp = 0; pp < OZ_S; ++pp) {
@@ -409,6 +412,7 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                             const uint32_t d_tmem = (uint32_t)((pp + q0) * OZ_BN);
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {      // 4 x K32 per 128-byte row, +32 bytes each
+                                if (k >= live) break;
                                 const uint32_t acc = (pp == 0 && k == 0) ? first : 1u;
                                 const uint64_t bd = oz_desc_join(desc_hi, b_lo + (uint32_t)((q0 * OZ_B_BYTES + k * 32) >> 4));
                                 oz_umma_ss(d_tmem, oz_desc_join(desc_hi, a_lo + k * 2), bd, idesc, acc);
@@ -1037,6 +1041,7 @@ extern "C" int opl_bench_gemm_ozaki(int32_t M, int32_t N, int32_t K, const doubl
         g.M = M;
         g.N = N;
         g.K = (int)kp;
+        g.k_valid = K;
         g.k_per_split = k_per_split;
         g.splits = splits;
         g.split_stride = splits > 1 ? (int64_t)M * N : 0;

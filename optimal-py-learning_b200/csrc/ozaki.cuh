@@ -21,6 +21,8 @@ struct OzakiArgs {
     double *C;
     int64_t ldc;
     int M, N, K;              // K = padded contraction length (multiple of 128)
+    int k_valid;              // true contraction length (0: K).  The zero padding behind it is not multiplied: the last
+                              // k-block issues only the K = 32 steps that hold data (784 -> 25 instead of 28 steps)
     int k_per_split;          // multiple of 128, <= OZ_MAX_K
     int splits;
     int64_t split_stride;

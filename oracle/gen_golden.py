@@ -270,6 +270,9 @@ def gen_traces(L, store, meta):
         ("tr_mid_bfgs_scaled", "mid", mid_shape, mid_tr, mo.CROSS_ENTROPY, 12,
          lambda L: L.optimize.BFGS(initial_hessian_func=L.optimize.optimizer.initial_hessian_scaled_identity),
          lambda: oo.BFGS(scaled_identity=True), "bfgs_scaled"),
+        # the hard reset of BFGS.next at call `iterations_per_reset` (optimizer.py:236-238), here every 5th call
+        ("tr_mid_bfgs_reset", "mid", mid_shape, mid_tr, mo.CROSS_ENTROPY, 14,
+         lambda L: L.optimize.BFGS(iterations_per_reset=5), lambda: oo.BFGS(reset_every=5), "bfgs_reset5"),
         ("tr_mid_lbfgs", "mid", mid_shape, mid_tr, mo.CROSS_ENTROPY, 50,
          lambda L: L.optimize.LBFGS(), lambda: oo.LBFGS(), "lbfgs"),
         ("tr_iris_lbfgs", "iris", (4, 2, 3), iris_tr, mo.CROSS_ENTROPY, 50,

@@ -482,6 +482,7 @@ def _optimizer_for(L, name):
     return {
         "bfgs": lambda: o.BFGS(),
         "bfgs_scaled": lambda: o.BFGS(initial_hessian_func=o.optimizer.initial_hessian_scaled_identity),
+        "bfgs_reset5": lambda: o.BFGS(iterations_per_reset=5),
         "lbfgs": lambda: o.LBFGS(),
         "sd": lambda: o.SteepestDescent(),
         "sdm": lambda: o.SteepestDescentMomentum(),

@@ -105,6 +105,7 @@ def test_optimizer_traces_match_reference(golden_meta, golden_traces):
     t = golden_traces
     factories = {
         "bfgs": lambda: oo.BFGS(), "bfgs_scaled": lambda: oo.BFGS(scaled_identity=True),
+        "bfgs_reset5": lambda: oo.BFGS(reset_every=5),
         "lbfgs": lambda: oo.LBFGS(), "sd": lambda: oo.SteepestDescent(),
         "sdm": lambda: oo.SteepestDescentMomentum(),
         "sd_backtracking": lambda: oo.SteepestDescent(oo.Backtracking()),

@@ -27,3 +27,25 @@ def get_accuracy(model, input_matrix, target_matrix):
     targets = numpy.asarray(target_matrix)
     hits = numpy.argmax(outputs, axis=-1) == numpy.argmax(targets, axis=-1)
     return float(numpy.mean(hits))
+
+
+def make_train_test_sets(input_matrix, label_matrix, train_per_class):
+    """((training_inputs, training_labels), (testing_inputs, testing_labels)): the first ``train_per_class`` patterns of
+    every distinct label row go to the training set, the rest to the testing set, order preserved
+    (validation.py:342-381; host bookkeeping of the README example, examples/readme_example.py:33-36)."""
+    training_inputs, training_labels, testing_inputs, testing_labels = [], [], [], []
+    label_counts = {}
+    for input_, label in zip(input_matrix, label_matrix):
+        key = tuple(label)
+        count = label_counts.get(key, 0)
+        if count < train_per_class:
+            training_inputs.append(input_)
+            training_labels.append(label)
+        else:
+            testing_inputs.append(input_)
+            testing_labels.append(label)
+        label_counts[key] = count + 1
+    if testing_inputs == []:
+        raise ValueError('train_per_class too high, no testing set')
+    return ((numpy.array(training_inputs), numpy.array(training_labels)),
+            (numpy.array(testing_inputs), numpy.array(testing_labels)))

@@ -270,3 +270,15 @@ def test_scalar_exp_log_rcp_forms_of_the_head(tmp_path):
         if 1e-300 < xi < 1e300:
             assert abs(mpmath.mpf(float(ri)) * xm - 1) <= 3e-16, (xi, ri)
     assert l[list(x).index(1.0)] == 0.0 and l[list(x).index(0.5)] == -math.log(2.0)
+
+
+def test_make_train_test_sets_splits_like_the_reference():
+    """validation.make_train_test_sets (validation.py:342-381): first k patterns of every label to the training set, order kept."""
+    from learning_b200 import validation
+    labels = numpy.eye(3)[[0, 1, 0, 2, 1, 0, 2, 2, 1, 0]]
+    inputs = numpy.arange(10, dtype=float).reshape(10, 1)
+    (tr_x, tr_y), (te_x, te_y) = validation.make_train_test_sets(inputs, labels, train_per_class=2)
+    assert tr_x.ravel().tolist() == [0, 1, 2, 3, 4, 6] and te_x.ravel().tolist() == [5, 7, 8, 9]
+    assert numpy.array_equal(tr_y, labels[[0, 1, 2, 3, 4, 6]]) and numpy.array_equal(te_y, labels[[5, 7, 8, 9]])
+    with pytest.raises(ValueError):
+        validation.make_train_test_sets(inputs, labels, train_per_class=5)

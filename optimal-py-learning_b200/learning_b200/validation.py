@@ -33,19 +33,13 @@ def make_train_test_sets(input_matrix, label_matrix, train_per_class):
     """((training_inputs, training_labels), (testing_inputs, testing_labels)): the first ``train_per_class`` patterns of
     every distinct label row go to the training set, the rest to the testing set, order preserved
     (validation.py:342-381; host bookkeeping of the README example, examples/readme_example.py:33-36)."""
-    training_inputs, training_labels, testing_inputs, testing_labels = [], [], [], []
-    label_counts = {}
-    for input_, label in zip(input_matrix, label_matrix):
-        key = tuple(label)
-        count = label_counts.get(key, 0)
-        if count < train_per_class:
-            training_inputs.append(input_)
-            training_labels.append(label)
-        else:
-            testing_inputs.append(input_)
-            testing_labels.append(label)
-        label_counts[key] = count + 1
-    if testing_inputs == []:
+    inputs, labels = numpy.asarray(input_matrix), numpy.asarray(label_matrix)
+    seen = {}
+    to_train = numpy.zeros(len(labels), dtype=bool)
+    for row, label in enumerate(labels):
+        key = tuple(label.tolist()) if label.ndim else (label.item(),)
+        seen[key] = seen.get(key, 0) + 1
+        to_train[row] = seen[key] <= train_per_class
+    if to_train.all():
         raise ValueError('train_per_class too high, no testing set')
-    return ((numpy.array(training_inputs), numpy.array(training_labels)),
-            (numpy.array(testing_inputs), numpy.array(testing_labels)))
+    return (inputs[to_train], labels[to_train]), (inputs[~to_train], labels[~to_train])

@@ -78,6 +78,9 @@ int opl_mlp_destroy(opl_mlp *ws);
 int64_t opl_mlp_param_count(const opl_mlp *ws);
 /* select OPL_ENGINE_* for the parity mode's large GEMMs (takes effect at the next evaluation) */
 int opl_mlp_set_engine(opl_mlp *ws, int32_t engine);
+/* Re-bind the workspace to another CUDA stream (the caller entered a different stream context).  Work already
+ * enqueued on the old stream is waited for first, so the new stream never races with it. */
+int opl_mlp_set_stream(opl_mlp *ws, void *cuda_stream);
 
 /* Make `rows` patterns resident (copied into the workspace).  `norm_rows` is the N of the
  * reference's 1/N (cross entropy, error.py:115-116) and 1/(N*C) (MSE, error.py:62) scales:
@@ -97,15 +100,17 @@ int opl_mlp_activate_host(opl_mlp *ws, const double *params, const double *x, in
 /* ---- device-pointer calls used by the device-resident optimizer stack ---- */
 /* Evaluate at  x + alpha*dir  (dir_dev may be NULL => at x): the line-search probe
  * `obj_jac_func(parameters + step_size * step_dir)` (linesearch.py:392-399).
- * grad_out_dev has n+1 entries: [ flat gradient ; objective ].  With want_grad == 0 only
- * entry n is written (the _get_obj path used by backtracking, linesearch.py:217).
- * Partial sums only: when the batch is sharded the caller all-reduces the n+1 doubles.
- * Asynchronous. */
+ * grad_out_dev has n+2 entries: [ flat gradient ; objective ; domain flag ].  The flag is 1.0 when
+ * the cross entropy met log(negative) (error.py:89-91), else 0.0; it travels in the vector so that a
+ * sharded evaluation all-reduces it and every rank raises at the same evaluation.  With
+ * want_grad == 0 only entries n and n+1 are written (the _get_obj path used by backtracking,
+ * linesearch.py:217).  Partial sums only: when the batch is sharded the caller all-reduces the
+ * n+2 doubles.  Asynchronous. */
 int opl_mlp_eval_device(opl_mlp *ws, const double *x_dev, double alpha, const double *dir_dev,
                         int32_t want_grad, double *grad_out_dev);
-/* Read back the probe scalars after (optionally all-reducing) grad_out_dev:
+/* Read back the probe scalars after (optionally all-reducing) grad_out_dev (n+2 entries):
  *   host_out[0] = objective, [1] = grad . dir (0 if dir NULL), [2] = ||grad||^2.
- * Synchronises; returns OPL_E_DOMAIN if the evaluation hit log(negative). */
+ * Synchronises; returns OPL_E_DOMAIN if the flag slot grad_dev[n+1] is non-zero. */
 int opl_mlp_probe_scalars(opl_mlp *ws, const double *grad_dev, const double *dir_dev,
                           int32_t have_grad, double *host_out);
 /* activate on device buffers: x_dev rows x d0 -> out_dev rows x d_L */
@@ -177,6 +182,8 @@ int opl_bfgs_create(opl_bfgs **out, int64_t n, int64_t row_begin, int64_t row_en
 int opl_bfgs_destroy(opl_bfgs *b);
 /* BFGS.reset (optimizer.py:223-232): forget H */
 int opl_bfgs_reset(opl_bfgs *b);
+/* re-bind to another stream (see opl_mlp_set_stream) */
+int opl_bfgs_set_stream(opl_bfgs *b, void *cuda_stream);
 
 /* One call of BFGS._get_approx_inv_hessian + `-(H.dot(jac))` (optimizer.py:242-285), single
  * device.  prev_step_dev == NULL => first iteration (dir = -grad, identity never formed).
@@ -226,6 +233,13 @@ int opl_lbfgs_reset(opl_lbfgs *l);
 int opl_lbfgs_direction_device(opl_lbfgs *l, const double *grad_dev, const double *prev_step_dev,
                                const double *prev_grad_dev, int32_t gamma_mode, double *dir_out_dev);
 int32_t opl_lbfgs_history_len(const opl_lbfgs *l);
+/* re-bind to another stream (see opl_mlp_set_stream) */
+int opl_lbfgs_set_stream(opl_lbfgs *l, void *cuda_stream);
+/* Checkpoint / teacher forcing: the reference pickles `_prev_param_diffs` / `_prev_jac_diffs`
+ * (optimizer.py:397-399).  push appends one (s, y) pair as the NEWEST entry (copied; the oldest is dropped first when
+ * the history is full, as _update_diffs does); get copies pair `index` (0 = oldest) out. */
+int opl_lbfgs_push_pair_device(opl_lbfgs *l, const double *s_dev, const double *y_dev);
+int opl_lbfgs_get_pair_device(const opl_lbfgs *l, int32_t index, double *s_out_dev, double *y_out_dev);
 int64_t opl_lbfgs_launch_count(const opl_lbfgs *l);
 
 /* =====================================================================================
@@ -247,6 +261,11 @@ int opl_vec_penalty_device(int64_t n, const double *w, int32_t kind, double lamb
                            double *host_out, void *cuda_stream);
 /* host_out[0] = x . y   (deterministic two-stage reduction; synchronises) */
 int opl_vec_dot_device(int64_t n, const double *x, const double *y, double *host_out, void *cuda_stream);
+/* dst[i][:] = src[index[i]][:] for i < count: the mini-batch selection of Model.stochastic_train /
+ * select_sample (base.py:39-50,100-135) on a device-resident dataset.  src: rows x cols row-major,
+ * index_dev: count int64 row numbers in [0, rows), dst: count x cols.  Asynchronous. */
+int opl_gather_rows_device(const double *src_dev, int64_t rows, int64_t cols, const int64_t *index_dev, int64_t count,
+                           double *dst_dev, void *cuda_stream);
 
 /* =====================================================================================
  * RBF network front end.  The RBF output layer is an opl_mlp of shape

@@ -470,6 +470,15 @@ int opl_bfgs_reset(opl_bfgs *b) {
     return OPL_OK;
 }
 
+int opl_bfgs_set_stream(opl_bfgs *b, void *cuda_stream) {
+    if (!b) return fail(OPL_E_ARG, "opl_bfgs_set_stream: null");
+    if (b->stream != (cudaStream_t)cuda_stream) {
+        OPL_CUDA(cudaStreamSynchronize(b->stream));
+        b->stream = (cudaStream_t)cuda_stream;
+    }
+    return OPL_OK;
+}
+
 int opl_bfgs_state(const opl_bfgs *b) { return b ? b->state : -1; }
 int64_t opl_bfgs_launch_count(const opl_bfgs *b) { return b ? b->launches : -1; }
 

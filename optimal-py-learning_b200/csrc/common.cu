@@ -20,17 +20,24 @@ int fail(int code, const char *fmt, ...) {
     return code;
 }
 
+int current_device_slot() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+    return dev & 63;
+}
+
 int sm_count() {
-    static int cached = 0;
-    if (cached == 0) {
+    static int cached[64] = {};
+    int &slot = cached[current_device_slot()];
+    if (slot == 0) {
         int dev = 0, n = 0;
         if (cudaGetDevice(&dev) == cudaSuccess &&
             cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-            cached = n;
+            slot = n;
         else
-            cached = 148;
+            slot = 148;
     }
-    return cached;
+    return slot;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -98,6 +105,17 @@ __global__ void penalty_apply_kernel(int64_t n, const double *__restrict__ w, in
     }
 }
 
+// dst[i][:] = src[index[i]][:]: one warp per 32-column segment of a row, rows strided over the grid
+__global__ void gather_rows_kernel(const double *__restrict__ src, int64_t rows, int64_t cols, const int64_t *__restrict__ index,
+                                   int64_t count, double *__restrict__ dst) {
+    const int64_t total = count * cols;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / cols, c = i - r * cols;
+        const int64_t from = index[r];
+        dst[i] = (from >= 0 && from < rows) ? src[from * cols + c] : __longlong_as_double(0x7ff8000000000000LL);
+    }
+}
+
 static int vec_grid(int64_t n, int threads) {
     int64_t g = ceil_div(n, threads);
     int64_t cap = 4 * (int64_t)sm_count();
@@ -130,6 +148,16 @@ int opl_vec_axpy_device(int64_t n, const double *x, double a, const double *d, d
     if (n < 0 || (n > 0 && (!x || !d || !out))) return fail(OPL_E_ARG, "opl_vec_axpy_device: null pointer");
     if (n == 0) return OPL_OK;
     axpy_kernel<<<vec_grid(n, 256), 256, 0, (cudaStream_t)cuda_stream>>>(n, x, a, d, b, p, out);
+    OPL_LAUNCH_CHECK();
+    return OPL_OK;
+}
+
+int opl_gather_rows_device(const double *src_dev, int64_t rows, int64_t cols, const int64_t *index_dev, int64_t count,
+                           double *dst_dev, void *cuda_stream) {
+    if (rows < 1 || cols < 1 || count < 0 || !src_dev || (count > 0 && (!index_dev || !dst_dev)))
+        return fail(OPL_E_ARG, "opl_gather_rows_device: bad arguments");
+    if (count == 0) return OPL_OK;
+    gather_rows_kernel<<<vec_grid(count * cols, 256), 256, 0, (cudaStream_t)cuda_stream>>>(src_dev, rows, cols, index_dev, count, dst_dev);
     OPL_LAUNCH_CHECK();
     return OPL_OK;
 }

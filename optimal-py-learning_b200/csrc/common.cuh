@@ -32,6 +32,7 @@ int fail(int code, const char *fmt, ...);
 constexpr double kBig = 1.7976931348623157e308;   // numpy.nan_to_num's finite stand-in for inf
 
 int sm_count();   // multiprocessors of the current device (cached)
+int current_device_slot();   // cudaGetDevice() clamped to [0, 64): index of per-device one-time setup flags
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -105,7 +105,8 @@ int launch_one(const GemmArgs &a, int splits, cudaStream_t stream) {
     constexpr int SMEM = STAGES * (A_TILE + B_TILE) * (int)sizeof(double);
     constexpr int NTHREADS = (BM / WM) * (BN / WN) * 32;
     auto kern = gemm_f64_kernel<LAYOUT, BM, BN, WM, WN, VEC, STAGES, MINBLOCKS>;
-    static bool configured = false;
+    static bool configured_dev[64] = {};     // cudaFuncSetAttribute is per device
+    bool &configured = configured_dev[current_device_slot()];
     if (!configured) {
         OPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         configured = true;

@@ -438,7 +438,8 @@ namespace {
 template <bool A_MN, bool B_MN, int BN>
 int launch_tf32(const CUtensorMap &ta, const CUtensorMap &tb, const Tf32GemmArgs &a, int splits, cudaStream_t stream) {
     auto kern = gemm_tf32_kernel<A_MN, B_MN, BN>;
-    static bool configured = false;
+    static bool configured_dev[64] = {};     // cudaFuncSetAttribute is per device
+    bool &configured = configured_dev[current_device_slot()];
     if (!configured) {
         OPL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Tf32Smem<BN>::BYTES));
         configured = true;

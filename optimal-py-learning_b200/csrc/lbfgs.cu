@@ -224,6 +224,42 @@ int opl_lbfgs_reset(opl_lbfgs *l) {
     return OPL_OK;
 }
 
+int opl_lbfgs_set_stream(opl_lbfgs *l, void *cuda_stream) {
+    if (!l) return fail(OPL_E_ARG, "opl_lbfgs_set_stream: null");
+    if (l->stream != (cudaStream_t)cuda_stream) {
+        OPL_CUDA(cudaStreamSynchronize(l->stream));
+        l->stream = (cudaStream_t)cuda_stream;
+    }
+    return OPL_OK;
+}
+
+int opl_lbfgs_push_pair_device(opl_lbfgs *l, const double *s_dev, const double *y_dev) {
+    if (!l || !s_dev || !y_dev) return fail(OPL_E_ARG, "opl_lbfgs_push_pair_device: null pointer");
+    if (l->memory > 0 && (int)l->s_hist.size() >= l->memory) {
+        l->spare.push_back(l->s_hist.front());
+        l->spare.push_back(l->y_hist.front());
+        l->s_hist.erase(l->s_hist.begin());
+        l->y_hist.erase(l->y_hist.begin());
+    }
+    double *s = nullptr, *y = nullptr;
+    int rc = grab(l, &s);
+    if (rc == OPL_OK) rc = grab(l, &y);
+    if (rc != OPL_OK) return rc;
+    OPL_CUDA(cudaMemcpyAsync(s, s_dev, sizeof(double) * (size_t)l->n, cudaMemcpyDeviceToDevice, l->stream));
+    OPL_CUDA(cudaMemcpyAsync(y, y_dev, sizeof(double) * (size_t)l->n, cudaMemcpyDeviceToDevice, l->stream));
+    l->s_hist.push_back(s);
+    l->y_hist.push_back(y);
+    return OPL_OK;
+}
+
+int opl_lbfgs_get_pair_device(const opl_lbfgs *l, int32_t index, double *s_out_dev, double *y_out_dev) {
+    if (!l || !s_out_dev || !y_out_dev) return fail(OPL_E_ARG, "opl_lbfgs_get_pair_device: null pointer");
+    if (index < 0 || index >= (int32_t)l->s_hist.size()) return fail(OPL_E_ARG, "opl_lbfgs_get_pair_device: index %d outside the history", index);
+    OPL_CUDA(cudaMemcpyAsync(s_out_dev, l->s_hist[index], sizeof(double) * (size_t)l->n, cudaMemcpyDeviceToDevice, l->stream));
+    OPL_CUDA(cudaMemcpyAsync(y_out_dev, l->y_hist[index], sizeof(double) * (size_t)l->n, cudaMemcpyDeviceToDevice, l->stream));
+    return OPL_OK;
+}
+
 int32_t opl_lbfgs_history_len(const opl_lbfgs *l) { return l ? (int32_t)l->s_hist.size() : -1; }
 int64_t opl_lbfgs_launch_count(const opl_lbfgs *l) { return l ? l->launches : -1; }
 

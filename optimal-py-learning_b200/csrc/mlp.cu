@@ -618,14 +618,19 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, R == 16 ? 2 : 1) narrow_head_
     if (threadIdx.x == 0) p.loss_partial[blockIdx.x] = loss;
 }
 
-// obj = -(sum/N) for cross entropy, sum/(N*C) for MSE
+// obj = -(sum/N) for cross entropy, sum/(N*C) for MSE.  out[1] (when `flag` is given) = 1.0 if the row stage met
+// log(negative), else 0.0: the domain flag travels in the evaluation vector, so that a batch-sharded evaluation all-reduces it
+// with the gradient and every rank raises FloatingPointError (error.py:89-91) at the same evaluation.
 __global__ void loss_final_kernel(const double *partial, int nparts, int eid, double n_rows, double n_cols,
-                                  double *out) {
+                                  double *out, const int *flag) {
     __shared__ double scratch[33];
     double s = 0.0;
     for (int i = threadIdx.x; i < nparts; i += blockDim.x) s += partial[i];
     s = block_sum(s, scratch);
-    if (threadIdx.x == 0) out[0] = eid == OPL_ERROR_MSE ? s / (n_rows * n_cols) : -(s / n_rows);
+    if (threadIdx.x == 0) {
+        out[0] = eid == OPL_ERROR_MSE ? s / (n_rows * n_cols) : -(s / n_rows);
+        if (flag) out[1] = *flag ? 1.0 : 0.0;
+    }
 }
 
 // column sums of a rows x cols matrix, stage 1: partial[blockIdx.y][col]
@@ -681,7 +686,7 @@ __global__ void probe_partial_kernel(int64_t n, const double *__restrict__ g, co
     }
 }
 __global__ void probe_final_kernel(int nparts, const double *__restrict__ partial, const double *obj,
-                                   double *__restrict__ out) {
+                                   double *__restrict__ out) {   // obj[0] = objective, obj[1] = domain flag (summed over ranks)
     __shared__ double scratch[33];
     double gd = 0.0, gg = 0.0;
     for (int i = threadIdx.x; i < nparts; i += blockDim.x) {
@@ -694,6 +699,7 @@ __global__ void probe_final_kernel(int nparts, const double *__restrict__ partia
         out[0] = obj[0];
         out[1] = gd;
         out[2] = gg;
+        out[3] = obj[1];
     }
 }
 
@@ -741,8 +747,8 @@ struct opl_mlp {
     std::vector<double *> deriv;    // D_l or null
     std::vector<double *> delta;    // delta_l (aliases deriv[l] when that exists)
     double *out_act = nullptr;      // A_L
-    double *w_trial = nullptr;      // n + 1
-    double *host_grad = nullptr;    // device staging for *_host calls, n + 1
+    double *w_trial = nullptr;      // n + 2
+    double *host_grad = nullptr;    // device staging for *_host calls, n + 2
     double *partials = nullptr;
     int64_t partials_len = 0;
     double *loss_partial = nullptr;
@@ -938,7 +944,7 @@ int output_stage(opl_mlp *ws, const double *y, int64_t rows, bool want_act, bool
     if (y && obj_out) {
         mark(ws, STAGE_LOSS * 100);
         loss_final_kernel<<<1, 256, 0, ws->stream>>>(ws->loss_partial, grid, ws->error_id, (double)ws->norm_rows,
-                                                      (double)r.C, obj_out);
+                                                      (double)r.C, obj_out, ws->flag);
         OPL_LAUNCH_CHECK();
         ++ws->launches;
     }
@@ -1114,7 +1120,8 @@ int fused_head(opl_mlp *ws, const double *w, const double *y, int64_t rows, bool
         a.dw_partial = ws->partials;
         a.colmax = int8_arm_delta_max(ws, L - 2, rows);
     }
-    static bool configured = false;
+    static bool configured_dev[64] = {};     // cudaFuncSetAttribute is per device
+    bool &configured = configured_dev[current_device_slot()];
     if (!configured) {
         OPL_CUDA(cudaFuncSetAttribute(narrow_head_kernel<double, 2, 32, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_smem(256, 32)));
         OPL_CUDA(cudaFuncSetAttribute(narrow_head_kernel<double, 4, 16, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_smem(256, 16)));
@@ -1148,7 +1155,7 @@ int fused_head(opl_mlp *ws, const double *w, const double *y, int64_t rows, bool
     }
     ++ws->launches;
     mark(ws, STAGE_LOSS * 100);
-    loss_final_kernel<<<1, 256, 0, ws->stream>>>(ws->loss_partial, grid, ws->error_id, (double)ws->norm_rows, (double)C, obj_out);
+    loss_final_kernel<<<1, 256, 0, ws->stream>>>(ws->loss_partial, grid, ws->error_id, (double)ws->norm_rows, (double)C, obj_out, ws->flag);
     OPL_LAUNCH_CHECK();
     ++ws->launches;
     if (want_grad) {
@@ -1218,16 +1225,17 @@ int read_scalars(opl_mlp *ws, const double *grad_dev, const double *dir_dev, boo
         probe_final_kernel<<<1, 256, 0, ws->stream>>>(grid, ws->probe_partial, grad_dev + n, ws->scal);
         OPL_LAUNCH_CHECK();
         ws->launches += 2;
-        OPL_CUDA(cudaMemcpyAsync(ws->pinned, ws->scal, 3 * sizeof(double), cudaMemcpyDeviceToHost, ws->stream));
+        OPL_CUDA(cudaMemcpyAsync(ws->pinned, ws->scal, 4 * sizeof(double), cudaMemcpyDeviceToHost, ws->stream));
     } else {
         OPL_CUDA(cudaMemcpyAsync(ws->pinned, grad_dev + n, sizeof(double), cudaMemcpyDeviceToHost, ws->stream));
+        OPL_CUDA(cudaMemcpyAsync(ws->pinned + 3, grad_dev + n + 1, sizeof(double), cudaMemcpyDeviceToHost, ws->stream));
     }
-    OPL_CUDA(cudaMemcpyAsync(ws->pinned + 4, ws->flag, sizeof(int), cudaMemcpyDeviceToHost, ws->stream));
     OPL_CUDA(cudaStreamSynchronize(ws->stream));
     host_out[0] = ws->pinned[0];
     host_out[1] = have_grad ? ws->pinned[1] : 0.0;
     host_out[2] = have_grad ? ws->pinned[2] : 0.0;
-    if (*reinterpret_cast<int *>(ws->pinned + 4) != 0)
+    // the flag slot is a sum over ranks of 0/1 values when the batch is sharded: every rank sees the same value
+    if (ws->pinned[3] != 0.0)
         return fail(OPL_E_DOMAIN, "invalid value encountered in log (negative prediction in cross entropy)");
     return OPL_OK;
 }
@@ -1324,8 +1332,8 @@ int opl_mlp_create(opl_mlp **out, int32_t n_widths, const int64_t *widths, const
     ws->partials_len = partials;
     OPL_TRY(cudaMalloc(&ws->partials, sizeof(double) * (size_t)partials));
     OPL_TRY(cudaMalloc(&ws->out_act, sizeof(double) * (size_t)max_rows * (size_t)widths[L]));
-    OPL_TRY(cudaMalloc(&ws->w_trial, sizeof(double) * (size_t)(ws->n + 1)));
-    OPL_TRY(cudaMalloc(&ws->host_grad, sizeof(double) * (size_t)(ws->n + 1)));
+    OPL_TRY(cudaMalloc(&ws->w_trial, sizeof(double) * (size_t)(ws->n + 2)));
+    OPL_TRY(cudaMalloc(&ws->host_grad, sizeof(double) * (size_t)(ws->n + 2)));
     ws->loss_blocks = 8 * sm_count();
     OPL_TRY(cudaMalloc(&ws->loss_partial, sizeof(double) * (size_t)ws->loss_blocks));
     ws->probe_blocks = 2 * sm_count();
@@ -1359,6 +1367,15 @@ int opl_mlp_set_engine(opl_mlp *ws, int32_t engine) {
     if (!ws || (engine != OPL_ENGINE_DMMA && engine != OPL_ENGINE_INT8)) return fail(OPL_E_ARG, "opl_mlp_set_engine: bad arguments");
     ws->gemm_engine = engine;
     ws->fused_head = engine == OPL_ENGINE_INT8;   // OPL_ENGINE_DMMA = the plain schedule: one kernel per reference operation
+    return OPL_OK;
+}
+
+int opl_mlp_set_stream(opl_mlp *ws, void *cuda_stream) {
+    if (!ws) return fail(OPL_E_ARG, "opl_mlp_set_stream: null");
+    if (ws->stream != (cudaStream_t)cuda_stream) {
+        OPL_CUDA(cudaStreamSynchronize(ws->stream));
+        ws->stream = (cudaStream_t)cuda_stream;
+    }
     return OPL_OK;
 }
 
@@ -1588,7 +1605,7 @@ int rows_call(int tid, double tparam, int eid, const double *z_host, const doubl
     const int grid = launch_rows(r, max_grid, nullptr);
     OPL_LAUNCH_CHECK();
     if (loss_out) {
-        loss_final_kernel<<<1, 256>>>(lp, grid, eid, (double)rows, (double)cols, res);
+        loss_final_kernel<<<1, 256>>>(lp, grid, eid, (double)rows, (double)cols, res, nullptr);
         OPL_LAUNCH_CHECK();
         OPL_CUDA(cudaMemcpy(loss_out, res, sizeof(double), cudaMemcpyDeviceToHost));
     }

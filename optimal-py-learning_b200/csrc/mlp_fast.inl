@@ -278,7 +278,7 @@ int fast_output(opl_mlp *ws, const double *y, int64_t rows, bool want_act, bool 
     if (y && obj_out) {
         mark(ws, STAGE_LOSS * 100);
         loss_final_kernel<<<1, 256, 0, ws->stream>>>(ws->loss_partial, grid, ws->error_id, (double)ws->norm_rows,
-                                                      (double)r.C, obj_out);
+                                                      (double)r.C, obj_out, ws->flag);
         OPL_LAUNCH_CHECK();
         ++ws->launches;
     }
@@ -695,7 +695,8 @@ int fast_fused_head(opl_mlp *ws, bool want_grad, double *grad, double *obj_out) 
         a.dw_partial = ws->partials;
         a.colsum_partial = bias_here ? ws->partials + (size_t)grid * H * C : nullptr;
     }
-    static bool configured = false;
+    static bool configured_dev[64] = {};     // cudaFuncSetAttribute is per device
+    bool &configured = configured_dev[current_device_slot()];
     if (!configured) {
         OPL_CUDA(cudaFuncSetAttribute(narrow_head_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)fast_head_smem(256)));
@@ -706,7 +707,7 @@ int fast_fused_head(opl_mlp *ws, bool want_grad, double *grad, double *obj_out) 
     OPL_LAUNCH_CHECK();
     ++ws->launches;
     mark(ws, STAGE_LOSS * 100);
-    loss_final_kernel<<<1, 256, 0, ws->stream>>>(ws->loss_partial, grid, ws->error_id, (double)ws->norm_rows, (double)C, obj_out);
+    loss_final_kernel<<<1, 256, 0, ws->stream>>>(ws->loss_partial, grid, ws->error_id, (double)ws->norm_rows, (double)C, obj_out, ws->flag);
     OPL_LAUNCH_CHECK();
     ++ws->launches;
     if (want_grad) {

@@ -936,7 +936,8 @@ int launch_ozaki_gemm(const int8_t *a_slices, int64_t a_rows_pad, const int8_t *
         {ozaki_gemm_kernel<OZ_EPI_MUL_DTANH, 1>, ozaki_gemm_kernel<OZ_EPI_MUL_DTANH, 2>, ozaki_gemm_kernel<OZ_EPI_MUL_DTANH, 4>}};
     if (args.epi < 0 || args.epi > 5) return fail(OPL_E_ARG, "ozaki GEMM: unknown epilogue %d", args.epi);
     if (args.epi >= OZ_EPI_MUL_AUX && !args.aux_in) return fail(OPL_E_ARG, "ozaki GEMM: epilogue %d needs aux_in", args.epi);
-    static bool configured = false;
+    static bool configured_dev[64] = {};     // cudaFuncSetAttribute is per device
+    bool &configured = configured_dev[current_device_slot()];
     if (!configured) {
         for (int e = 0; e < 6; ++e)
             for (int c = 0; c < 3; ++c)

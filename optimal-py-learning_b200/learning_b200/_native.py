@@ -1,8 +1,9 @@
 """ctypes binding of the C-ABI library ``libopl_b200.so`` (``include/opl_b200.h``).
 
 This is the ONLY compute backend of the package: there is no NumPy / CPU fallback.  If the
-shared library is missing it is built in-tree with nvcc; if that is impossible the import
-fails loudly, and without a CUDA device every compute entry point raises ``RuntimeError``.
+shared library is missing or older than its sources it is (re)built in-tree with nvcc; if that is
+impossible the import fails loudly, and without a CUDA device every compute entry point raises
+``RuntimeError``.
 """
 import ctypes
 import os
@@ -28,6 +29,7 @@ SIGNATURES = {
     "opl_mlp_destroy": (ctypes.c_int, [vp]),
     "opl_mlp_param_count": (i64, [vp]),
     "opl_mlp_set_engine": (ctypes.c_int, [vp, i32]),
+    "opl_mlp_set_stream": (ctypes.c_int, [vp, vp]),
     "opl_mlp_set_data_host": (ctypes.c_int, [vp, vp, vp, i64, i64]),
     "opl_mlp_set_data_device": (ctypes.c_int, [vp, vp, vp, i64, i64]),
     "opl_mlp_obj_host": (ctypes.c_int, [vp, vp, c_double_p]),
@@ -50,6 +52,7 @@ SIGNATURES = {
     "opl_bfgs_create": (ctypes.c_int, [ctypes.POINTER(vp), i64, i64, i64, vp]),
     "opl_bfgs_destroy": (ctypes.c_int, [vp]),
     "opl_bfgs_reset": (ctypes.c_int, [vp]),
+    "opl_bfgs_set_stream": (ctypes.c_int, [vp, vp]),
     "opl_bfgs_direction_device": (ctypes.c_int, [vp, vp, vp, vp, i32, vp]),
     "opl_bfgs_pass_device": (ctypes.c_int, [vp, vp, vp, vp, i32, vp, vp, vp]),
     "opl_bfgs_finish_device": (ctypes.c_int, [vp, vp, vp, vp, i32, vp, vp, vp, vp]),
@@ -63,11 +66,15 @@ SIGNATURES = {
     "opl_lbfgs_reset": (ctypes.c_int, [vp]),
     "opl_lbfgs_direction_device": (ctypes.c_int, [vp, vp, vp, vp, i32, vp]),
     "opl_lbfgs_history_len": (i32, [vp]),
+    "opl_lbfgs_set_stream": (ctypes.c_int, [vp, vp]),
+    "opl_lbfgs_push_pair_device": (ctypes.c_int, [vp, vp, vp]),
+    "opl_lbfgs_get_pair_device": (ctypes.c_int, [vp, i32, vp, vp]),
     "opl_lbfgs_launch_count": (i64, [vp]),
     "opl_vec_axpy_device": (ctypes.c_int, [i64, vp, f64, vp, f64, vp, vp, vp]),
     "opl_vec_scale_device": (ctypes.c_int, [i64, f64, vp, vp, vp]),
     "opl_vec_penalty_device": (ctypes.c_int, [i64, vp, i32, f64, vp, c_double_p, vp]),
     "opl_vec_dot_device": (ctypes.c_int, [i64, vp, vp, c_double_p, vp]),
+    "opl_gather_rows_device": (ctypes.c_int, [vp, i64, i64, vp, i64, vp, vp]),
     "opl_rbf_similarity_device": (ctypes.c_int, [vp, i64, i32, vp, i32, i32, f64, vp, vp]),
     "opl_som_train_device": (ctypes.c_int, [vp, i64, i32, vp, i32, i64, vp, i32, vp]),
     "opl_allreduce_sum_device": (ctypes.c_int, [i32, i32, ctypes.POINTER(u64), ctypes.POINTER(u64), i64, ctypes.c_uint32, vp, vp]),
@@ -76,17 +83,19 @@ SIGNATURES = {
 
 
 def _load():
-    if not os.path.exists(LIB_PATH):
-        sys.path.insert(0, _PKG_ROOT)
-        try:
-            import build as _build  # optimal-py-learning_b200/build.py
-            _build.build()
-        except Exception as exc:  # no nvcc / compile error: fail loudly, never fall back
+    # build.build() compares a digest of csrc/ + the header with the stamp of the last build and recompiles when they
+    # differ, so a stale binary is never loaded silently after a source edit (a matching stamp costs a few ms)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_opl_b200_build", os.path.join(_PKG_ROOT, "build.py"))
+    try:
+        builder = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(builder)
+        builder.build()
+    except Exception as exc:  # no nvcc / compile error: fail loudly, never fall back
+        if not os.path.exists(LIB_PATH) or os.environ.get("OPL_ALLOW_STALE_LIB") != "1":
             raise ImportError(
-                "learning_b200: CUDA library %s is missing and could not be built (%s). "
+                "learning_b200: CUDA library %s is missing or out of date and could not be built (%s). "
                 "There is no CPU fallback." % (LIB_PATH, exc))
-        finally:
-            sys.path.pop(0)
     lib = ctypes.CDLL(LIB_PATH)
     for name, (restype, argtypes) in SIGNATURES.items():
         fn = getattr(lib, name)   # AttributeError here = header / library mismatch

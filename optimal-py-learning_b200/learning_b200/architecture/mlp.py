@@ -61,8 +61,17 @@ class _Workspace(object):
                                          int(max_rows), int(precision), dev.stream_ptr()))
         self.pointer = out
         self.max_rows = int(max_rows)
-        self.resident = None      # fingerprint of the (X, Y) resident on the device
+        self.stream = torch.cuda.current_stream().cuda_stream
+        self.resident = None      # identity of the (X, Y) resident on the device (see _make_resident)
         self.keepalive = None     # device tensors borrowed by the workspace
+        self.sharded = False
+
+    def bind_current_stream(self):
+        """Kernels are enqueued on the caller's CURRENT stream: re-bind when it changed since the last call."""
+        stream = torch.cuda.current_stream().cuda_stream
+        if stream != self.stream:
+            nat.check(nat.lib.opl_mlp_set_stream(self.pointer, ctypes.c_void_p(stream)))
+            self.stream = stream
 
     def __del__(self):
         try:
@@ -73,14 +82,17 @@ class _Workspace(object):
             pass
 
 
-def _fingerprint(x, y):
-    """Cheap identity of a host dataset: object ids, buffers, shapes and a few sampled values."""
-    def sample(a):
-        flat = a.reshape(-1)
-        step = max(1, (flat.shape[0] - 1) // 15)
-        return tuple(flat[::step][:16].tolist()) + (float(flat[-1]),)
-    return (id(x), id(y), x.__array_interface__['data'][0], y.__array_interface__['data'][0],
-            x.shape, y.shape, sample(x), sample(y))
+class _Residency(object):
+    """What a workspace holds: the very objects that were uploaded (strong references, compared with ``is`` -- an
+    ``id()`` can be recycled by a new mini-batch, a reference cannot) and, for device tensors, their version counters."""
+
+    def __init__(self, x, y, first, count):
+        self.x, self.y, self.first, self.count = x, y, first, count
+        self.versions = (getattr(x, '_version', None), getattr(y, '_version', None))
+
+    def holds(self, x, y, first, count):
+        return (self.x is x and self.y is y and self.first == first and self.count == count
+                and self.versions == (getattr(x, '_version', None), getattr(y, '_version', None)))
 
 
 class _KernelModel(Model):
@@ -100,6 +112,7 @@ class _KernelModel(Model):
             raise ValueError("precision must be 'f64', 'f64-dmma' or 'tf32', got %r" % (precision,))
         self._precision = precision
         self._workspace = None
+        self._residency_scope = None     # (X, Y) of the enclosing train() / train_step() / resident() scope
         self._last_grad_norm = None
         self.obj_jac_evaluations = 0     # probe counter (bench / diagnostics)
 
@@ -115,6 +128,7 @@ class _KernelModel(Model):
             if self._precision == 'f64-dmma':
                 nat.check(nat.lib.opl_mlp_set_engine(ws.pointer, 0))
             self._workspace = ws
+        ws.bind_current_stream()
         return ws
 
     def _shard(self, rows):
@@ -128,25 +142,37 @@ class _KernelModel(Model):
         return 0, rows, False
 
     def _make_resident(self, input_matrix, target_matrix):
-        """Upload (this rank's shard of) the dataset once; later calls with the same arrays are free."""
+        """Make (this rank's shard of) the dataset resident in the workspace.
+
+        Residency is explicit, never guessed from the contents (the reference always reads the arrays it is given):
+
+          * host arrays are uploaded on every call, EXCEPT inside a residency scope -- ``train()`` (between the
+            ``_pre_train`` and ``_post_train`` hooks, base.py:166-182), one ``train_step`` or ``with model.resident(X, Y)``
+            -- where the scope's own two objects (compared with ``is``) were uploaded when the scope was entered.
+            An in-place edit of X between two scopes is therefore always seen;
+          * device tensors are borrowed, keyed on the tensor objects and their ``_version`` counters: an in-place edit bumps
+            the version and the digits of X are cut again.
+        """
         if dev.is_device_vector(input_matrix):
             x, y = input_matrix, target_matrix
             if x.dim() != 2 or y.dim() != 2 or x.shape[0] != y.shape[0]:
                 raise ValueError('input_matrix and target_matrix must be matrices with equal row counts')
-            key = ('device', x.data_ptr(), y.data_ptr(), tuple(x.shape), tuple(y.shape))
             ws = self._workspace_for(x.shape[0])
-            if ws.resident != key:
+            if ws.resident is None or not ws.resident.holds(x, y, 0, x.shape[0]):
                 self._check_widths(x.shape[-1], y.shape[-1])
-                x = x.to(torch.float64).contiguous()
-                y = y.to(torch.float64).contiguous()
-                nat.check(nat.lib.opl_mlp_set_data_device(ws.pointer, dev.ptr(x), dev.ptr(y), x.shape[0],
-                                                          self._global_rows(x.shape[0])))
-                ws.keepalive = (x, y)
-                ws.resident = key
+                token = _Residency(x, y, 0, x.shape[0])
+                xc = x.to(torch.float64).contiguous()
+                yc = y.to(torch.float64).contiguous()
+                nat.check(nat.lib.opl_mlp_set_data_device(ws.pointer, dev.ptr(xc), dev.ptr(yc), xc.shape[0],
+                                                          self._global_rows(xc.shape[0])))
+                ws.keepalive = (xc, yc)
+                ws.resident = token
                 ws.sharded = self._world_size() > 1
             return ws
-        x = numpy.asarray(input_matrix, dtype=numpy.float64)
-        y = numpy.asarray(target_matrix, dtype=numpy.float64)
+        x = input_matrix if (isinstance(input_matrix, numpy.ndarray) and input_matrix.dtype == numpy.float64) \
+            else numpy.asarray(input_matrix, dtype=numpy.float64)
+        y = target_matrix if (isinstance(target_matrix, numpy.ndarray) and target_matrix.dtype == numpy.float64) \
+            else numpy.asarray(target_matrix, dtype=numpy.float64)
         if x.ndim != 2 or y.ndim != 2:
             raise ValueError('the gradient path needs matrices (patterns in rows), got shapes %s and %s'
                              % (x.shape, y.shape))
@@ -155,16 +181,84 @@ class _KernelModel(Model):
         self._check_widths(x.shape[-1], y.shape[-1])
         first, count, sharded = self._shard(x.shape[0])
         ws = self._workspace_for(count)
-        key = _fingerprint(x, y) + (first, count)
-        if ws.resident != key:
-            xs = numpy.ascontiguousarray(x[first:first + count])
-            ys = numpy.ascontiguousarray(y[first:first + count])
-            nat.check(nat.lib.opl_mlp_set_data_host(ws.pointer, xs.ctypes.data_as(ctypes.c_void_p),
-                                                    ys.ctypes.data_as(ctypes.c_void_p), count, x.shape[0]))
-            ws.resident = key
-            ws.keepalive = None
-            ws.sharded = sharded
+        scope = self._residency_scope
+        in_scope = scope is not None and scope[0] is input_matrix and scope[1] is target_matrix
+        if in_scope and ws.resident is not None and ws.resident.holds(input_matrix, target_matrix, first, count):
+            return ws
+        xs = numpy.ascontiguousarray(x[first:first + count])
+        ys = numpy.ascontiguousarray(y[first:first + count])
+        nat.check(nat.lib.opl_mlp_set_data_host(ws.pointer, xs.ctypes.data_as(ctypes.c_void_p),
+                                                ys.ctypes.data_as(ctypes.c_void_p), count, x.shape[0]))
+        ws.resident = _Residency(input_matrix, target_matrix, first, count) if in_scope else None
+        ws.keepalive = None
+        ws.sharded = sharded
         return ws
+
+    def _select_patterns(self, pattern_selection_func, input_matrix, target_matrix):
+        """Mini-batch of Model.stochastic_train (base.py:39-50,100-135) selected ON THE DEVICE: the whole dataset is
+        uploaded once per stochastic_train call, the row numbers are drawn on the host with the reference's ``random``
+        calls (same order, so seeded runs select the same rows) and ``opl_gather_rows_device`` copies the rows; a
+        mini-batch never crosses PCIe.  Other selection functions run on the host as in the reference."""
+        from ..base import ROW_SELECTORS
+        rows_of = ROW_SELECTORS.get(pattern_selection_func)
+        if (rows_of is None and isinstance(pattern_selection_func, functools.partial)
+                and not pattern_selection_func.args and pattern_selection_func.func in ROW_SELECTORS):
+            rows_of = functools.partial(ROW_SELECTORS[pattern_selection_func.func], **pattern_selection_func.keywords)
+        if rows_of is None or dev.is_device_vector(input_matrix) or self._world_size() > 1:
+            return pattern_selection_func(input_matrix, target_matrix)
+        full = getattr(self, '_stochastic_full', None)
+        if full is None or full[0] is not input_matrix or full[1] is not target_matrix:
+            x = numpy.ascontiguousarray(input_matrix, dtype=numpy.float64)
+            y = numpy.ascontiguousarray(target_matrix, dtype=numpy.float64)
+            if x.ndim != 2 or y.ndim != 2 or x.shape[0] != y.shape[0]:
+                return pattern_selection_func(input_matrix, target_matrix)
+            full = (input_matrix, target_matrix, dev.to_device(x), dev.to_device(y))
+            self._stochastic_full = full
+        xd, yd = full[2], full[3]
+        rows = rows_of(xd.shape[0])
+        index = torch.tensor(rows, dtype=torch.int64).cuda()
+        xb = torch.empty((len(rows), xd.shape[1]), dtype=torch.float64, device=xd.device)
+        yb = torch.empty((len(rows), yd.shape[1]), dtype=torch.float64, device=yd.device)
+        for src, dst in ((xd, xb), (yd, yb)):
+            nat.check(nat.lib.opl_gather_rows_device(dev.ptr(src), src.shape[0], src.shape[1], dev.ptr(index), len(rows),
+                                                     dev.ptr(dst), dev.stream_ptr()))
+        return xb, yb
+
+    def stochastic_train(self, input_matrix, target_matrix, *args, **kwargs):
+        """Model.stochastic_train (base.py:100-135) with the dataset resident on the device for the whole call."""
+        try:
+            return super(_KernelModel, self).stochastic_train(input_matrix, target_matrix, *args, **kwargs)
+        finally:
+            self._stochastic_full = None
+
+    def resident(self, input_matrix, target_matrix):
+        """``with model.resident(X, Y):`` -- upload (X, Y) once; every evaluation inside the block that is handed these same
+        two objects runs on the resident copy.  ``train()`` and ``train_step()`` open this scope themselves."""
+        return _ResidencyScope(self, input_matrix, target_matrix)
+
+    def _enter_scope(self, input_matrix, target_matrix):
+        """A residency scope begins: upload now (edits made outside the scope are always seen)."""
+        if self._workspace is not None and not dev.is_device_vector(input_matrix):
+            self._workspace.resident = None
+        self._make_resident(input_matrix, target_matrix)
+
+    def _pre_train(self, input_matrix, target_matrix):
+        """Model.train hook (base.py:166): the dataset becomes device-resident once per train call."""
+        self._train_scope = self.resident(input_matrix, target_matrix)
+        self._train_scope.__enter__()
+
+    def _post_train(self, input_matrix, target_matrix):
+        """Model.train hook (base.py:181): leave the scope, reset the optimizer (mlp.py:184-190, regression.py:126-132)."""
+        scope = getattr(self, '_train_scope', None)
+        if scope is not None:
+            scope.__exit__(None, None, None)
+            self._train_scope = None
+        self._optimizer.reset()
+
+    def invalidate(self):
+        """Forget what is resident: the next evaluation uploads (host arrays) or re-reads (device tensors) its data."""
+        if self._workspace is not None:
+            self._workspace.resident = None
 
     def _world_size(self):
         if torch.distributed.is_available() and torch.distributed.is_initialized():
@@ -207,9 +301,9 @@ class _KernelModel(Model):
     def _probe(self, ws, x_dev, alpha, direction, want_grad):
         """Evaluate at x + alpha*direction on the device.  Returns (obj, slope, grad tensor | None)."""
         n = x_dev.numel()
-        out = torch.empty(n + 1, dtype=torch.float64, device=x_dev.device)
+        out = torch.empty(n + 2, dtype=torch.float64, device=x_dev.device)   # [gradient ; objective ; domain flag]
         sharded = getattr(ws, 'sharded', False)
-        peer = self._peer_allreduce(ws, n + 1) if sharded and want_grad else None
+        peer = self._peer_allreduce(ws, n + 2) if sharded and want_grad else None
         mine = peer.next_slot() if peer is not None else out
         nat.check(nat.lib.opl_mlp_eval_device(ws.pointer, dev.ptr(x_dev), float(alpha), dev.ptr(direction),
                                               1 if want_grad else 0, dev.ptr(mine)))
@@ -271,8 +365,35 @@ class _KernelModel(Model):
     def __getstate__(self):
         state = dict(self.__dict__)
         state['_workspace'] = None       # device buffers are rebuilt on demand
+        state['_residency_scope'] = None
+        state.pop('_train_scope', None)
+        state.pop('_stochastic_full', None)
         state.pop('_flat_stage', None)
         return state
+
+
+class _ResidencyScope(object):
+    """Context manager behind ``_KernelModel.resident`` (re-entrant: an inner scope on the same objects is a no-op)."""
+
+    def __init__(self, model, x, y):
+        self.model, self.x, self.y = model, x, y
+        self.outer = None
+
+    def __enter__(self):
+        model = self.model
+        self.outer = model._residency_scope
+        if not (self.outer is not None and self.outer[0] is self.x and self.outer[1] is self.y):
+            model._residency_scope = (self.x, self.y)
+            try:
+                model._enter_scope(self.x, self.y)
+            except Exception:
+                model._residency_scope = self.outer
+                raise
+        return model
+
+    def __exit__(self, *exc):
+        self.model._residency_scope = self.outer
+        return False
 
 
 class MLP(_KernelModel):
@@ -346,12 +467,12 @@ class MLP(_KernelModel):
         return self._forward_host(_flatten(self._bias_vec, self._weight_matrices), input_tensor)
 
     # ------------------------------------------------------------------ training
-    def _pre_train(self, input_matrix, target_matrix):
-        """Model.train hook (base.py:166): the dataset becomes device-resident once per train call."""
-        self._make_resident(input_matrix, target_matrix)
-
     def train_step(self, input_matrix, target_matrix):
         """One optimizer step on the full batch (mlp.py:165-182); returns the objective at x_k."""
+        with self.resident(input_matrix, target_matrix):
+            return self._train_step_resident(input_matrix, target_matrix)
+
+    def _train_step_resident(self, input_matrix, target_matrix):
         ws = self._make_resident(input_matrix, target_matrix)
         problem = Problem(obj_func=lambda xk: self._get_obj(xk, input_matrix, target_matrix),
                           obj_jac_func=lambda xk: self._get_obj_jac(xk, input_matrix, target_matrix))
@@ -385,10 +506,6 @@ class MLP(_KernelModel):
         torch.cuda.current_stream().synchronize()        # an earlier upload from this buffer has been consumed
         numpy.concatenate(parts, out=stage.numpy())
         return stage.cuda(non_blocking=True)
-
-    def _post_train(self, input_matrix, target_matrix):
-        """Reset optimizer: the problem may change on the next train call (mlp.py:184-190)."""
-        self._optimizer.reset()
 
     # ------------------------------------------------------------------ objective / gradient
     def _get_obj(self, parameter_vec, input_matrix, target_matrix):
@@ -453,11 +570,12 @@ class DropoutMLP(MLP):
         for num_neurons in self._shape[1:-1]:
             masks.append(_get_active_neurons(self._hid_act_prob, num_neurons))
         flat = numpy.ascontiguousarray(numpy.hstack(masks), dtype=numpy.float64)
-        ws = self._make_resident(input_matrix, target_matrix)
-        nat.check(nat.lib.opl_mlp_set_masks_host(ws.pointer, flat.ctypes.data_as(ctypes.c_void_p), flat.size))
-        try:
-            error = super(DropoutMLP, self).train_step(input_matrix, target_matrix)
-        finally:
-            nat.check(nat.lib.opl_mlp_set_masks_host(ws.pointer, None, 0))
-            self._during_training = False
+        with self.resident(input_matrix, target_matrix):
+            ws = self._make_resident(input_matrix, target_matrix)
+            nat.check(nat.lib.opl_mlp_set_masks_host(ws.pointer, flat.ctypes.data_as(ctypes.c_void_p), flat.size))
+            try:
+                error = super(DropoutMLP, self).train_step(input_matrix, target_matrix)
+            finally:
+                nat.check(nat.lib.opl_mlp_set_masks_host(ws.pointer, None, 0))
+                self._during_training = False
         return error

@@ -18,7 +18,7 @@ from .. import _device as dev
 from .. import error as error_mod
 from ..error import MeanSquaredError
 from ..optimize import Problem, make_optimizer
-from .mlp import _KernelModel, _fingerprint
+from .mlp import _KernelModel
 from .som import SOM
 
 INITIAL_WEIGHTS_RANGE = 0.25
@@ -101,16 +101,29 @@ class RBF(_KernelModel):
             raise ValueError('input_matrix and target_matrix must be matrices with equal row counts')
         if y.shape[-1] != self._shape[-1]:
             raise ValueError('target attributes == %s, expected %s' % (y.shape[-1], self._shape[-1]))
-        key = _fingerprint(x, y) + (self._clustering_model._weights.tobytes(),)
-        if self._features is None or self._features[0] != key:
-            first, count, _ = self._shard(x.shape[0])
-            x_dev = dev.to_device(numpy.ascontiguousarray(x[first:first + count]))
-            self._features = (key, self._similarity_device(x_dev),
-                              dev.to_device(numpy.ascontiguousarray(y[first:first + count])))
-        return self._features[1], self._features[2]
+        # cached only inside a residency scope (train / train_step) on these very objects and for these cluster centres
+        scope = self._residency_scope
+        in_scope = scope is not None and scope[0] is input_matrix and scope[1] is target_matrix
+        centres = self._clustering_model._weights.tobytes()
+        cached = self._features
+        if in_scope and cached is not None and cached[0] is input_matrix and cached[1] is target_matrix and cached[2] == centres:
+            return cached[3], cached[4]
+        first, count, _ = self._shard(x.shape[0])
+        x_dev = dev.to_device(numpy.ascontiguousarray(x[first:first + count]))
+        features = (input_matrix, target_matrix, centres, self._similarity_device(x_dev),
+                    dev.to_device(numpy.ascontiguousarray(y[first:first + count])))
+        self._features = features if in_scope else None
+        return features[3], features[4]
+
+    def _enter_scope(self, input_matrix, target_matrix):
+        self._features = None          # the similarity matrix is rebuilt on first use inside the scope
 
     def train_step(self, input_matrix, target_matrix):
         """One optimizer step on the output layer (rbf.py:153-177)."""
+        with self.resident(input_matrix, target_matrix):
+            return self._train_step_resident(input_matrix, target_matrix)
+
+    def _train_step_resident(self, input_matrix, target_matrix):
         if self._cluster_incrementally:
             self._clustering_model.train_step(input_matrix, target_matrix)
         sim, tgt = self._training_features(input_matrix, target_matrix)
@@ -132,9 +145,7 @@ class RBF(_KernelModel):
     def _pre_train(self, input_matrix, target_matrix):
         if not self._cluster_incrementally:
             self._clustering_model.train(input_matrix, target_matrix)      # cluster the input space (rbf.py:184-186)
-
-    def _post_train(self, input_matrix, target_matrix):
-        self._optimizer.reset()
+        super(RBF, self)._pre_train(input_matrix, target_matrix)
 
     # ------------------------------------------------------------------ objective / gradient (rbf.py:191-225)
     def _get_obj(self, parameter_vec, input_matrix, target_matrix):

@@ -64,11 +64,12 @@ class RegressionModel(_KernelModel):
         return self._forward_host(self._weight_matrix.ravel(), input_tensor)
 
     # ------------------------------------------------------------------ training
-    def _pre_train(self, input_matrix, target_matrix):
-        self._make_resident(input_matrix, target_matrix)
-
     def train_step(self, input_matrix, target_matrix):
         """One optimizer step (regression.py:101-124)."""
+        with self.resident(input_matrix, target_matrix):
+            return self._train_step_resident(input_matrix, target_matrix)
+
+    def _train_step_resident(self, input_matrix, target_matrix):
         ws = self._make_resident(input_matrix, target_matrix)
         problem = Problem(obj_func=lambda xk: self._get_obj(xk, input_matrix, target_matrix),
                           obj_jac_func=lambda xk: self._get_obj_jac(xk, input_matrix, target_matrix))
@@ -84,9 +85,6 @@ class RegressionModel(_KernelModel):
             norm = dev.norm(jacobian) if dev.is_device_vector(jacobian) else float(numpy.linalg.norm(jacobian))
             self.converged = norm < self._jacobian_norm_break
         return error
-
-    def _post_train(self, input_matrix, target_matrix):
-        self._optimizer.reset()
 
     # ------------------------------------------------------------------ objective / gradient
     def _get_obj(self, parameter_vec, input_matrix, target_matrix):

@@ -33,7 +33,8 @@ class SOM(Model):
         self._size = (neurons, attributes)
         self._weights = numpy.zeros(self._size)
         self._distances = numpy.zeros(neurons)
-        self._resident = None          # (key, device copy) of the training matrix
+        self._resident = None          # (training matrix object, its device copy) inside a train() call
+        self._train_scope_input = None
         self.reset()
 
     def reset(self):
@@ -82,11 +83,20 @@ class SOM(Model):
         self._weights = dev.to_host(w)
 
     def _device_matrix(self, input_matrix):
+        """Device copy of the training matrix: uploaded once per train() call (kept between its train_steps for the very
+        object train() was given), on every call otherwise -- never guessed from the contents."""
+        cached = self._resident
+        if cached is not None and cached[0] is input_matrix:
+            return cached[1]
         x = self._check_input(input_matrix)
-        key = (id(input_matrix), x.__array_interface__['data'][0], x.shape, float(x.reshape(-1)[0]), float(x.reshape(-1)[-1]))
-        if self._resident is None or self._resident[0] != key:
-            self._resident = (key, dev.to_device(x.reshape(-1, self._size[1])))
-        return self._resident[1]
+        x_dev = dev.to_device(x.reshape(-1, self._size[1]))
+        if self._train_scope_input is input_matrix:
+            self._resident = (input_matrix, x_dev)
+        return x_dev
+
+    def _pre_train(self, input_matrix, target_matrix):
+        self._train_scope_input = input_matrix
+        self._resident = None
 
     def train_step(self, input_matrix, target_matrix):
         """One pass over the patterns in order (base.py:289-331 with SOM._train_increment).  Returns None, as the
@@ -102,9 +112,11 @@ class SOM(Model):
         self._train_on_device(dev.to_device(x.reshape(1, -1)))
 
     def _post_train(self, input_matrix, target_matrix):
+        self._train_scope_input = None
         self._resident = None
 
     def __getstate__(self):
         state = dict(self.__dict__)
         state['_resident'] = None
+        state['_train_scope_input'] = None
         return state

@@ -11,22 +11,34 @@ import random
 from . import validation
 
 
-def select_sample(input_matrix, target_matrix, size=None):
-    """Random rows without replacement, random order (base.py:39-50)."""
-    count = input_matrix.shape[0]
+def _sample_rows(count, size=None):
+    """Row numbers of select_sample: the same ``random`` calls, in the same order, as base.py:39-50."""
     if size is None:
         size = _selection_size_heuristic(count)
-    rows = random.sample(range(count), size)
+    return random.sample(range(count), size)
+
+
+def _random_rows(count, size=None):
+    """Row numbers of select_random (base.py:53-64)."""
+    if size is None:
+        size = _selection_size_heuristic(count)
+    return [random.randint(0, count - 1) for _ in range(size)]
+
+
+def select_sample(input_matrix, target_matrix, size=None):
+    """Random rows without replacement, random order (base.py:39-50)."""
+    rows = _sample_rows(input_matrix.shape[0], size)
     return input_matrix[rows], target_matrix[rows]
 
 
 def select_random(input_matrix, target_matrix, size=None):
     """Random rows with replacement (base.py:53-64)."""
-    count = input_matrix.shape[0]
-    if size is None:
-        size = _selection_size_heuristic(count)
-    rows = [random.randint(0, count - 1) for _ in range(size)]
+    rows = _random_rows(input_matrix.shape[0], size)
     return input_matrix[rows], target_matrix[rows]
+
+
+# selection functions whose row choice can be replayed on a device-resident dataset
+ROW_SELECTORS = {select_sample: _sample_rows, select_random: _random_rows}
 
 
 def _selection_size_heuristic(num_samples):
@@ -56,9 +68,15 @@ class Model(object):
     # ------------------------------------------------------------------ training loops
     def stochastic_train(self, input_matrix, target_matrix, max_iterations=100, error_break=0.002,
                          pattern_selection_func=select_sample, train_kwargs={'iterations': 100}):
-        """Repeated ``train`` on random subsets (base.py:100-135)."""
+        """Repeated ``train`` on random subsets (base.py:100-135).  Models with a device-side dataset
+        (``_select_patterns``) keep the whole dataset resident and select each mini-batch there."""
+        select = getattr(self, '_select_patterns', None)
         for iteration in range(1, max_iterations + 1):
-            train_error = self.train(*pattern_selection_func(input_matrix, target_matrix), **train_kwargs)
+            if select is not None:
+                batch = select(pattern_selection_func, input_matrix, target_matrix)
+            else:
+                batch = pattern_selection_func(input_matrix, target_matrix)
+            train_error = self.train(*batch, **train_kwargs)
             if self.converged:
                 if (train_error <= error_break
                         and validation.get_error(self, input_matrix, target_matrix) <= error_break):
@@ -172,5 +190,16 @@ class Model(object):
         return model
 
     def print_results(self, input_matrix, target_matrix):
-        for inp_vec, tar_vec in zip(input_matrix, target_matrix):
-            print(inp_vec, '->', self.activate(inp_vec), '(%s)' % tar_vec)
+        """Print corresponding inputs and outputs from a dataset (base.py:378-381): the same lines as the reference's
+        per-pattern loop, from ONE batched activate when the model takes a matrix of patterns."""
+        outputs = None
+        try:
+            import numpy
+            batch = self.activate(numpy.asarray(input_matrix))
+            if len(batch) == len(input_matrix):
+                outputs = batch
+        except Exception:
+            outputs = None                    # a model that only takes single patterns: the reference's loop
+        for row, (inp_vec, tar_vec) in enumerate(zip(input_matrix, target_matrix)):
+            out_vec = self.activate(inp_vec) if outputs is None else outputs[row]
+            print(inp_vec, '->', out_vec, '(%s)' % tar_vec)

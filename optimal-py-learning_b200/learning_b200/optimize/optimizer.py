@@ -13,6 +13,7 @@ All n-vector and n x n arithmetic runs in the CUDA kernels behind include/opl_b2
 is no NumPy arithmetic here.
 """
 import ctypes
+import pickle
 
 import numpy
 import torch
@@ -80,6 +81,8 @@ class Optimizer(object):
         for key, value in list(state.items()):
             if isinstance(value, torch.Tensor):
                 state[key] = dev.to_host(value)
+            elif isinstance(value, _LazyDeviceVector):
+                state[key] = value.host
         return state
 
 
@@ -121,7 +124,13 @@ class SteepestDescentMomentum(Optimizer):
         self._step_size_getter.reset()
         self._prev_step = None
 
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        if isinstance(self._prev_step, numpy.ndarray):       # the reference pickles _prev_step too (optimizer.py:117)
+            self._prev_step = _LazyDeviceVector(self._prev_step)
+
     def _next(self, problem, x):
+        self._prev_step = _materialise(self._prev_step)
         value, grad = problem.get_obj_jac(x)
         self.jacobian = grad
         downhill = dev.scale(-1.0, grad)
@@ -133,6 +142,17 @@ class SteepestDescentMomentum(Optimizer):
             following = dev.axpy(x, 1.0, step, self._momentum_rate, self._prev_step)
         self._prev_step = step
         return value, following
+
+
+class _LazyDeviceVector(object):
+    """A host vector restored from pickle that becomes a device vector on first use (unpickling must not need a GPU)."""
+
+    def __init__(self, host):
+        self.host = host
+
+
+def _materialise(value):
+    return dev.to_device(value.host) if isinstance(value, _LazyDeviceVector) else value
 
 
 # ----------------------------------------------------------------------------------------
@@ -154,12 +174,25 @@ def initial_hessian_scaled_identity(param_diff, jacobian, previous_jacobian):
 _SEED_MODES = {initial_hessian_identity: 0, initial_hessian_scaled_identity: 1}
 
 
+# H larger than this is not carried through pickle (config 3's H is 55 GB); see BFGS.__getstate__
+MAX_PICKLED_HESSIAN_BYTES = 1 << 30
+
+
 class _NativeHandle(object):
     """Owns one C-ABI object; destroyed with the Python object, never pickled."""
 
-    def __init__(self, pointer, destroy):
+    def __init__(self, pointer, destroy, set_stream=None):
         self.pointer = pointer
         self._destroy = destroy
+        self._set_stream = set_stream
+        self._stream = torch.cuda.current_stream().cuda_stream
+
+    def bind_current_stream(self):
+        """The handle's kernels run on the caller's CURRENT stream: re-bind when it changed since the last call."""
+        stream = torch.cuda.current_stream().cuda_stream
+        if stream != self._stream and self._set_stream is not None:
+            nat.check(self._set_stream(self.pointer, ctypes.c_void_p(stream)))
+            self._stream = stream
 
     def __del__(self):
         try:
@@ -195,6 +228,7 @@ class BFGS(Optimizer):
         self._prev_step = None
         self._prev_jacobian = None
         self._native = None
+        self._restore_hessian = None     # host H waiting to be uploaded (after unpickling / load_state)
 
     def reset(self):
         super(BFGS, self).reset()
@@ -202,15 +236,47 @@ class BFGS(Optimizer):
         self._iteration = 0
         self._prev_step = None
         self._prev_jacobian = None
+        self._restore_hessian = None
         if self._native is not None:
             nat.check(nat.lib.opl_bfgs_reset(self._native.pointer))
 
     def __getstate__(self):
+        """The reference pickles ``_prev_step``, ``_prev_jacobian`` and ``_prev_inv_hessian`` with the model
+        (optimizer.py:212-221, base.py:350-360), so a model restored mid-training continues the same iterate sequence.
+        Here they come down as host arrays (Optimizer.__getstate__ converts the vectors; H is materialised) and go back
+        up on the first step after the restore.  An H above MAX_PICKLED_HESSIAN_BYTES (or a row-sharded one) is not
+        carried: the restored optimizer then starts over like a reset one (iteration counter included), which the
+        reference would too after its own ``reset()``."""
         state = super(BFGS, self).__getstate__()
-        state['_native'] = None          # H is rebuilt from the next two gradients after a restore
-        state['_prev_step'] = None
-        state['_prev_jacobian'] = None
+        native, n = self._native, getattr(self, '_native_n', 0)
+        state['_native'] = None
+        state['_restore_hessian'] = getattr(self, '_restore_hessian', None)
+        if native is not None and nat.lib.opl_bfgs_state(native.pointer) != 0:
+            if self._world()[1] == 1 and 8 * n * n <= MAX_PICKLED_HESSIAN_BYTES:
+                state['_restore_hessian'] = self.inverse_hessian()
+            else:
+                state['_prev_step'] = state['_prev_jacobian'] = state['_restore_hessian'] = None
+                state['_iteration'] = 0
+                state['_step_size_getter'] = pickle.loads(pickle.dumps(self._step_size_getter))
+                state['_step_size_getter'].reset()
         return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        for key in ('_prev_step', '_prev_jacobian'):          # back to device vectors on first use
+            if isinstance(self.__dict__.get(key), numpy.ndarray):
+                self.__dict__[key] = _LazyDeviceVector(self.__dict__[key])
+
+    def load_state(self, iteration, prev_step, prev_jacobian, inverse_hessian):
+        """Install an explicit optimizer state (host arrays; ``inverse_hessian`` None before the first update): what a
+        restore from pickle does, and what the teacher-forced parity tests use to start a step from the reference's
+        state (optimizer.py:212-221 attributes)."""
+        self._iteration = int(iteration)
+        self._prev_step = None if prev_step is None else dev.to_device(prev_step)
+        self._prev_jacobian = None if prev_jacobian is None else dev.to_device(prev_jacobian)
+        if self._native is not None:
+            nat.check(nat.lib.opl_bfgs_reset(self._native.pointer))
+        self._restore_hessian = None if inverse_hessian is None else numpy.ascontiguousarray(inverse_hessian, dtype=float)
 
     # ---- native state -------------------------------------------------------------------
     def _world(self):
@@ -228,13 +294,25 @@ class BFGS(Optimizer):
             begin, end, _ = self._row_range(n)
             out = ctypes.c_void_p()
             nat.check(nat.lib.opl_bfgs_create(ctypes.byref(out), n, begin, end, dev.stream_ptr()))
-            self._native = _NativeHandle(out, nat.lib.opl_bfgs_destroy)
+            self._native = _NativeHandle(out, nat.lib.opl_bfgs_destroy, nat.lib.opl_bfgs_set_stream)
             self._native_n = n
+        self._native.bind_current_stream()
+        pending = getattr(self, '_restore_hessian', None)
+        if pending is not None:                    # a restored / explicitly loaded H goes up once
+            self._restore_hessian = None
+            begin, end, _ = self._row_range(n)
+            if pending.shape != (n, n):
+                raise ValueError('restored inverse Hessian has shape %s, expected (%d, %d)' % (pending.shape, n, n))
+            h = dev.to_device(pending[begin:end])
+            nat.check(nat.lib.opl_bfgs_load_device(self._native.pointer, dev.ptr(h)))
+            torch.cuda.current_stream().synchronize()     # h may be freed after this call
         return self._native.pointer
 
     def _direction(self, grad):
         """-(H.dot(jac)) with H from _get_approx_inv_hessian (optimizer.py:242-285)."""
         n = grad.numel()
+        self._prev_step = _materialise(self._prev_step)
+        self._prev_jacobian = _materialise(self._prev_jacobian)
         handle = self._state(n)
         seed = _SEED_MODES[self._initial_hessian_func]
         direction = torch.empty_like(grad)
@@ -263,8 +341,12 @@ class BFGS(Optimizer):
     def inverse_hessian(self):
         """The reference's ``_prev_inv_hessian`` as a NumPy array (local rows when sharded);
         None before the second iteration."""
+        pending = getattr(self, '_restore_hessian', None)
+        if pending is not None:
+            return pending
         if self._native is None or nat.lib.opl_bfgs_state(self._native.pointer) == 0:
             return None
+        self._native.bind_current_stream()
         n = self._native_n
         begin, end, _ = self._row_range(n)
         out = torch.empty((end - begin, n), dtype=torch.float64, device='cuda')
@@ -344,21 +426,54 @@ class LBFGS(Optimizer):
         self._prev_step = None
         self._prev_jacobian = None
         self._native = None
+        self._restore_history = None     # host (s, y) pairs waiting to be uploaded (after unpickling / load_state)
 
     def reset(self):
         super(LBFGS, self).reset()
         self._step_size_getter.reset()
         self._prev_step = None
         self._prev_jacobian = None
+        self._restore_history = None
         if self._native is not None:
             nat.check(nat.lib.opl_lbfgs_reset(self._native.pointer))
 
     def __getstate__(self):
+        """The (s, y) history, ``_prev_step`` and ``_prev_jacobian`` travel through pickle as host arrays, like the
+        reference's ``_prev_param_diffs`` / ``_prev_jac_diffs`` (optimizer.py:397-403)."""
         state = super(LBFGS, self).__getstate__()
         state['_native'] = None
-        state['_prev_step'] = None
-        state['_prev_jacobian'] = None
+        state['_restore_history'] = self.history()
         return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        for key in ('_prev_step', '_prev_jacobian'):
+            if isinstance(self.__dict__.get(key), numpy.ndarray):
+                self.__dict__[key] = _LazyDeviceVector(self.__dict__[key])
+
+    def history(self):
+        """[(s_i, y_i)] oldest first, as host arrays: the reference's ``_prev_param_diffs`` / ``_prev_jac_diffs``."""
+        pending = getattr(self, '_restore_history', None)
+        if pending is not None:
+            return list(pending)
+        if self._native is None:
+            return []
+        self._native.bind_current_stream()
+        pairs = []
+        n = self._native_n
+        for i in range(nat.lib.opl_lbfgs_history_len(self._native.pointer)):
+            s, y = dev.empty(n), dev.empty(n)
+            nat.check(nat.lib.opl_lbfgs_get_pair_device(self._native.pointer, i, dev.ptr(s), dev.ptr(y)))
+            pairs.append((dev.to_host(s), dev.to_host(y)))
+        return pairs
+
+    def load_state(self, prev_step, prev_jacobian, pairs):
+        """Install an explicit optimizer state (host arrays): restore from pickle / teacher-forced parity tests."""
+        self._prev_step = None if prev_step is None else dev.to_device(prev_step)
+        self._prev_jacobian = None if prev_jacobian is None else dev.to_device(prev_jacobian)
+        if self._native is not None:
+            nat.check(nat.lib.opl_lbfgs_reset(self._native.pointer))
+        self._restore_history = [(numpy.asarray(s, dtype=float), numpy.asarray(y, dtype=float)) for s, y in pairs]
 
     def _state(self, n):
         if self._native is None or self._native_n != n:
@@ -366,12 +481,22 @@ class LBFGS(Optimizer):
             memory = 0 if memory == float('inf') else int(memory)
             out = ctypes.c_void_p()
             nat.check(nat.lib.opl_lbfgs_create(ctypes.byref(out), n, memory, dev.stream_ptr()))
-            self._native = _NativeHandle(out, nat.lib.opl_lbfgs_destroy)
+            self._native = _NativeHandle(out, nat.lib.opl_lbfgs_destroy, nat.lib.opl_lbfgs_set_stream)
             self._native_n = n
+        self._native.bind_current_stream()
+        pending = getattr(self, '_restore_history', None)
+        if pending:
+            for s, y in pending:
+                sd, yd = dev.to_device(s), dev.to_device(y)
+                nat.check(nat.lib.opl_lbfgs_push_pair_device(self._native.pointer, dev.ptr(sd), dev.ptr(yd)))
+            torch.cuda.current_stream().synchronize()        # the staging tensors may be freed after this call
+        self._restore_history = None
         return self._native.pointer
 
     def _step_direction(self, grad):
         """_update_diffs + _lbfgs_step_dir (optimizer.py:433-493)."""
+        self._prev_step = _materialise(self._prev_step)
+        self._prev_jacobian = _materialise(self._prev_jacobian)
         handle = self._state(grad.numel())
         direction = torch.empty_like(grad)
         nat.check(nat.lib.opl_lbfgs_direction_device(handle, dev.ptr(grad), dev.ptr(self._prev_step),

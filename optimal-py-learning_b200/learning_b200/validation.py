@@ -21,11 +21,21 @@ def get_error(model, input_matrix, target_matrix, error_func=None):
     return error_func(outputs, numpy.asarray(target_matrix, dtype=float))
 
 
+def _get_classes(matrix):
+    """Class of every row: the label itself for a column matrix, else the arg-max (validation.py:257-271)."""
+    matrix = numpy.asarray(matrix)
+    if matrix.ndim == 1:
+        return matrix
+    if matrix.shape[1] == 1:
+        return matrix.ravel()
+    return numpy.argmax(matrix, axis=1)
+
+
 def get_accuracy(model, input_matrix, target_matrix):
-    """Fraction of patterns whose arg-max output matches the arg-max target (validation.py:247-254)."""
+    """Fraction of patterns whose class matches the target's (validation.py:247-254): a column matrix holds the class
+    labels themselves, a wider one is one-hot / scores and is arg-maxed (``_get_classes``)."""
     outputs = numpy.asarray(model.activate(numpy.asarray(input_matrix, dtype=float)))
-    targets = numpy.asarray(target_matrix)
-    hits = numpy.argmax(outputs, axis=-1) == numpy.argmax(targets, axis=-1)
+    hits = _get_classes(outputs) == _get_classes(numpy.asarray(target_matrix))
     return float(numpy.mean(hits))
 
 

@@ -88,6 +88,10 @@ def test_device_api_matches_host_api_and_probe(L, golden_meta, golden_objgrad):
     ((96, 72, 40, 5), [(2, 0), (0, 0), (0, 0)], 0, 1111),   # linear hidden + linear output + MSE through the fused head
     ((40, 70, 33, 65), [(4, 0), (2, 0), (2, 0)], 0, 517),   # hidden softmax, wide output
     ((3, 1), [(0, 0)], 0, 5),
+    # BASELINE config 4's shape: INT8 forward / dW / dA (OZ_EPI_MUL_AUX) GEMMs, 32 classes (no fused head), digits of hidden layers
+    ((1024, 256, 256, 32), [(2, 0), (2, 0), (4, 0)], 1, 4096),
+    # BASELINE config 5's shape: four 1024-wide softplus layers, linear output + MSE (MLP defaults), fused narrow head
+    ((256, 1024, 1024, 1024, 1024, 10), [(2, 0), (2, 0), (2, 0), (2, 0), (0, 0)], 0, 4096),
 ])
 @pytest.mark.parametrize("precision", ["f64", "f64-dmma"])   # INT8 (Ozaki) engine for the large GEMMs / DMMA everywhere
 def test_objgrad_against_oracle_at_size(L, shape, transfers, eid, rows, precision):
@@ -205,6 +209,95 @@ def test_full_size_properties_config2(L):
     o_s, g_s = m2._get_obj_jac(w.copy(), x[sl], y[sl])
     want_o, want_g = mo.objective_gradient(w, shape, transfers, eid, x[sl], y[sl], literal_softmax=False)
     assert rel_err(o_s, want_o) <= TOL and rel_err(g_s, want_g) <= TOL
+
+
+def test_full_size_config2_against_oracle(L):
+    """BASELINE config 2 at its real size -- all 60000 x 784 patterns, (784,256,10) softplus / softmax + cross entropy --
+    against the oracle's objective and gradient of the SAME 60000 rows (not a slice), in the parity mode and in the fast
+    mode; plus residency: an in-place edit of X between two calls must be seen."""
+    rng = numpy.random.default_rng(0)
+    shape, transfers, eid = (784, 256, 10), [(2, 0), (4, 0)], 1
+    x, y = mo.random_classification(60000, 784, 10, rng)
+    w = mo.random_params(shape, rng)
+    want_obj, want_grad = mo.objective_gradient(w, shape, transfers, eid, x, y, literal_softmax=False)
+    model = _model(L, shape, transfers, eid)
+    obj, grad = model._get_obj_jac(w.copy(), x, y)
+    assert rel_err(obj, want_obj) <= TOL and rel_err(grad, want_grad) <= TOL, (rel_err(obj, want_obj), rel_err(grad, want_grad))
+    fast = _fast_model(L, shape, transfers, eid)
+    obj_f, grad_f = fast._get_obj_jac(w.copy(), x, y)
+    assert rel_err(obj_f, want_obj) <= FAST_TOL and rel_err(grad_f, want_grad) <= FAST_TOL, rel_err(grad_f, want_grad)
+    # the reference always reads the arrays it is given: edit X in place (same object, same buffer), evaluate again
+    x[::3] *= -0.5
+    want_obj2, want_grad2 = mo.objective_gradient(w, shape, transfers, eid, x, y, literal_softmax=False)
+    assert rel_err(want_grad2, want_grad) > 1e-3
+    obj2, grad2 = model._get_obj_jac(w.copy(), x, y)
+    assert rel_err(obj2, want_obj2) <= TOL and rel_err(grad2, want_grad2) <= TOL, rel_err(grad2, want_grad2)
+
+
+def test_residency_is_explicit_never_guessed(L):
+    """Dataset residency (architecture/mlp.py _make_resident): inside a residency scope the upload happens once; outside
+    every call reads the arrays it is given; device tensors are re-read when their version counter moves."""
+    import torch
+    from learning_b200 import _device as dev
+    rng = numpy.random.default_rng(3)
+    shape, transfers, eid = (128, 64, 5), [(2, 0), (4, 0)], 1
+    x, y = mo.random_classification(1536, 128, 5, rng)          # INT8-engine size: the digits of X are cached per set_data
+    w = mo.random_params(shape, rng)
+    model = _model(L, shape, transfers, eid)
+    ref = lambda xx: mo.objective_gradient(w, shape, transfers, eid, xx, y)
+    _, g0 = model._get_obj_jac(w.copy(), x, y)
+    assert rel_err(g0, ref(x)[1]) <= TOL
+    x[5:50] += 0.25                                              # in place, same object
+    _, g1 = model._get_obj_jac(w.copy(), x, y)
+    assert rel_err(g1, ref(x)[1]) <= TOL and rel_err(g1, g0) > 1e-6
+    # a NEW array that happens to reuse a freed id / address is a different object
+    for _ in range(3):
+        xb = x + rng.standard_normal(x.shape) * 0.1
+        _, gb = model._get_obj_jac(w.copy(), xb, y)
+        assert rel_err(gb, ref(xb)[1]) <= TOL
+        del xb
+    # inside a scope: one upload, evaluations on the resident copy
+    with model.resident(x, y):
+        token = model._workspace.resident
+        assert token is not None
+        _, ga = model._get_obj_jac(w.copy(), x, y)
+        assert model._workspace.resident is token               # no second upload
+        assert numpy.array_equal(ga, g1)
+    # device tensors: version counter
+    xd, yd = dev.to_device(x), dev.to_device(y)
+    wd = dev.to_device(w)
+    _, gd = model._get_obj_jac(wd, xd, yd)
+    assert numpy.array_equal(dev.to_host(gd), g1)
+    xd[5:50] -= 0.25                                             # in place on the device: _version moves
+    x[5:50] -= 0.25
+    _, gd2 = model._get_obj_jac(wd, xd, yd)
+    assert rel_err(dev.to_host(gd2), ref(x)[1]) <= TOL
+    model.invalidate()
+    _, gd3 = model._get_obj_jac(wd, xd, yd)
+    assert numpy.array_equal(dev.to_host(gd3), dev.to_host(gd2))
+
+
+def test_evaluation_follows_the_current_stream(L):
+    """Handles re-bind to the caller's current CUDA stream: an evaluation, a BFGS direction and an
+    L-BFGS direction issued under torch.cuda.stream(s) are ordered with the torch work of that stream."""
+    import torch
+    rng = numpy.random.default_rng(5)
+    shape, transfers, eid = (20, 16, 5), [(2, 0), (4, 0)], 1
+    x, y = mo.random_classification(300, 20, 5, rng)
+    w = mo.random_params(shape, rng)
+    for make in (L.optimize.BFGS, L.optimize.LBFGS):
+        a = _model(L, shape, transfers, eid, optimizer=make())
+        b = _model(L, shape, transfers, eid, optimizer=make())
+        for m in (a, b):
+            m.logging = False
+            m._bias_vec, m._weight_matrices = w[:16].copy(), [w[16:336].reshape(20, 16).copy(), w[336:].reshape(16, 5).copy()]
+        side = torch.cuda.Stream()
+        for step in range(4):
+            ea = a.train_step(x, y)
+            with torch.cuda.stream(side if step % 2 else torch.cuda.current_stream()):
+                eb = b.train_step(x, y)
+            assert ea == eb
+        assert numpy.array_equal(a._weight_matrices[0], b._weight_matrices[0])
 
 
 def test_reference_known_answers(L, golden_meta):
@@ -491,12 +584,78 @@ def _optimizer_for(L, name):
     }[name]()
 
 
+def _set_weights(model, flat, shape):
+    bias, mats = numpy.split(numpy.array(flat, dtype=float, copy=True), [shape[1]])
+    model._bias_vec = bias
+    model._weight_matrices = [m.reshape(s) for m, s in zip(
+        numpy.split(mats, numpy.cumsum([a * b for a, b in zip(shape[:-1], shape[1:])])[:-1]),
+        zip(shape[:-1], shape[1:]))]
+
+
+def _flat(model):
+    return numpy.hstack([model._bias_vec] + [m.ravel() for m in model._weight_matrices])
+
+
+def _teacher_forced_step(L, run, t, record):
+    """One train_step of the product from the ORACLE's x_k and optimizer state; returns (rel err of x_{k+1},
+    rel err of the step x_{k+1} - x_k, rel err of H_{k+1} or None)."""
+    from oracle_helpers import install_state
+    shape, transfers, eid = specs(run)
+    x_k, state, val, x_next, h_next = record
+    model = _model(L, shape, transfers, eid, optimizer=_optimizer_for(L, run["optimizer"]))
+    model.logging = False
+    _set_weights(model, x_k, shape)
+    install_state(L, model._optimizer, state)
+    err = model.train_step(t[run["data"] + "_x"], t[run["data"] + "_y"])
+    got = _flat(model)
+    e_obj = rel_err(err, val)
+    e_x = rel_err(got, x_next)
+    e_step = rel_err(got - x_k, x_next - x_k)
+    e_h = None
+    if h_next is not None and hasattr(model._optimizer, "inverse_hessian"):
+        e_h = rel_err(model._optimizer.inverse_hessian(), h_next)
+    return e_obj, e_x, e_step, e_h
+
+
+def test_teacher_forced_steps_with_optimizer_state_match_reference(L, golden_meta, golden_traces):
+    """Stateful teacher forcing (SURVEY section 7 hard part (i); reference optimize/optimizer.py:234-285,414-508): for
+    EVERY recorded step k of all ten reference traces, load the reference's x_k and its optimizer state before the step
+    (H_{k-1} / (s, y) history, previous step and gradient, iteration counter, initial-step memory), take one step and
+    compare the objective, x_{k+1} and H_k with the reference's to 1e-10.  The oracle that supplies the states reproduces
+    the golden traces bit for bit (tests/test_oracle.py), and that is re-asserted here."""
+    from oracle_helpers import oracle_trace_with_states
+    t = golden_traces
+    report = {}
+    for run in golden_meta["traces"]:
+        records = oracle_trace_with_states(run, t)
+        xs = t[run["key"] + "_xs"]
+        worst = [0.0, 0.0, 0.0, 0.0]
+        flips = []
+        for k, record in enumerate(records):
+            assert rel_err(record[3], xs[k + 1]) <= 1e-9, (run["key"], k)       # the oracle IS the reference trace
+            e_obj, e_x, e_step, e_h = _teacher_forced_step(L, run, t, record)
+            if e_step > 1e-6:
+                flips.append((k, e_step))
+            worst = [max(worst[0], e_obj), max(worst[1], e_x), max(worst[2], e_step if e_step <= 1e-6 else 0.0),
+                     max(worst[3], e_h or 0.0)]
+            assert e_obj <= TOL, (run["key"], k, e_obj)
+            assert e_h is None or e_h <= TOL, (run["key"], k, e_h)
+        report[run["key"]] = dict(steps=len(records), obj=worst[0], x=worst[1], step=worst[2], H=worst[3], flips=flips)
+    print("teacher-forced steps (worst relative errors per trace):", report)
+    for key, r in report.items():
+        # a line-search branch decided by a difference below the evaluation's own rounding may flip: at most one such step
+        # per trace is tolerated and it is reported; every other step must reproduce x_{k+1} to 1e-10
+        assert len(r["flips"]) <= 1, (key, r)
+        assert r["x"] <= TOL or r["flips"], (key, r)
+        assert r["step"] <= 1e-6, (key, r)
+
+
 def test_optimizer_iterate_sequences_match_reference(L, golden_meta, golden_traces):
-    """Free-running: same iterate sequence as the reference over the recorded steps.  Branch
-    decisions of the line search are chaotic on ill-conditioned problems, so the
-    gate is: agreement to 1e-8 for at least the first 20 steps on every trace and for all 50
-    on the well-conditioned 'mid' problems; the first divergence is reported."""
-    from learning_b200 import _device as dev
+    """Free-running: the same iterate sequence as the reference over the recorded steps (up to 50).  Gate: every trace
+    agrees to 1e-8 on ALL its steps, or up to its first line-search branch flip, which must come after step 20 and must be a
+    flip (not an arithmetic defect): the teacher-forced step from the reference's state at that very step reproduces the
+    reference's x_{k+1}.  Branch decisions are chaotic on ill-conditioned problems."""
+    from oracle_helpers import oracle_trace_with_states
     t = golden_traces
     report = {}
     for run in golden_meta["traces"]:
@@ -504,46 +663,48 @@ def test_optimizer_iterate_sequences_match_reference(L, golden_meta, golden_trac
         x, y = t[run["data"] + "_x"], t[run["data"] + "_y"]
         model = _model(L, shape, transfers, eid, optimizer=_optimizer_for(L, run["optimizer"]))
         model.logging = False
-        bias, mats = numpy.split(t[run["key"] + "_w0"].copy(), [shape[1]])
-        model._bias_vec = bias
-        model._weight_matrices = [m.reshape(s) for m, s in zip(
-            numpy.split(mats, numpy.cumsum([a * b for a, b in zip(shape[:-1], shape[1:])])[:-1]),
-            zip(shape[:-1], shape[1:]))]
+        _set_weights(model, t[run["key"] + "_w0"], shape)
         xs, objs = t[run["key"] + "_xs"], t[run["key"] + "_objs"]
         agree = 0
         for step in range(run["steps"]):
             err = model.train_step(x, y)
-            cur = numpy.hstack([model._bias_vec] + [m.ravel() for m in model._weight_matrices])
-            if rel_err(err, objs[step]) <= 1e-8 and rel_err(cur, xs[step + 1]) <= 1e-8:
+            if rel_err(err, objs[step]) <= 1e-8 and rel_err(_flat(model), xs[step + 1]) <= 1e-8:
                 agree = step + 1
             else:
                 break
         report[run["key"]] = (agree, run["steps"])
     print("iterate agreement (steps matching reference to 1e-8):", report)
-    for key, (agree, steps) in report.items():
-        assert agree >= min(20, steps), (key, agree, report)
-        if "_mid_" in key or "_reg_" in key:
-            assert agree == steps, (key, agree, report)
+    for run in golden_meta["traces"]:
+        agree, steps = report[run["key"]]
+        if agree == steps:
+            continue
+        assert agree >= 20 and "_mid_" not in run["key"] and "_reg_" not in run["key"], (run["key"], agree, report)
+        record = oracle_trace_with_states(run, t)[agree]
+        e_obj, e_x, e_step, e_h = _teacher_forced_step(L, run, t, record)
+        print("first divergence of %s at step %d: teacher-forced from the reference's state there: obj %.1e x %.1e"
+              % (run["key"], agree, e_obj, e_x))
+        assert e_obj <= TOL and e_x <= 1e-8, (run["key"], agree, e_obj, e_x)
 
 
-def test_teacher_forced_steps_match_reference(L, golden_meta, golden_traces):
-    """Teacher forcing: restart from the reference's x_k at every step (fresh optimizer state is
-    equivalent to the reference's first iteration) and compare x_{k+1}."""
+def test_checkpoint_mid_training_continues_the_same_sequence(L, golden_meta, golden_traces):
+    """Model.serialize / unserialize (base.py:350-373) mid-training: the reference pickles the optimizer's H / history /
+    previous step and gradient with the model, so a restored model continues the SAME iterate sequence."""
     t = golden_traces
-    run = [r for r in golden_meta["traces"] if r["key"] == "tr_iris_bfgs"][0]
-    shape, transfers, eid = specs(run)
-    x, y = t["iris_x"], t["iris_y"]
-    xs = t["tr_iris_bfgs_xs"]
-    from oracle_helpers import first_step_from
-    for k in (0, 7, 23, 41):
-        want = first_step_from(xs[k], shape, transfers, eid, x, y)
-        model = _model(L, shape, transfers, eid, optimizer=L.optimize.BFGS())
+    for name in ("tr_mid_bfgs", "tr_mid_lbfgs", "tr_reg_sdm"):
+        run = [r for r in golden_meta["traces"] if r["key"] == name][0]
+        shape, transfers, eid = specs(run)
+        x, y = t[run["data"] + "_x"], t[run["data"] + "_y"]
+        model = _model(L, shape, transfers, eid, optimizer=_optimizer_for(L, run["optimizer"]))
         model.logging = False
-        model._bias_vec, model._weight_matrices = xs[k][:shape[1]].copy(), [
-            xs[k][2:10].reshape(4, 2).copy(), xs[k][10:16].reshape(2, 3).copy()]
-        model.train_step(x, y)
-        cur = numpy.hstack([model._bias_vec] + [m.ravel() for m in model._weight_matrices])
-        assert rel_err(cur, want) <= 1e-9, k
+        _set_weights(model, t[name + "_w0"], shape)
+        for _ in range(6):
+            model.train_step(x, y)
+        clone = type(model).unserialize(model.serialize())
+        for step in range(6, 12):
+            ea, eb = model.train_step(x, y), clone.train_step(x, y)
+            assert ea == eb, (name, step)
+            assert numpy.array_equal(_flat(model), _flat(clone)), (name, step)
+        assert rel_err(_flat(clone), t[name + "_xs"][12]) <= 1e-8
 
 
 def test_readme_example_trains_like_the_reference(L, golden_traces):
@@ -652,6 +813,9 @@ def test_fast_mode_golden_cases(L, golden_meta, golden_objgrad):
     # a partial last step; then 16 classes, tanh output + MSE through the generic row stage
     ((64, 40, 5), [(1, 0), (4, 0)], 1, 1003),
     ((96, 72, 16), [(2, 0), (1, 0)], 0, 333),
+    # BASELINE config 4 / config 5 shapes: 128x256 TF32 tiles, five layers of TF32 error growth (gate 1e-3)
+    ((1024, 256, 256, 32), [(2, 0), (2, 0), (4, 0)], 1, 4096),
+    ((256, 1024, 1024, 1024, 1024, 10), [(2, 0), (2, 0), (2, 0), (2, 0), (0, 0)], 0, 4096),
 ])
 def test_fast_mode_against_oracle_at_size(L, shape, transfers, eid, rows):
     rng = numpy.random.default_rng(hash(shape) % 1000 + 1)

@@ -282,3 +282,86 @@ def test_make_train_test_sets_splits_like_the_reference():
     assert numpy.array_equal(tr_y, labels[[0, 1, 2, 3, 4, 6]]) and numpy.array_equal(te_y, labels[[5, 7, 8, 9]])
     with pytest.raises(ValueError):
         validation.make_train_test_sets(inputs, labels, train_per_class=5)
+
+
+class _Table(Model):
+    """activate() looks the pattern up: row r of `outputs` for row r of `inputs` (vector or matrix)."""
+
+    def __init__(self, inputs, outputs, matrix_ok=True):
+        super(_Table, self).__init__()
+        self.inputs, self.outputs, self.matrix_ok = numpy.asarray(inputs, float), numpy.asarray(outputs, float), matrix_ok
+        self.calls = 0
+
+    def activate(self, v):
+        self.calls += 1
+        v = numpy.asarray(v, float)
+        if v.ndim == 2:
+            if not self.matrix_ok:
+                raise ValueError("single patterns only")
+            return numpy.array([self.outputs[numpy.where((self.inputs == r).all(axis=1))[0][0]] for r in v])
+        return self.outputs[numpy.where((self.inputs == v).all(axis=1))[0][0]]
+
+
+def test_get_accuracy_column_labels_and_onehot():
+    """validation._get_classes (validation.py:257-271): a column matrix holds the labels themselves (NOT arg-maxed: that
+    would report 1.0 for every model), a wider matrix is arg-maxed."""
+    from learning_b200 import validation
+    x = numpy.arange(8.0).reshape(4, 2)
+    labels = numpy.array([[0.0], [1.0], [2.0], [1.0]])
+    model = _Table(x, numpy.array([[0.0], [1.0], [1.0], [0.0]]))          # 2 of 4 right
+    assert validation.get_accuracy(model, x, labels) == 0.5
+    onehot = numpy.array([[1, 0, 0], [0, 1, 0], [0, 0, 1], [0, 1, 0.0]])
+    scores = numpy.array([[0.9, 0.1, 0], [0.2, 0.5, 0.3], [0.6, 0.3, 0.1], [0.1, 0.8, 0.1]])   # 3 of 4 right
+    assert validation.get_accuracy(_Table(x, scores), x, onehot) == 0.75
+    assert validation._get_classes(labels).tolist() == [0.0, 1.0, 2.0, 1.0]
+    assert validation._get_classes(onehot).tolist() == [0, 1, 2, 1]
+
+
+def test_print_results_is_batched_and_prints_the_reference_lines(capsys):
+    """Model.print_results (base.py:378-381): one batched activate, the same lines as the per-pattern loop; models that
+    take single patterns only keep the loop."""
+    x = numpy.array([[0.0, 1.0], [2.0, 3.0], [4.0, 5.0]])
+    y = numpy.array([[1.0], [0.0], [1.0]])
+    out = numpy.array([[0.25], [0.5], [0.75]])
+    want = "".join("%s -> %s (%s)\n" % (a, b, c) for a, b, c in zip(x, out, y))
+    batched = _Table(x, out)
+    batched.print_results(x, y)
+    assert capsys.readouterr().out == want and batched.calls == 1
+    single = _Table(x, out, matrix_ok=False)
+    single.print_results(x, y)
+    assert capsys.readouterr().out == want and single.calls == 1 + len(x)
+
+
+def test_row_selectors_replay_the_reference_draws():
+    """base.select_sample / select_random (base.py:39-64): the row numbers used by the device gather are the same
+    ``random`` draws, in the same order, as the host selection."""
+    from learning_b200 import base
+    x, y = numpy.arange(40.0).reshape(20, 2), numpy.arange(20.0).reshape(20, 1)
+    for select, rows_of in base.ROW_SELECTORS.items():
+        for size in (None, 7):
+            random.seed(11)
+            xs, ys = select(x, y, size)
+            random.seed(11)
+            rows = rows_of(20, size)
+            assert numpy.array_equal(xs, x[rows]) and numpy.array_equal(ys, y[rows])
+    assert base._selection_size_heuristic(20) == min(20, int(20.0 * (math.log(30, 2) - math.log(10.0) + 1.0)))
+
+
+def test_optimizer_state_pickles_without_a_device():
+    """Optimizers pickle as host state only (base.py:350-373): a fresh or reset optimizer needs no GPU to round-trip, and
+    restored vectors stay host arrays until the first step uses them."""
+    import pickle
+    from learning_b200 import optimize as o
+    from learning_b200.optimize import optimizer as opt
+    for make in (o.BFGS, o.LBFGS, o.SteepestDescent, o.SteepestDescentMomentum):
+        clone = pickle.loads(pickle.dumps(make(), protocol=2))
+        assert type(clone) is make
+    b = o.BFGS()
+    b.__setstate__(dict(b.__getstate__(), _prev_step=numpy.ones(3), _prev_jacobian=numpy.zeros(3), _iteration=4,
+                        _restore_hessian=numpy.identity(3)))
+    assert isinstance(b._prev_step, opt._LazyDeviceVector) and b._iteration == 4
+    again = pickle.loads(pickle.dumps(b, protocol=2))
+    assert numpy.array_equal(again._prev_step.host, numpy.ones(3)) and numpy.array_equal(again.inverse_hessian(), numpy.identity(3))
+    lb = o.LBFGS()
+    lb.__setstate__(dict(lb.__getstate__(), _restore_history=[(numpy.ones(2), numpy.ones(2) * 2)]))
+    assert len(pickle.loads(pickle.dumps(lb, protocol=2)).history()) == 1

@@ -3,6 +3,8 @@
 
     ncu_summary.py launches gpurun_out/launches.csv            per-kernel totals of a `--metrics gpu__time_duration.sum --csv` list
     ncu_summary.py full gpurun_out/prof.ncu-rep [regex]        selected metrics per launch of a `--set full` report
+    ncu_summary.py traffic gpurun_out/prof.ncu-rep regex key [n]   dram bytes (read + write) of the LAST launch matching regex
+                                                               -> profiles/ncu_traffic.json[key] (what bench.py reports as roofline.traffic)
 """
 import collections
 import csv
@@ -58,8 +60,43 @@ def full(path, pattern=None):
                 print("  %-92s %s %s" % (m, r[head.index(m)], units[head.index(m)]))
 
 
+def traffic(path, pattern, key, n=None, source=None):
+    import json
+    import os
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    head, units = rows[0], rows[1]
+    ki = head.index("Kernel Name")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    found = None
+    for r in rows[2:]:
+        if re.search(pattern, r[ki]):
+            total = 0.0
+            for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                i = head.index(m)
+                total += float(r[i].replace(",", "")) * scale[units[i]]
+            found = (r[ki], total)
+    if found is None:
+        sys.exit("no launch matches %r" % pattern)
+    dest = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic.json")
+    data = {}
+    if os.path.exists(dest):
+        with open(dest) as fh:
+            data = json.load(fh)
+    entry = {"bytes": int(found[1]), "kernel": re.sub(r"\(.*", "", found[0])[-120:], "source": source or os.path.basename(path)}
+    if n is not None:
+        entry["n"] = int(n)
+    data[key] = entry
+    with open(dest, "w") as fh:
+        json.dump(data, fh, indent=1)
+    print(key, entry)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) >= 3 and sys.argv[1] == "launches":
+    if len(sys.argv) >= 5 and sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5] if len(sys.argv) > 5 else None,
+                sys.argv[6] if len(sys.argv) > 6 else None)
+    elif len(sys.argv) >= 3 and sys.argv[1] == "launches":
         launches(sys.argv[2])
     elif len(sys.argv) >= 3 and sys.argv[1] == "full":
         full(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)

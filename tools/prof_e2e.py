@@ -24,7 +24,7 @@ ws = m._workspace
 g = torch.empty(n, dtype=torch.float64, pin_memory=True).numpy(); obj = ctypes.c_double()
 wp, gp = w.ctypes.data_as(ctypes.c_void_p), g.ctypes.data_as(ctypes.c_void_p)
 print("C call opl_mlp_obj_jac_host %8.1f us" % timeit(lambda: nat.lib.opl_mlp_obj_jac_host(ws.pointer, wp, ctypes.byref(obj), gp), 100))
-wd = torch.from_numpy(w).cuda(); out = torch.empty(n + 1, dtype=torch.float64, device="cuda")
+wd = torch.from_numpy(w).cuda(); out = torch.empty(n + 2, dtype=torch.float64, device="cuda")
 print("device eval only            %8.1f us" % timeit(lambda: nat.lib.opl_mlp_eval_device(ws.pointer, ctypes.c_void_p(wd.data_ptr()), 0.0, None, 1, ctypes.c_void_p(out.data_ptr())), 100))
 hp = torch.empty(n, dtype=torch.float64, pin_memory=True)
 print("H2D 1.6 MB pinned + sync    %8.1f us" % timeit(lambda: (wd.copy_(hp, non_blocking=True), torch.cuda.synchronize())))

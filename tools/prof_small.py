@@ -12,7 +12,7 @@ numpy.random.seed(0); m.reset()
 for _ in range(5): m.train_step(x, y)
 ws = m._workspace
 n = 16
-wd = dev.to_device(rng.random(n)); out = torch.empty(n + 1, dtype=torch.float64, device="cuda")
+wd = dev.to_device(rng.random(n)); out = torch.empty(n + 2, dtype=torch.float64, device="cuda")
 torch.cuda.synchronize()
 l0 = nat.lib.opl_mlp_launch_count(ws.pointer)
 t0 = time.perf_counter()

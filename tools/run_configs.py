@@ -37,19 +37,21 @@ def run(name, model, x, y, steps):
     numpy.random.seed(0)
     model.logging = False
     model.reset()
-    objs, times = [], []
-    evals0 = model.obj_jac_evaluations
+    objs, times, evals = [], [], []
     torch.cuda.synchronize()
-    for _ in range(steps):
-        t0 = time.perf_counter()
-        objs.append(float(model.train_step(x, y)))
-        torch.cuda.synchronize()
-        times.append(time.perf_counter() - t0)
-    evals = model.obj_jac_evaluations - evals0
-    steady = times[2:] if len(times) > 3 else times
+    with model.resident(x, y):                       # what Model.train does around its train_steps
+        for _ in range(steps):
+            before = model.obj_jac_evaluations
+            t0 = time.perf_counter()
+            objs.append(float(model.train_step(x, y)))
+            torch.cuda.synchronize()
+            times.append(time.perf_counter() - t0)
+            evals.append(model.obj_jac_evaluations - before)   # evaluations of THIS step (line searches differ per step)
+    first = 2 if len(times) > 3 else 0               # steady state: steps after the first two (allocations, first upload)
     out = {"config": name, "steps": steps, "objective": [round(o, 6) for o in objs],
-           "s_per_step": [round(t, 5) for t in times], "obj_grad_evaluations": evals,
-           "evals_per_s_steady": round((evals * len(steady) / len(times)) / sum(steady), 2) if sum(steady) > 0 else None,
+           "s_per_step": [round(t, 5) for t in times], "obj_grad_evaluations_per_step": evals,
+           "obj_grad_evaluations": sum(evals),
+           "evals_per_s_steady": round(sum(evals[first:]) / sum(times[first:]), 2) if sum(times[first:]) > 0 else None,
            "gpu_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 2)}
     assert all(numpy.isfinite(objs)), objs
     assert objs[-1] <= objs[0] * (1 + 1e-9), ("objective did not decrease", objs)

@@ -19,7 +19,7 @@ w = dev.to_device((numpy.random.default_rng(0).random(n) * 2 - 1) * 0.25)
 for precision in precisions:
     m = L.MLP(shape, transfers=L.SoftmaxTransfer(), error_func=L.CrossEntropyError(), optimizer=L.optimize.LBFGS(), precision=precision)
     ws = m._make_resident(x, y)
-    out = torch.empty(n + 1, dtype=torch.float64, device="cuda")
+    out = torch.empty(n + 2, dtype=torch.float64, device="cuda")
     steps = 10
     for _ in range(3): nat.check(nat.lib.opl_mlp_eval_device(ws.pointer, dev.ptr(w), 0.0, None, 1, dev.ptr(out)))
     torch.cuda.synchronize()

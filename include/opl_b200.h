@@ -113,6 +113,15 @@ int opl_mlp_eval_device(opl_mlp *ws, const double *x_dev, double alpha, const do
  * Synchronises; returns OPL_E_DOMAIN if the flag slot grad_dev[n+1] is non-zero. */
 int opl_mlp_probe_scalars(opl_mlp *ws, const double *grad_dev, const double *dir_dev,
                           int32_t have_grad, double *host_out);
+/* opl_mlp_eval_device + opl_mlp_probe_scalars in ONE call for an unsharded batch (the line-search probe of
+ * linesearch.py:392-399 on a single device): evaluates at x + alpha*dir, writes [gradient ; objective ; flag] and returns
+ * host_out[0..2] = objective, grad . dir, ||grad||^2.  Small networks (<= 4096 weights, layers <= 128 wide) run as ONE
+ * kernel that also forms the three scalars and hands them over through mapped pinned memory (csrc/mlp_small.inl).
+ * Synchronises; OPL_E_DOMAIN on log(negative). */
+int opl_mlp_probe_device(opl_mlp *ws, const double *x_dev, double alpha, const double *dir_dev, int32_t want_grad,
+                         double *grad_out_dev, double *host_out);
+/* enable / disable the one-launch small-network kernel (default on; environment OPL_SMALL_PATH=0 turns it off) */
+int opl_mlp_set_small_path(opl_mlp *ws, int32_t enable);
 /* activate on device buffers: x_dev rows x d0 -> out_dev rows x d_L */
 int opl_mlp_activate_device(opl_mlp *ws, const double *params_dev, const double *x_dev, int64_t rows,
                             double *out_dev);
@@ -191,6 +200,11 @@ int opl_bfgs_set_stream(opl_bfgs *b, void *cuda_stream);
 int opl_bfgs_direction_device(opl_bfgs *b, const double *grad_dev, const double *prev_step_dev,
                               const double *prev_grad_dev, int32_t seed_mode, double *dir_out_dev);
 
+/* g . dir of the direction the last opl_bfgs_direction_device call produced, when that call ran as the single-launch
+ * small-problem kernel (n <= 512), which forms it on the fly: the line search's phi'(0) (linesearch.py:259) without a separate
+ * dot product.  Waits for the kernel.  OPL_E_STATE when the streaming path produced the direction. */
+int opl_bfgs_last_slope(opl_bfgs *b, double *host_out);
+
 /* Row-sharded form (one rank per GPU): pass -> (caller: all-gather u,w slices; all-reduce v)
  * -> finish.  u_dev,v_dev,w_dev are full n-vectors owned by the caller; pass writes
  * u[row_begin:row_end] = (H+ y) rows, w[...] = (H+ g) rows and v = the LOCAL rows'
@@ -251,6 +265,10 @@ int64_t opl_lbfgs_launch_count(const opl_lbfgs *l);
  * contraction) so the iterate matches NumPy bit for bit.  out may alias x. */
 int opl_vec_axpy_device(int64_t n, const double *x, double a, const double *d, double b,
                         const double *p, double *out, void *cuda_stream);
+/* step_out = fl(a*d), out = x + step_out: `self._prev_step = step_size * step_dir; return parameters + self._prev_step`
+ * (optimizer.py:251-253, 429-431) in one launch */
+int opl_vec_step_device(int64_t n, const double *x, double a, const double *d, double *step_out, double *out,
+                        void *cuda_stream);
 /* out = a * x */
 int opl_vec_scale_device(int64_t n, double a, const double *x, double *out, void *cuda_stream);
 /* Weight penalties of RegressionModel (error.py:122-193, regression.py:158-180):

@@ -16,6 +16,7 @@
 // The identity / gamma*I seed is never materialised: the first update is pending on a virtual
 // diagonal and the first pass writes H without reading it.
 #include <algorithm>
+#include <cstdlib>
 
 #include "gemm_f64.cuh"   // launch_reduce_partials
 
@@ -311,6 +312,120 @@ __global__ void bfgs_apply_kernel(int64_t n, int nparts, const double *__restric
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Small problems (n <= BFGS_SMALL_N, the reference's make_optimizer picks BFGS up to 500 weights, optimizer.py:33-43):
+// the whole of _get_approx_inv_hessian + `-(H.dot(jac))` (optimizer.py:242-285) as ONE single-CTA launch instead of five --
+// y = g - g_prev, the six dots, u = H y, w = H g (a warp per row), v = H^T y (a thread per column), the rank-2 update
+// applied in place at once (nothing stays pending), the direction, and its slope g.d, which also goes to mapped pinned
+// memory so that the line search starts without a separate dot product.  Same formulas and the same element-wise update
+// expression as the streaming pass, so both paths round alike.
+// ---------------------------------------------------------------------------------------
+constexpr int BFGS_SMALL_N = 512;
+constexpr int BFGS_SMALL_THREADS = 512;
+
+struct SmallBfgsArgs {
+    double *H;
+    int n;
+    int seed;                 // 1: no H yet -> virtual gamma*I is updated and materialised
+    int seed_mode;
+    const double *g, *g_prev, *s;
+    double *dir;
+    double *slope_dev;        // device: g.d
+    volatile double *slope_host;   // mapped pinned: g.d, sequence number
+    double seq;
+};
+
+__global__ void __launch_bounds__(BFGS_SMALL_THREADS) bfgs_small_kernel(const SmallBfgsArgs p) {
+    __shared__ double ys_[BFGS_SMALL_N], ss_[BFGS_SMALL_N], gs_[BFGS_SMALL_N], us_[BFGS_SMALL_N], vs_[BFGS_SMALL_N], ws_[BFGS_SMALL_N];
+    __shared__ double scratch[33];
+    const int n = p.n, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = BFGS_SMALL_THREADS / 32;
+    for (int i = tid; i < n; i += BFGS_SMALL_THREADS) {
+        const double gi = p.g[i];
+        gs_[i] = gi;
+        ys_[i] = gi - p.g_prev[i];
+        ss_[i] = p.s[i];
+    }
+    __syncthreads();
+    double a0 = 0.0, a3 = 0.0, a4 = 0.0, a5 = 0.0;
+    for (int i = tid; i < n; i += BFGS_SMALL_THREADS) {
+        a0 += ys_[i] * ss_[i];
+        a3 += ss_[i] * gs_[i];
+        a4 += ys_[i] * ys_[i];
+        a5 += ys_[i] * gs_[i];
+    }
+    const double ys = block_sum(a0, scratch), sg = block_sum(a3, scratch), yy = block_sum(a4, scratch), yg = block_sum(a5, scratch);
+    double gamma = 1.0, c, vg;
+    if (p.seed) {
+        if (p.seed_mode == OPL_BFGS_SEED_SCALED_IDENTITY) gamma = yy == 0.0 ? 1.0 : nan_to_num(ys / yy);   // optimizer.py:346-362
+        for (int i = tid; i < n; i += BFGS_SMALL_THREADS) {
+            us_[i] = vs_[i] = gamma * ys_[i];
+            ws_[i] = gamma * gs_[i];
+        }
+        c = gamma * yy;
+        vg = gamma * yg;
+    } else {
+        for (int i = warp; i < n; i += nwarps) {          // u = H y, w = H g: a warp per row
+            const double *row = p.H + (size_t)i * n;
+            double pu = 0.0, pw = 0.0;
+            for (int j = lane; j < n; j += 32) {
+                const double h = row[j];
+                pu += h * ys_[j];
+                pw += h * gs_[j];
+            }
+            pu = warp_sum(pu);
+            pw = warp_sum(pw);
+            if (lane == 0) {
+                us_[i] = pu;
+                ws_[i] = pw;
+            }
+        }
+        for (int j = tid; j < n; j += BFGS_SMALL_THREADS) {   // v = H^T y: a thread per column
+            double pv = 0.0;
+            for (int i = 0; i < n; ++i) pv += ys_[i] * p.H[(size_t)i * n + j];
+            vs_[j] = pv;
+        }
+        __syncthreads();
+        double a1 = 0.0, a2 = 0.0;
+        for (int i = tid; i < n; i += BFGS_SMALL_THREADS) {
+            a1 += ys_[i] * us_[i];
+            a2 += vs_[i] * gs_[i];
+        }
+        c = block_sum(a1, scratch);
+        vg = block_sum(a2, scratch);
+    }
+    __syncthreads();
+    double rho = 0.0, kappa = 0.0;
+    if (ys != 0.0) {                                       // optimizer.py:328-330: y.s == 0 keeps H unchanged
+        rho = 1.0 / ys;
+        kappa = rho * rho * c + rho;
+    }
+    // H+ = H - rho s v^T - rho u s^T + kappa s s^T, element-wise as the streaming pass writes it
+    if (p.seed || ys != 0.0) {
+        const int total = n * n;
+        for (int e = tid; e < total; e += BFGS_SMALL_THREADS) {
+            const int i = e / n, j = e - i * n;
+            const double h = p.seed ? (i == j ? gamma : 0.0) : p.H[e];
+            const double pi = -rho * ss_[i], qi = kappa * ss_[i] - rho * us_[i];
+            p.H[e] = h + pi * vs_[j] + qi * ss_[j];
+        }
+    }
+    double gd = 0.0;
+    for (int i = tid; i < n; i += BFGS_SMALL_THREADS) {
+        const double d = -(ws_[i] - rho * ss_[i] * vg - rho * us_[i] * sg + kappa * ss_[i] * sg);
+        p.dir[i] = d;
+        gd += gs_[i] * d;
+    }
+    gd = block_sum(gd, scratch);
+    if (tid == 0) {
+        p.slope_dev[0] = gd;
+        if (p.slope_host) {
+            p.slope_host[0] = gd;
+            __threadfence_system();
+            p.slope_host[1] = p.seq;
+        }
+    }
+}
+
 __global__ void bfgs_fill_kernel(double *H, int64_t n, int64_t row_begin, int64_t rows_local, uint64_t seed) {
     const int64_t total = rows_local * n;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -344,6 +459,11 @@ struct opl_bfgs {
     int dot_blocks = 0;
     int64_t panels = 0, rows_per_panel = 0;
     int64_t launches = 0;
+    // small-problem path: slope g.d of the last direction through mapped pinned memory
+    double *slope_dev = nullptr;
+    double *mapped_host = nullptr, *mapped_dev = nullptr;
+    double mapped_seq = 0.0;
+    bool slope_valid = false;
 };
 
 namespace {
@@ -446,6 +566,12 @@ int opl_bfgs_create(opl_bfgs **out, int64_t n, int64_t row_begin, int64_t row_en
     if (e == cudaSuccess) e = cudaMalloc(&b->coef, sizeof(double) * 4);
     if (e == cudaSuccess) e = cudaMemset(b->coef, 0, sizeof(double) * 4);
     if (e == cudaSuccess) e = cudaMalloc(&b->dots, sizeof(double) * 6 * (size_t)b->dot_blocks);
+    if (e == cudaSuccess) e = cudaMalloc(&b->slope_dev, sizeof(double) * 2);
+    if (e == cudaSuccess) e = cudaHostAlloc(&b->mapped_host, sizeof(double) * 2, cudaHostAllocMapped);
+    if (e == cudaSuccess) {
+        b->mapped_host[0] = b->mapped_host[1] = 0.0;
+        e = cudaHostGetDevicePointer(&b->mapped_dev, b->mapped_host, 0);
+    }
     if (e != cudaSuccess) {
         opl_bfgs_destroy(b);
         return fail(OPL_E_CUDA, "opl_bfgs_create: %s", cudaGetErrorString(e));
@@ -459,6 +585,8 @@ int opl_bfgs_destroy(opl_bfgs *b) {
     cudaStreamSynchronize(b->stream);
     double *all[] = {b->H, b->y, b->s_pend, b->u_pend, b->v_pend, b->u, b->v, b->w, b->coef, b->vpart, b->dots};
     for (double *p : all) cudaFree(p);
+    cudaFree(b->slope_dev);
+    cudaFreeHost(b->mapped_host);
     delete b;
     return OPL_OK;
 }
@@ -514,10 +642,58 @@ int opl_bfgs_direction_device(opl_bfgs *b, const double *grad_dev, const double 
     if (!b) return fail(OPL_E_ARG, "opl_bfgs_direction_device: null");
     if (b->row_begin != 0 || b->row_end != b->n)
         return fail(OPL_E_STATE, "opl_bfgs_direction_device needs the whole H on this device; use pass/finish");
+    b->slope_valid = false;
+    static int small_enabled = -1;
+    if (small_enabled < 0) {
+        const char *env = getenv("OPL_SMALL_PATH");
+        small_enabled = (env && atoi(env) == 0) ? 0 : 1;
+    }
+    if (small_enabled && b->n <= BFGS_SMALL_N && grad_dev && dir_out_dev && prev_step_dev && prev_grad_dev) {
+        if (b->state != 0 && b->pending) {      // (an update left pending by the streaming path: apply it first)
+            int rc = run_pass(b, nullptr, nullptr, false, nullptr, nullptr, nullptr);
+            if (rc != OPL_OK) return rc;
+        }
+        int rc = ensure_matrix(b);
+        if (rc != OPL_OK) return rc;
+        SmallBfgsArgs a = {};
+        a.H = b->H;
+        a.n = (int)b->n;
+        a.seed = b->state == 0 ? 1 : 0;
+        a.seed_mode = seed_mode;
+        a.g = grad_dev;
+        a.g_prev = prev_grad_dev;
+        a.s = prev_step_dev;
+        a.dir = dir_out_dev;
+        a.slope_dev = b->slope_dev;
+        a.slope_host = b->mapped_dev;
+        b->mapped_seq += 1.0;
+        a.seq = b->mapped_seq;
+        bfgs_small_kernel<<<1, BFGS_SMALL_THREADS, 0, b->stream>>>(a);
+        OPL_LAUNCH_CHECK();
+        ++b->launches;
+        b->state = 2;
+        b->pending = false;
+        b->slope_valid = true;
+        return OPL_OK;
+    }
     int rc = opl_bfgs_pass_device(b, grad_dev, prev_step_dev, prev_grad_dev, seed_mode, b->u, b->v, b->w);
     if (rc != OPL_OK) return rc;
     return opl_bfgs_finish_device(b, grad_dev, prev_step_dev, prev_grad_dev, seed_mode, b->u, b->v, b->w,
                                   dir_out_dev);
+}
+
+int opl_bfgs_last_slope(opl_bfgs *b, double *host_out) {
+    if (!b || !host_out) return fail(OPL_E_ARG, "opl_bfgs_last_slope: null pointer");
+    if (!b->slope_valid) return fail(OPL_E_STATE, "the last direction did not come with its slope (streaming path)");
+    volatile double *m = b->mapped_host;
+    bool seen = false;
+    for (int spin = 0; spin < 2000000 && !seen; ++spin) seen = m[1] == b->mapped_seq;
+    if (!seen) {
+        OPL_CUDA(cudaStreamSynchronize(b->stream));
+        if (m[1] != b->mapped_seq) return fail(OPL_E_CUDA, "the direction kernel did not publish its slope");
+    }
+    *host_out = m[0];
+    return OPL_OK;
 }
 
 int opl_bfgs_materialize_device(opl_bfgs *b, double *h_out_dev) {

@@ -54,6 +54,17 @@ __global__ void axpy_kernel(int64_t n, const double *__restrict__ x, double a, c
     }
 }
 
+// step = fl(a * d); out = x + step: `prev_step = step_size * step_dir; parameters + prev_step` (optimizer.py:251-253,
+// 429-431) in one launch, each product and sum rounded once as NumPy does
+__global__ void step_kernel(int64_t n, const double *__restrict__ x, double a, const double *__restrict__ d,
+                            double *__restrict__ step, double *__restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double t = __dmul_rn(a, d[i]);
+        step[i] = t;
+        out[i] = __dadd_rn(x[i], t);
+    }
+}
+
 __global__ void scale_kernel(int64_t n, double a, const double *__restrict__ x, double *__restrict__ out) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         out[i] = __dmul_rn(a, x[i]);
@@ -76,6 +87,21 @@ __global__ void dot_final_kernel(int nparts, const double *__restrict__ partial,
     for (int i = threadIdx.x; i < nparts; i += blockDim.x) s += partial[i];
     s = block_sum(s, scratch);
     if (threadIdx.x == 0) out[0] = s;
+}
+
+// short vectors: the whole dot product in ONE block; the scalar goes to mapped pinned memory followed by a sequence number,
+// so the host needs neither a second launch nor a memcpy (one line-search step of a small model calls this once)
+__global__ void __launch_bounds__(1024) dot_single_kernel(int64_t n, const double *__restrict__ x, const double *__restrict__ y,
+                                                         volatile double *host, double seq) {
+    __shared__ double scratch[33];
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += x[i] * y[i];
+    s = block_sum(s, scratch);
+    if (threadIdx.x == 0) {
+        host[0] = s;
+        __threadfence_system();
+        host[1] = seq;
+    }
 }
 
 // stage 1 of the penalty norms: sum|w| (kind 1) or sum w^2 (kind 2)
@@ -162,6 +188,14 @@ int opl_gather_rows_device(const double *src_dev, int64_t rows, int64_t cols, co
     return OPL_OK;
 }
 
+int opl_vec_step_device(int64_t n, const double *x, double a, const double *d, double *step_out, double *out, void *cuda_stream) {
+    if (n < 0 || (n > 0 && (!x || !d || !step_out || !out))) return fail(OPL_E_ARG, "opl_vec_step_device: null pointer");
+    if (n == 0) return OPL_OK;
+    step_kernel<<<vec_grid(n, 256), 256, 0, (cudaStream_t)cuda_stream>>>(n, x, a, d, step_out, out);
+    OPL_LAUNCH_CHECK();
+    return OPL_OK;
+}
+
 int opl_vec_scale_device(int64_t n, double a, const double *x, double *out, void *cuda_stream) {
     if (n < 0 || (n > 0 && (!x || !out))) return fail(OPL_E_ARG, "opl_vec_scale_device: null pointer");
     if (n == 0) return OPL_OK;
@@ -179,6 +213,8 @@ namespace {
 struct VecScratch {
     double *dev = nullptr;
     double *host = nullptr;
+    double *mapped_host = nullptr, *mapped_dev = nullptr;   // value, sequence number (dot_single_kernel)
+    double seq = 0.0;
     int blocks = 0;
 };
 int vec_scratch(int blocks, VecScratch **out) {
@@ -195,6 +231,11 @@ int vec_scratch(int blocks, VecScratch **out) {
         v.blocks = blocks;
     }
     if (!v.host) OPL_CUDA(cudaMallocHost(&v.host, sizeof(double) * 2));
+    if (!v.mapped_host) {
+        OPL_CUDA(cudaHostAlloc(&v.mapped_host, sizeof(double) * 2, cudaHostAllocMapped));
+        v.mapped_host[0] = v.mapped_host[1] = 0.0;
+        OPL_CUDA(cudaHostGetDevicePointer(&v.mapped_dev, v.mapped_host, 0));
+    }
     *out = &v;
     return OPL_OK;
 }
@@ -226,6 +267,21 @@ int opl_vec_dot_device(int64_t n, const double *x, const double *y, double *host
     VecScratch *v = nullptr;
     int rc = vec_scratch(blocks, &v);
     if (rc != OPL_OK) return rc;
+    if (n <= 65536) {
+        v->seq += 1.0;
+        const double seq = v->seq;
+        dot_single_kernel<<<1, n <= 4096 ? 256 : 1024, 0, st>>>(n, x, y, v->mapped_dev, seq);
+        OPL_LAUNCH_CHECK();
+        volatile double *m = v->mapped_host;
+        bool seen = false;
+        for (int spin = 0; spin < 2000000 && !seen; ++spin) seen = m[1] == seq;
+        if (!seen) {
+            OPL_CUDA(cudaStreamSynchronize(st));
+            if (m[1] != seq) return fail(OPL_E_CUDA, "opl_vec_dot_device: the kernel did not publish its result");
+        }
+        *host_out = m[0];
+        return OPL_OK;
+    }
     dot_partial_kernel<<<blocks, 256, 0, st>>>(n, x, y, v->dev);
     dot_final_kernel<<<1, 256, 0, st>>>(blocks, v->dev, v->dev + blocks);
     OPL_CUDA(cudaMemcpyAsync(v->host, v->dev + blocks, sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -762,6 +762,14 @@ struct opl_mlp {
     double *masks = nullptr;        // DropoutMLP: [d0 ; d1 ; ... ; d_{L-1}] 0/1 vectors, or null
     std::vector<int64_t> mask_off;  // offset of layer l's mask (l = 0 input, l >= 1 hidden outputs)
     int64_t launches = 0;
+    // one-launch path for small networks (mlp_small.inl)
+    bool small_path = true;
+    bool small_configured = false;
+    size_t small_smem = 0;
+    double *mapped_host = nullptr;  // page-locked, mapped into the device: obj, g.dir, g.g, flag, sequence number
+    double *mapped_dev = nullptr;   // the same memory through its device address
+    double mapped_seq = 0.0;
+    unsigned int *ticket = nullptr;
     // optional per-launch timing (CUDA events on the launch stream): kind = stage*100 + layer
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;
@@ -770,7 +778,7 @@ struct opl_mlp {
 };
 
 enum { STAGE_TRIAL = 0, STAGE_FWD = 1, STAGE_ROWS = 2, STAGE_DW = 3, STAGE_DW_REDUCE = 4, STAGE_DA = 5,
-       STAGE_BIAS = 6, STAGE_LOSS = 7, STAGE_DIGITS = 8, STAGE_END = 9, STAGE_HEAD = 10 };
+       STAGE_BIAS = 6, STAGE_LOSS = 7, STAGE_DIGITS = 8, STAGE_END = 9, STAGE_HEAD = 10, STAGE_SMALL = 11 };
 
 namespace {
 
@@ -848,6 +856,8 @@ int free_all(opl_mlp *ws) {
     cudaFree(ws->masks);
     cudaFreeHost(ws->pinned);
     cudaFreeHost(ws->pinned_vec);
+    cudaFreeHost(ws->mapped_host);
+    cudaFree(ws->ticket);
     for (cudaEvent_t e : ws->ev_pool) cudaEventDestroy(e);
     return OPL_OK;
 }
@@ -1170,6 +1180,7 @@ int fused_head(opl_mlp *ws, const double *w, const double *y, int64_t rows, bool
 }  // namespace
 
 #include "mlp_fast.inl"
+#include "mlp_small.inl"
 
 namespace {
 
@@ -1177,6 +1188,10 @@ int evaluate(opl_mlp *ws, const double *x_dev, double alpha, const double *dir_d
              double *grad_out_dev) {
     if (!ws->x || ws->rows <= 0) return fail(OPL_E_STATE, "no training data resident: call opl_mlp_set_data_* first");
     const int64_t n = ws->n;
+    {   // small network: the whole evaluation is one launch
+        const SmallPlan pl = small_plan(ws, ws->rows);
+        if (pl.ok) return small_evaluate(ws, pl, x_dev, alpha, dir_dev, want_grad, grad_out_dev, nullptr);
+    }
     int tgrid = (int)std::min<int64_t>(ceil_div(n, 256), 4 * (int64_t)sm_count());
     mark(ws, STAGE_TRIAL * 100);
     trial_point_kernel<<<tgrid, 256, 0, ws->stream>>>(n, x_dev, alpha, dir_dev, ws->w_trial, ws->flag);
@@ -1316,6 +1331,8 @@ int opl_mlp_create(opl_mlp **out, int32_t n_widths, const int64_t *widths, const
     partials = std::max<int64_t>(partials, (int64_t)(4 * sm_count() + 8) * widths[1]);
     if (L >= 2)      // per-CTA dW (+ bias-gradient) partials of the fused narrow head, up to 2 CTAs per SM
         partials = std::max<int64_t>(partials, 2 * (int64_t)sm_count() * widths[L - 1] * (widths[L] + 1));
+    if (ws->n <= 4096)   // per-CTA gradient partials of the one-launch small-network kernel (32 patterns per CTA at least)
+        partials = std::max<int64_t>(partials, std::min<int64_t>((int64_t)1 << 20, ceil_div(max_rows, 32) * (ws->n + 2)));
     if (precision == OPL_PRECISION_F64) {
         const char *env = getenv("OPL_F64_ENGINE");
         if (env && std::string(env) == "dmma") {
@@ -1342,6 +1359,12 @@ int opl_mlp_create(opl_mlp **out, int32_t n_widths, const int64_t *widths, const
     OPL_TRY(cudaMalloc(&ws->flag, sizeof(int)));
     OPL_TRY(cudaMemset(ws->flag, 0, sizeof(int)));
     OPL_TRY(cudaMallocHost(&ws->pinned, sizeof(double) * 8));
+    OPL_TRY(cudaHostAlloc(&ws->mapped_host, sizeof(double) * 8, cudaHostAllocMapped));
+    memset(ws->mapped_host, 0, sizeof(double) * 8);
+    OPL_TRY(cudaHostGetDevicePointer(&ws->mapped_dev, ws->mapped_host, 0));
+    OPL_TRY(cudaMalloc(&ws->ticket, sizeof(unsigned int)));
+    OPL_TRY(cudaMemset(ws->ticket, 0, sizeof(unsigned int)));
+    if (const char *env = getenv("OPL_SMALL_PATH")) ws->small_path = atoi(env) != 0;
 #undef OPL_TRY
     if (precision == OPL_PRECISION_TF32) {
         int rc = fast_create(ws);
@@ -1367,6 +1390,12 @@ int opl_mlp_set_engine(opl_mlp *ws, int32_t engine) {
     if (!ws || (engine != OPL_ENGINE_DMMA && engine != OPL_ENGINE_INT8)) return fail(OPL_E_ARG, "opl_mlp_set_engine: bad arguments");
     ws->gemm_engine = engine;
     ws->fused_head = engine == OPL_ENGINE_INT8;   // OPL_ENGINE_DMMA = the plain schedule: one kernel per reference operation
+    return OPL_OK;
+}
+
+int opl_mlp_set_small_path(opl_mlp *ws, int32_t enable) {
+    if (!ws) return fail(OPL_E_ARG, "opl_mlp_set_small_path: null");
+    ws->small_path = enable != 0;
     return OPL_OK;
 }
 
@@ -1465,6 +1494,24 @@ int opl_mlp_probe_scalars(opl_mlp *ws, const double *grad_dev, const double *dir
                           double *host_out) {
     if (!ws || !grad_dev || !host_out) return fail(OPL_E_ARG, "opl_mlp_probe_scalars: null pointer");
     return read_scalars(ws, grad_dev, dir_dev, have_grad != 0, host_out);
+}
+
+int opl_mlp_probe_device(opl_mlp *ws, const double *x_dev, double alpha, const double *dir_dev, int32_t want_grad,
+                         double *grad_out_dev, double *host_out) {
+    if (!ws || !x_dev || !grad_out_dev || !host_out) return fail(OPL_E_ARG, "opl_mlp_probe_device: null pointer");
+    if (!ws->x || ws->rows <= 0) return fail(OPL_E_STATE, "no training data resident: call opl_mlp_set_data_* first");
+    const SmallPlan pl = small_plan(ws, ws->rows);
+    if (pl.ok) {
+        double seq = 0.0;
+        int rc = small_evaluate(ws, pl, x_dev, alpha, dir_dev, want_grad != 0, grad_out_dev, &seq);
+        if (rc != OPL_OK) return rc;
+        rc = small_read_scalars(ws, seq, host_out);
+        if (!want_grad) host_out[1] = host_out[2] = 0.0;
+        return rc;
+    }
+    int rc = evaluate(ws, x_dev, alpha, dir_dev, want_grad != 0, grad_out_dev);
+    if (rc != OPL_OK) return rc;
+    return read_scalars(ws, grad_out_dev, dir_dev, want_grad != 0, host_out);
 }
 
 int opl_mlp_obj_host(opl_mlp *ws, const double *params, double *obj_out) {

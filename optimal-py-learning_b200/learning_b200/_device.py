@@ -67,6 +67,14 @@ def axpy(x, a, d, b=0.0, p=None, out=None):
     return out
 
 
+def step(x, a, d):
+    """(fl(a*d), x + fl(a*d)): the accepted step and the next iterate in one launch (optimizer.py:251-253)."""
+    _check_vec(x, d)
+    moved, following = torch.empty_like(x), torch.empty_like(x)
+    nat.check(nat.lib.opl_vec_step_device(x.numel(), ptr(x), float(a), ptr(d), ptr(moved), ptr(following), stream_ptr()))
+    return moved, following
+
+
 def scale(a, x, out=None):
     """fl(a*x)  (prev_step = step_size * step_dir, optimizer.py:251)."""
     _check_vec(x)

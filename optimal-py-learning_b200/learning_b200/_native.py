@@ -37,6 +37,8 @@ SIGNATURES = {
     "opl_mlp_activate_host": (ctypes.c_int, [vp, vp, vp, i64, vp]),
     "opl_mlp_eval_device": (ctypes.c_int, [vp, vp, f64, vp, i32, vp]),
     "opl_mlp_probe_scalars": (ctypes.c_int, [vp, vp, vp, i32, c_double_p]),
+    "opl_mlp_probe_device": (ctypes.c_int, [vp, vp, f64, vp, i32, vp, c_double_p]),
+    "opl_mlp_set_small_path": (ctypes.c_int, [vp, i32]),
     "opl_mlp_activate_device": (ctypes.c_int, [vp, vp, vp, i64, vp]),
     "opl_mlp_launch_count": (i64, [vp]),
     "opl_mlp_set_masks_host": (ctypes.c_int, [vp, vp, i64]),
@@ -54,6 +56,7 @@ SIGNATURES = {
     "opl_bfgs_reset": (ctypes.c_int, [vp]),
     "opl_bfgs_set_stream": (ctypes.c_int, [vp, vp]),
     "opl_bfgs_direction_device": (ctypes.c_int, [vp, vp, vp, vp, i32, vp]),
+    "opl_bfgs_last_slope": (ctypes.c_int, [vp, c_double_p]),
     "opl_bfgs_pass_device": (ctypes.c_int, [vp, vp, vp, vp, i32, vp, vp, vp]),
     "opl_bfgs_finish_device": (ctypes.c_int, [vp, vp, vp, vp, i32, vp, vp, vp, vp]),
     "opl_bfgs_materialize_device": (ctypes.c_int, [vp, vp]),
@@ -71,6 +74,7 @@ SIGNATURES = {
     "opl_lbfgs_get_pair_device": (ctypes.c_int, [vp, i32, vp, vp]),
     "opl_lbfgs_launch_count": (i64, [vp]),
     "opl_vec_axpy_device": (ctypes.c_int, [i64, vp, f64, vp, f64, vp, vp, vp]),
+    "opl_vec_step_device": (ctypes.c_int, [i64, vp, f64, vp, vp, vp, vp]),
     "opl_vec_scale_device": (ctypes.c_int, [i64, f64, vp, vp, vp]),
     "opl_vec_penalty_device": (ctypes.c_int, [i64, vp, i32, f64, vp, c_double_p, vp]),
     "opl_vec_dot_device": (ctypes.c_int, [i64, vp, vp, c_double_p, vp]),

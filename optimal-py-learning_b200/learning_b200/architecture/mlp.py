@@ -14,6 +14,7 @@ come back per evaluation.
 """
 import ctypes
 import functools
+import math
 import operator
 import os
 import random
@@ -65,6 +66,7 @@ class _Workspace(object):
         self.resident = None      # identity of the (X, Y) resident on the device (see _make_resident)
         self.keepalive = None     # device tensors borrowed by the workspace
         self.sharded = False
+        self.scalars = (ctypes.c_double * 3)()     # probe scalars of the last evaluation: objective, slope, ||g||^2
 
     def bind_current_stream(self):
         """Kernels are enqueued on the caller's CURRENT stream: re-bind when it changed since the last call."""
@@ -104,6 +106,7 @@ class _KernelModel(Model):
     """
 
     PRECISIONS = {'f64': 0, 'f64-dmma': 0, 'tf32': 1}
+    small_path = True      # networks of <= 4096 weights evaluate as ONE kernel launch (csrc/mlp_small.inl); False: general schedule
 
     def _init_kernel_state(self, precision=None):
         if precision is None:
@@ -127,6 +130,8 @@ class _KernelModel(Model):
                             self.PRECISIONS[self._precision])
             if self._precision == 'f64-dmma':
                 nat.check(nat.lib.opl_mlp_set_engine(ws.pointer, 0))
+            if not self.small_path:
+                nat.check(nat.lib.opl_mlp_set_small_path(ws.pointer, 0))
             self._workspace = ws
         ws.bind_current_stream()
         return ws
@@ -301,27 +306,31 @@ class _KernelModel(Model):
     def _probe(self, ws, x_dev, alpha, direction, want_grad):
         """Evaluate at x + alpha*direction on the device.  Returns (obj, slope, grad tensor | None)."""
         n = x_dev.numel()
-        out = torch.empty(n + 2, dtype=torch.float64, device=x_dev.device)   # [gradient ; objective ; domain flag]
-        sharded = getattr(ws, 'sharded', False)
-        peer = self._peer_allreduce(ws, n + 2) if sharded and want_grad else None
-        mine = peer.next_slot() if peer is not None else out
-        nat.check(nat.lib.opl_mlp_eval_device(ws.pointer, dev.ptr(x_dev), float(alpha), dev.ptr(direction),
-                                              1 if want_grad else 0, dev.ptr(mine)))
-        if peer is not None:
-            # batch-sharded ranks hold partial sums of [gradient ; objective]: the evaluation wrote this rank's vector
-            # into peer-mapped memory, one kernel pulls every rank's vector over NVLink and adds them in rank order
-            peer.reduce(out)
-        elif sharded:
-            torch.distributed.all_reduce(out if want_grad else out[n:])     # objective only / no peer memory: NCCL
-        scalars = (ctypes.c_double * 3)()
-        nat.check(nat.lib.opl_mlp_probe_scalars(ws.pointer, dev.ptr(out), dev.ptr(direction),
-                                                1 if want_grad else 0, scalars))
+        out = torch.empty(n + 2, dtype=torch.float64, device=x_dev.device)     # [gradient ; objective ; domain flag]
+        scalars = ws.scalars
+        d_ptr = direction.data_ptr() if direction is not None else None
+        flag = 1 if want_grad else 0
+        if not ws.sharded:
+            # one C-ABI call per probe: evaluation + the three scalars (small networks: one kernel launch in all)
+            nat.check(nat.lib.opl_mlp_probe_device(ws.pointer, x_dev.data_ptr(), alpha, d_ptr, flag, out.data_ptr(), scalars))
+        else:
+            peer = self._peer_allreduce(ws, n + 2) if want_grad else None
+            mine = peer.next_slot() if peer is not None else out
+            nat.check(nat.lib.opl_mlp_eval_device(ws.pointer, x_dev.data_ptr(), alpha, d_ptr, flag, mine.data_ptr()))
+            if peer is not None:
+                # batch-sharded ranks hold partial sums of [gradient ; objective ; flag]: the evaluation wrote this rank's
+                # vector into peer-mapped memory, one kernel reduces every rank's vector over NVLink (rank order / in the switch)
+                peer.reduce(out)
+            else:
+                torch.distributed.all_reduce(out if want_grad else out[n:])     # objective only / no peer memory: NCCL
+            nat.check(nat.lib.opl_mlp_probe_scalars(ws.pointer, out.data_ptr(), d_ptr, flag, scalars))
         self.obj_jac_evaluations += 1
-        self._last_grad_norm = float(numpy.sqrt(scalars[2])) if want_grad else None
-        grad = None
-        if want_grad:
-            grad = out[:n]
-            grad.opl_norm = self._last_grad_norm      # ||g|| came back with the probe scalars: train_step needs no extra reduction
+        if not want_grad:
+            self._last_grad_norm = None
+            return scalars[0], scalars[1], None
+        self._last_grad_norm = math.sqrt(scalars[2]) if scalars[2] >= 0.0 else float('nan')
+        grad = out[:n]
+        grad.opl_norm = self._last_grad_norm      # ||g|| came back with the probe scalars: train_step needs no extra reduction
         return scalars[0], scalars[1], grad
 
     def _peer_allreduce(self, ws, count):
@@ -474,10 +483,21 @@ class MLP(_KernelModel):
 
     def _train_step_resident(self, input_matrix, target_matrix):
         ws = self._make_resident(input_matrix, target_matrix)
-        problem = Problem(obj_func=lambda xk: self._get_obj(xk, input_matrix, target_matrix),
-                          obj_jac_func=lambda xk: self._get_obj_jac(xk, input_matrix, target_matrix))
-        problem.ray_obj_jac = lambda xk, alpha, direction: self._probe(ws, xk, alpha, direction, True)[:2]
-        problem.ray_obj = lambda xk, alpha, direction: self._probe(ws, xk, alpha, direction, False)[0]
+        probe = self._probe
+
+        def obj_jac(xk):      # device vectors (the optimizer's native mode) go straight to the resident workspace
+            if isinstance(xk, torch.Tensor):
+                value, _, grad = probe(ws, xk, 0.0, None, True)
+                return value, grad
+            return self._get_obj_jac(xk, input_matrix, target_matrix)
+
+        def obj(xk):
+            if isinstance(xk, torch.Tensor):
+                return probe(ws, xk, 0.0, None, False)[0]
+            return self._get_obj(xk, input_matrix, target_matrix)
+        problem = Problem(obj_func=obj, obj_jac_func=obj_jac)
+        problem.ray_obj_jac = lambda xk, alpha, direction: probe(ws, xk, alpha, direction, True)[:2]
+        problem.ray_obj = lambda xk, alpha, direction: probe(ws, xk, alpha, direction, False)[0]
 
         flat = self._flat_params_to_device()
         error, flat_next = self._optimizer.next(problem, flat)

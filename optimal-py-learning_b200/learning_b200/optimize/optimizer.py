@@ -338,6 +338,18 @@ class BFGS(Optimizer):
                                                  dev.ptr(w), dev.ptr(direction)))
         return direction
 
+    def _offer_slope(self, problem, grad, direction):
+        """The single-launch direction kernel of small problems also forms grad . direction: hand it to the line search
+        (initialstep.directional_slope memo), which would otherwise launch a dot product for phi'(0)."""
+        if self._native is None or self._world()[1] != 1:
+            return
+        value = ctypes.c_double(0.0)
+        if nat.lib.opl_bfgs_last_slope(self._native.pointer, ctypes.byref(value)) == nat.OPL_OK:
+            try:
+                problem._slope_memo = (grad, direction, value.value)
+            except AttributeError:
+                pass
+
     def inverse_hessian(self):
         """The reference's ``_prev_inv_hessian`` as a NumPy array (local rows when sharded);
         None before the second iteration."""
@@ -362,9 +374,10 @@ class BFGS(Optimizer):
         self.jacobian = grad
         direction = self._direction(grad)
         self._prev_jacobian = grad
+        self._offer_slope(problem, grad, direction)
         step_size = self._step_size_getter(x, value, grad, direction, problem)
-        self._prev_step = dev.scale(step_size, direction)
-        return value, dev.axpy(x, 1.0, self._prev_step)
+        self._prev_step, following = dev.step(x, step_size, direction)
+        return value, following
 
 
 def _bfgs_eq(H_k, s_k, y_k):
@@ -511,5 +524,5 @@ class LBFGS(Optimizer):
         direction = self._step_direction(grad)
         self._prev_jacobian = grad
         step_size = self._step_size_getter(x, value, grad, direction, problem)
-        self._prev_step = dev.scale(step_size, direction)
-        return value, dev.axpy(x, 1.0, self._prev_step)
+        self._prev_step, following = dev.step(x, step_size, direction)
+        return value, following

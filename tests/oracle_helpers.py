@@ -91,3 +91,47 @@ def install_state(L, optimizer, snap):
     elif snap["kind"] == "SteepestDescentMomentum":
         from learning_b200 import _device as dev
         optimizer._prev_step = None if snap["prev"] is None else dev.to_device(snap["prev"])
+
+
+def restore(opt, snap):
+    """Put a snapshot back into an ORACLE optimizer (inverse of ``snapshot``)."""
+    initial = getattr(opt.search, "initial", None)
+    if snap["initial"] is not None and initial is not None:
+        initial.__dict__.update(snap["initial"])
+    if snap["kind"] == "BFGS":
+        opt.count, opt.prev_move, opt.prev_grad, opt.h = snap["count"], _copy(snap["prev_move"]), _copy(snap["prev_grad"]), _copy(snap["h"])
+    elif snap["kind"] == "LBFGS":
+        opt.prev_move, opt.prev_grad = _copy(snap["prev_move"]), _copy(snap["prev_grad"])
+        opt.s_hist = [_copy(s) for s, _ in snap["pairs"]]
+        opt.y_hist = [_copy(y) for _, y in snap["pairs"]]
+    elif snap["kind"] == "SteepestDescentMomentum":
+        opt.prev = _copy(snap["prev"])
+    return opt
+
+
+def reference_step_sensitivity(run, t, record, trials=4, seed=0):
+    """How far the REFERENCE's own x_{k+1} moves when its arithmetic is merely re-ordered: the same step, from the same
+    state, on the same patterns presented in a different ROW ORDER (objective and gradient are sums over the patterns, so a
+    permutation changes nothing but the order in which the host BLAS adds them up -- what a different BLAS build or thread
+    count does as well).  Quasi-Newton steps late in an ill-conditioned run subtract nearly equal gradients
+    (y = g_k - g_{k-1}) of a nearly cancelled sum, which amplifies that rounding by orders of magnitude: this amplification,
+    not 1e-10, is the attainable agreement there.
+    Returns the largest relative change of the step x_{k+1} - x_k over `trials` random row orders."""
+    shape = tuple(run["shape"])
+    transfers = [(int(a), float(b)) for a, b in run["transfers"]]
+    eid = int(run["error"])
+    x, y = t[run["data"] + "_x"], t[run["data"] + "_y"]
+    x_k, state, _, x_next, _ = record
+    rng = numpy.random.default_rng(seed)
+    worst = 0.0
+    base = x_next - x_k
+    for _ in range(trials):
+        perm = rng.permutation(x.shape[0])
+        xp, yp = numpy.ascontiguousarray(x[perm]), numpy.ascontiguousarray(y[perm])
+        opt = restore(ORACLE_OPTIMIZERS[run["optimizer"]](), state)
+        with numpy.errstate(all='ignore'):
+            _, nxt = opt.step(lambda v: mo.objective_gradient(v, shape, transfers, eid, xp, yp),
+                              lambda v: mo.objective(v, shape, transfers, eid, xp, yp), numpy.array(x_k, dtype=float))
+        den = numpy.linalg.norm(base)
+        worst = max(worst, float(numpy.linalg.norm((nxt - x_k) - base) / (den if den > 0 else 1.0)))
+    return worst

@@ -35,12 +35,14 @@ def _model(L, shape, transfers, eid, optimizer=None, precision=None):
 # ----------------------------------------------------------------------------------------
 # objective / gradient / activate
 # ----------------------------------------------------------------------------------------
-def test_objgrad_golden_cases_host_api(L, golden_meta, golden_objgrad):
+@pytest.mark.parametrize("small_path", [True, False])   # one-launch small-network kernel / general kernel schedule
+def test_objgrad_golden_cases_host_api(L, golden_meta, golden_objgrad, small_path):
     g = golden_objgrad
     for entry in golden_meta["objgrad"]:
         k = entry["key"]
         shape, transfers, eid = specs(entry)
         model = _model(L, shape, transfers, eid)
+        model.small_path = small_path
         obj = model._get_obj(g[k + "_w"].copy(), g[k + "_x"], g[k + "_y"])
         obj2, grad = model._get_obj_jac(g[k + "_w"].copy(), g[k + "_x"], g[k + "_y"])
         assert rel_err(obj, g[k + "_obj"]) <= TOL, (entry["name"], obj, float(g[k + "_obj"]))
@@ -209,6 +211,75 @@ def test_full_size_properties_config2(L):
     o_s, g_s = m2._get_obj_jac(w.copy(), x[sl], y[sl])
     want_o, want_g = mo.objective_gradient(w, shape, transfers, eid, x[sl], y[sl], literal_softmax=False)
     assert rel_err(o_s, want_o) <= TOL and rel_err(g_s, want_g) <= TOL
+
+
+@pytest.mark.parametrize("shape,transfers,eid", [
+    ((4, 2, 3), [(2, 0), (4, 0)], 1),                         # BASELINE config 1 (README iris MLP)
+    ((20, 16, 5), [(2, 0), (4, 0)], 1),
+    ((7, 9, 6, 4), [(1, 0), (3, 0.8), (0, 0)], 0),            # tanh / gaussian / linear + MSE
+    ((5, 8, 6, 3), [(4, 0), (2, 0), (4, 0)], 1),              # hidden softmax
+    ((12, 128, 10), [(2, 0), (0, 0)], 0),                     # widest layer the kernel takes, n = 2944
+    ((3, 1), [(0, 0)], 0),
+])
+@pytest.mark.parametrize("rows", [1, 33, 129, 1000, 5000])    # one partial CTA .. 40 CTAs folded by the last one
+def test_small_network_one_launch_kernel(L, shape, transfers, eid, rows):
+    """csrc/mlp_small.inl: trial point, forward, error, back-propagation, flat gradient, objective, slope and gradient norm
+    in ONE launch -- against the oracle (1e-10), against the general kernel schedule, and through the fused probe."""
+    import torch
+    from learning_b200 import _device as dev
+    rng = numpy.random.default_rng(rows + len(shape))
+    gen = mo.random_classification if eid == 1 else mo.random_regression
+    x, y = gen(rows, shape[0], shape[-1], rng)
+    w = mo.random_params(shape, rng)
+    want_obj, want_grad = mo.objective_gradient(w, shape, transfers, eid, x, y)
+    small = _model(L, shape, transfers, eid)
+    plain = _model(L, shape, transfers, eid)
+    plain.small_path = False
+    with small.resident(x, y):
+        l0 = nat_launches(small)
+        obj, grad = small._get_obj_jac(w.copy(), x, y)
+        assert nat_launches(small) - l0 == 1                   # ONE kernel per evaluation
+        assert rel_err(obj, want_obj) <= TOL and rel_err(grad, want_grad) <= TOL, (rel_err(obj, want_obj), rel_err(grad, want_grad))
+        assert rel_err(small._get_obj(w.copy(), x, y), want_obj) <= TOL
+        obj2, grad2 = small._get_obj_jac(w.copy(), x, y)
+        assert obj2 == obj and numpy.array_equal(grad2, grad)  # fixed-order fold of the CTA partials
+        # fused probe: scalars formed inside the same launch
+        d = rng.standard_normal(w.size)
+        ws = small._make_resident(x, y)
+        l0 = nat_launches(small)
+        val, slope, g = small._probe(ws, dev.to_device(w), 0.3, dev.to_device(d), True)
+        assert nat_launches(small) - l0 == 1
+        e_obj, e_grad = mo.objective_gradient(w + 0.3 * d, shape, transfers, eid, x, y)
+        assert rel_err(val, e_obj) <= TOL and rel_err(dev.to_host(g), e_grad) <= TOL
+        assert rel_err(slope, e_grad.dot(d)) <= 1e-9 and rel_err(g.opl_norm, numpy.linalg.norm(e_grad)) <= 1e-10
+    obj_p, grad_p = plain._get_obj_jac(w.copy(), x, y)
+    assert rel_err(obj, obj_p) <= 1e-12 and rel_err(grad, grad_p) <= 1e-11
+
+
+def nat_launches(model):
+    from learning_b200 import _native as nat
+    return nat.lib.opl_mlp_launch_count(model._workspace.pointer)
+
+
+def test_small_network_kernel_keeps_reference_edge_semantics(L):
+    """Saturated softmax (target probability underflows to 0: log(0) -> -1.797e308, Y/A -> 1.797e308 and a zero Jacobian row)
+    and log(negative) -> FloatingPointError on the one-launch path (error.py:89-116)."""
+    rng = numpy.random.default_rng(9)
+    shape, transfers = (6, 8, 4), [(1, 0), (4, 0)]
+    x, y = mo.random_classification(200, 6, 4, rng)
+    w = mo.random_params(shape, rng)
+    w[8 + 48:] *= 4000.0
+    with numpy.errstate(all="ignore"):
+        want_obj, want_grad = mo.objective_gradient(w, shape, transfers, 1, x, y, literal_softmax=True)
+    assert want_obj > 1e300
+    model = _model(L, shape, transfers, 1)
+    obj, grad = model._get_obj_jac(w.copy(), x, y)
+    assert rel_err(obj, want_obj) <= TOL and rel_err(grad, want_grad) <= 1e-9
+    lin = _model(L, shape, [(1, 0), (0, 0)], 1)
+    with pytest.raises(FloatingPointError):
+        lin._get_obj_jac(mo.random_params(shape, rng), x, y)
+    with pytest.raises(FloatingPointError):
+        lin._get_obj(mo.random_params(shape, rng), x, y)
 
 
 def test_full_size_config2_against_oracle(L):
@@ -617,44 +688,63 @@ def _teacher_forced_step(L, run, t, record):
     return e_obj, e_x, e_step, e_h
 
 
+STEP_TOL = 1e-9          # relative agreement of the step x_{k+1} - x_k where the reference's own step is well conditioned
+
+
+def _step_gate(run, t, record, e_step):
+    """A teacher-forced step passes when it reproduces the reference's step to STEP_TOL, or -- where the reference's own step
+    is ill conditioned -- to within 100x what the reference's step itself moves under 1e-15 relative perturbations of its
+    gradients (oracle_helpers.reference_step_sensitivity).  Returns (passed, sensitivity or None)."""
+    if e_step <= STEP_TOL:
+        return True, None
+    from oracle_helpers import reference_step_sensitivity
+    sens = reference_step_sensitivity(run, t, record)
+    return e_step <= 100.0 * sens, sens
+
+
 def test_teacher_forced_steps_with_optimizer_state_match_reference(L, golden_meta, golden_traces):
     """Stateful teacher forcing (SURVEY section 7 hard part (i); reference optimize/optimizer.py:234-285,414-508): for
     EVERY recorded step k of all ten reference traces, load the reference's x_k and its optimizer state before the step
     (H_{k-1} / (s, y) history, previous step and gradient, iteration counter, initial-step memory), take one step and
-    compare the objective, x_{k+1} and H_k with the reference's to 1e-10.  The oracle that supplies the states reproduces
-    the golden traces bit for bit (tests/test_oracle.py), and that is re-asserted here."""
+    compare the objective and H_k to 1e-10, x_{k+1} to 1e-10 and the step x_{k+1} - x_k itself to 1e-9 -- except on steps
+    where the reference's own step is ill conditioned (late iris L-BFGS steps subtract nearly equal gradients), where the
+    bound is 100x the reference's measured sensitivity to rounding-level gradient perturbations.  The oracle that supplies
+    the states reproduces the golden traces bit for bit (tests/test_oracle.py), which is re-asserted here."""
     from oracle_helpers import oracle_trace_with_states
     t = golden_traces
     report = {}
     for run in golden_meta["traces"]:
         records = oracle_trace_with_states(run, t)
         xs = t[run["key"] + "_xs"]
-        worst = [0.0, 0.0, 0.0, 0.0]
-        flips = []
+        worst = dict(obj=0.0, x=0.0, step=0.0, H=0.0)
+        conditioned = []
         for k, record in enumerate(records):
             assert rel_err(record[3], xs[k + 1]) <= 1e-9, (run["key"], k)       # the oracle IS the reference trace
             e_obj, e_x, e_step, e_h = _teacher_forced_step(L, run, t, record)
-            if e_step > 1e-6:
-                flips.append((k, e_step))
-            worst = [max(worst[0], e_obj), max(worst[1], e_x), max(worst[2], e_step if e_step <= 1e-6 else 0.0),
-                     max(worst[3], e_h or 0.0)]
             assert e_obj <= TOL, (run["key"], k, e_obj)
             assert e_h is None or e_h <= TOL, (run["key"], k, e_h)
-        report[run["key"]] = dict(steps=len(records), obj=worst[0], x=worst[1], step=worst[2], H=worst[3], flips=flips)
-    print("teacher-forced steps (worst relative errors per trace):", report)
-    for key, r in report.items():
-        # a line-search branch decided by a difference below the evaluation's own rounding may flip: at most one such step
-        # per trace is tolerated and it is reported; every other step must reproduce x_{k+1} to 1e-10
-        assert len(r["flips"]) <= 1, (key, r)
-        assert r["x"] <= TOL or r["flips"], (key, r)
-        assert r["step"] <= 1e-6, (key, r)
+            passed, sens = _step_gate(run, t, record, e_step)
+            assert passed, (run["key"], k, "step error %.2e, reference sensitivity %.2e" % (e_step, sens))
+            if sens is None:
+                assert e_x <= TOL, (run["key"], k, e_x)
+                worst["step"] = max(worst["step"], e_step)
+                worst["x"] = max(worst["x"], e_x)
+            else:
+                conditioned.append((k, float("%.2e" % e_step), float("%.2e" % sens)))
+            worst["obj"] = max(worst["obj"], e_obj)
+            worst["H"] = max(worst["H"], e_h or 0.0)
+        report[run["key"]] = dict(steps=len(records), ill_conditioned_steps=conditioned, **worst)
+    print("teacher-forced steps (worst relative errors per trace; ill-conditioned steps as (k, step error, reference sensitivity)):", report)
+    total = sum(r["steps"] for r in report.values())
+    ill = sum(len(r["ill_conditioned_steps"]) for r in report.values())
+    assert ill <= 0.05 * total, report                 # the conditioning clause is the exception, not the rule
 
 
 def test_optimizer_iterate_sequences_match_reference(L, golden_meta, golden_traces):
     """Free-running: the same iterate sequence as the reference over the recorded steps (up to 50).  Gate: every trace
-    agrees to 1e-8 on ALL its steps, or up to its first line-search branch flip, which must come after step 20 and must be a
-    flip (not an arithmetic defect): the teacher-forced step from the reference's state at that very step reproduces the
-    reference's x_{k+1}.  Branch decisions are chaotic on ill-conditioned problems."""
+    agrees to 1e-8 on ALL its steps, or up to a first divergence that must come after step 20 and must be conditioning, not
+    an arithmetic defect: the teacher-forced step from the reference's own state at that very step passes the step gate
+    (1e-9, or 100x the reference's sensitivity to rounding-level gradient perturbations).  SURVEY.md section 7."""
     from oracle_helpers import oracle_trace_with_states
     t = golden_traces
     report = {}
@@ -681,9 +771,10 @@ def test_optimizer_iterate_sequences_match_reference(L, golden_meta, golden_trac
         assert agree >= 20 and "_mid_" not in run["key"] and "_reg_" not in run["key"], (run["key"], agree, report)
         record = oracle_trace_with_states(run, t)[agree]
         e_obj, e_x, e_step, e_h = _teacher_forced_step(L, run, t, record)
-        print("first divergence of %s at step %d: teacher-forced from the reference's state there: obj %.1e x %.1e"
-              % (run["key"], agree, e_obj, e_x))
-        assert e_obj <= TOL and e_x <= 1e-8, (run["key"], agree, e_obj, e_x)
+        passed, sens = _step_gate(run, t, record, e_step)
+        print("first divergence of %s at step %d: teacher-forced from the reference's state there: obj %.1e, step %.1e, "
+              "reference sensitivity %s" % (run["key"], agree, e_obj, e_step, sens))
+        assert e_obj <= TOL and passed, (run["key"], agree, e_obj, e_step, sens)
 
 
 def test_checkpoint_mid_training_continues_the_same_sequence(L, golden_meta, golden_traces):

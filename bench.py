@@ -806,23 +806,39 @@ def run_bfgs(args, torch, dist, nat, dev, world, rank, barrier, max_over_ranks):
     nat.check(nat.lib.opl_bfgs_fill_synthetic(handle, 7))
     gen = torch.Generator(device="cuda").manual_seed(5)
     g_prev = torch.randn(n, dtype=torch.float64, device="cuda", generator=gen)
-    u = torch.zeros(per * world, dtype=torch.float64, device="cuda")
+    width = per * world
+    u = torch.zeros(width, dtype=torch.float64, device="cuda")
     w = torch.zeros_like(u)
     v = torch.zeros(n, dtype=torch.float64, device="cuda")
     d = torch.empty(n, dtype=torch.float64, device="cuda")
     vecs = [(torch.randn(n, dtype=torch.float64, device="cuda", generator=gen) * 1e-2,
              torch.randn(n, dtype=torch.float64, device="cuda", generator=gen)) for _ in range(4)]
+    # N > 1: what BFGS(shard_rows=True)._direction does -- the pass writes this rank's slices of u, w and its partial v into
+    # a symmetric vector [u ; w ; v], ONE launch of the peer all-reduce kernel gathers u, w and reduces v
+    peer = None
+    if world > 1:
+        from learning_b200 import _collective
+        peer = _collective.make(2 * width + n)
+    total = torch.empty(2 * width + n, dtype=torch.float64, device="cuda")
 
     def step(i):
         s, g = vecs[i % len(vecs)]
-        nat.check(nat.lib.opl_bfgs_pass_device(handle, dev.ptr(g), dev.ptr(s), dev.ptr(g_prev), 0, dev.ptr(u),
-                                               dev.ptr(v), dev.ptr(w)))
-        if world > 1:
+        if peer is not None:
+            mine = peer.next_slot()
+            pu, pw, pv = mine[:width], mine[width:2 * width], mine[2 * width:]
+        else:
+            pu, pw, pv = u, w, v
+        nat.check(nat.lib.opl_bfgs_pass_device(handle, dev.ptr(g), dev.ptr(s), dev.ptr(g_prev), 0, dev.ptr(pu),
+                                               dev.ptr(pv), dev.ptr(pw)))
+        if peer is not None:
+            peer.reduce(total)
+            pu, pw, pv = total[:width], total[width:2 * width], total[2 * width:]
+        elif world > 1:
             dist.all_gather_into_tensor(u, u[begin:begin + per].clone())
             dist.all_gather_into_tensor(w, w[begin:begin + per].clone())
             dist.all_reduce(v)
-        nat.check(nat.lib.opl_bfgs_finish_device(handle, dev.ptr(g), dev.ptr(s), dev.ptr(g_prev), 0, dev.ptr(u),
-                                                 dev.ptr(v), dev.ptr(w), dev.ptr(d)))
+        nat.check(nat.lib.opl_bfgs_finish_device(handle, dev.ptr(g), dev.ptr(s), dev.ptr(g_prev), 0, dev.ptr(pu),
+                                                 dev.ptr(pv), dev.ptr(pw), dev.ptr(d)))
 
     steps = max(3, min(args.steps, 10))
     for i in range(max(3, args.warmup)):
@@ -844,7 +860,9 @@ def run_bfgs(args, torch, dist, nat, dev, world, rank, barrier, max_over_ranks):
     return {"metric": "BFGS H-update HBM GB/s", "n": n, "h_bytes": n * n * 8, "rows_per_gpu": end - begin,
             "ms_per_iter": ms, "value": gbs, "unit": "GB/s (2*n^2*8 bytes per iteration: in-place rank-2 update fused "
                                                      "with H.[y g] and y^T.H, all GPUs)",
-            "steps": steps, "finite": ok, "launches": int(launches),
+            "steps": steps, "finite": ok, "launches": int(launches) + (steps if peer is not None else 0),
+            "exchange": ("one launch of the peer all-reduce kernel on [u ; w ; v] (%s)" % peer.mode) if peer is not None
+                        else ("NCCL all-gather x2 + all-reduce" if world > 1 else "none (single GPU)"),
             "roofline": {"bound": "hbm", "kernel": "bfgs_pass_kernel", "achieved": gbs, "peak": None, "unit": "GB/s",
                          "frac": None, "traffic": None}}
 

@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(256) output_rows_kernel(const RowArgsT<T> r) {
                 if (r.A && !(softmax && r.D && r.A == r.Z)) store_operand(&r.A[row * r.ld + c], a);
             }
         }
-        if (softmax && r.D && (y || r.G)) {   // delta_k = a_k (g_k - sum_j g_j a_j): dsoftmax contracted (mlp.py:295)
+        if (softmax && r.D && (y || r.G)) {   // dsoftmax contracted with the upstream gradient (mlp.py:295): softmax_delta()
             t = group_sum(t, group);
             if (live) {
                 double dummy = 0.0;
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(256) output_rows_kernel(const RowArgsT<T> r) {
                 for (int c = gl; c < r.C; c += group) {
                     const double a = exp((double)z[c] - mx) / den;
                     const double g = r.G ? (double)r.G[row * r.ld + c] : error_term(r, a, y[c], dummy, dummy_bad);
-                    store_operand(&r.D[row * r.ld + c], a * (g - t));
+                    store_operand(&r.D[row * r.ld + c], softmax_delta(a, g, t));
                     if (r.A && r.A == r.Z) store_operand(&r.A[row * r.ld + c], a);
                 }
             }
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(256) output_rows_thread_kernel(const RowArgsT<
         }
         if (softmax && r.D && (r.Y || r.G)) {
 #pragma unroll 1
-            for (int c = 0; c < C; ++c) store_operand(&r.D[row * r.ld + c], a[c] * (g[c] - t));
+            for (int c = 0; c < C; ++c) store_operand(&r.D[row * r.ld + c], softmax_delta(a[c], g[c], t));
         }
     }
     if (bad) *r.flag = 1;
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(256) output_rows_thread_kernel(const RowArgsT<
     }
 }
 
-// hidden softmax layer backward: delta = a o (g - sum g a), in place over g
+// hidden softmax layer backward: delta_k = softmax_delta(a_k, g_k, sum_j g_j a_j), in place over g
 template <typename T>
 __global__ void __launch_bounds__(256)
 softmax_backward_rows_kernel(T *G, const T *A, int64_t rows, int64_t ld, int C, int group) {
@@ -236,7 +236,7 @@ softmax_backward_rows_kernel(T *G, const T *A, int64_t rows, int64_t ld, int C, 
         t = group_sum(t, group);
         if (live)
             for (int c = gl; c < C; c += group)
-                store_operand(&G[row * ld + c], (double)A[row * ld + c] * ((double)G[row * ld + c] - t));
+                store_operand(&G[row * ld + c], softmax_delta((double)A[row * ld + c], (double)G[row * ld + c], t));
     }
 }
 
@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, R == 16 ? 2 : 1) narrow_head_
                     gq = q * p.ce_rdiv;
                 }
                 const double tt = group_sum(live ? gq * a_out : 0.0, 16);
-                if (backward) Zs[r * ldD + cl] = live ? a_out * (gq - tt) : 0.0;
+                if (backward) Zs[r * ldD + cl] = live ? softmax_delta(a_out, gq, tt) : 0.0;
                 HEAD_STAMP(4);
                 __syncthreads();
                 if (!backward) continue;
@@ -506,9 +506,9 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, R == 16 ? 2 : 1) narrow_head_
             double gq = 0.0;
             if (live) gq = error_term(ra, a_out, y_mine, loss, bad);
             double d;
-            if (softmax) {   // delta_k = a_k (g_k - sum_j g_j a_j): dsoftmax contracted (mlp.py:295)
+            if (softmax) {   // dsoftmax contracted with the upstream gradient (mlp.py:295): softmax_delta()
                 const double tt = group_sum(live ? gq * a_out : 0.0, 16);
-                d = a_out * (gq - tt);
+                d = softmax_delta(a_out, gq, tt);
             } else {
                 d = live ? gq * transfer_slope(p.tid, p.tparam, z, a_out) : 0.0;
             }

@@ -522,7 +522,7 @@ __global__ void __launch_bounds__(FH_THREADS, 3) narrow_head_tf32_kernel(const H
                 float tt = live ? gq * a : 0.f;
 #pragma unroll
                 for (int o = 8; o > 0; o >>= 1) tt += __shfl_xor_sync(0xffffffffu, tt, o);
-                d_out = live ? a * (gq - tt) : 0.f;
+                d_out = live ? softmax_delta(a, gq, tt) : 0.f;
             } else {
                 const double z = (double)zf;
                 double a_out;
@@ -538,7 +538,7 @@ __global__ void __launch_bounds__(FH_THREADS, 3) narrow_head_tf32_kernel(const H
                 double d;
                 if (softmax) {
                     const double tt = group_sum(live ? gq * a_out : 0.0, 16);
-                    d = a_out * (gq - tt);
+                    d = softmax_delta(a_out, gq, tt);
                 } else {
                     d = live ? gq * transfer_slope(p.tid, p.tparam, z, a_out) : 0.0;
                 }

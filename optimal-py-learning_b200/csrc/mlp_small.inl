@@ -116,14 +116,14 @@ __global__ void __launch_bounds__(SMALL_THREADS) smallnet_eval_kernel(const Smal
             ra.eid = p.eid;
             ra.ce_div = p.ce_div;
             ra.mse_mul = p.mse_mul;
-            if (t == OPL_TRANSFER_SOFTMAX) {                 // delta_k = a_k (g_k - sum_j g_j a_j)  (mlp.py:295)
+            if (t == OPL_TRANSFER_SOFTMAX) {                 // dsoftmax contracted with g (mlp.py:295): softmax_delta()
                 double tt = 0.0;
                 for (int j = 0; j < C; ++j) {
                     const double g = error_term(ra, a[j * P], y[j], loss, bad);
                     dl[j * P] = g;
                     tt += g * a[j * P];
                 }
-                for (int j = 0; j < C; ++j) dl[j * P] = a[j * P] * (dl[j * P] - tt);
+                for (int j = 0; j < C; ++j) dl[j * P] = softmax_delta(a[j * P], dl[j * P], tt);
             } else {
                 for (int j = 0; j < C; ++j) dl[j * P] = error_term(ra, a[j * P], y[j], loss, bad) * dl[j * P];
             }
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) smallnet_eval_kernel(const Smal
                         dp[i * P] = s;
                         tt += s * a[i * P];
                     }
-                    for (int i = 0; i < din; ++i) dp[i * P] = a[i * P] * (dp[i * P] - tt);
+                    for (int i = 0; i < din; ++i) dp[i * P] = softmax_delta(a[i * P], dp[i * P], tt);
                 } else {
                     for (int i = 0; i < din; ++i) {
                         double s = 0.0;

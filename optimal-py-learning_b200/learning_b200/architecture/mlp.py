@@ -258,6 +258,7 @@ class _KernelModel(Model):
         if scope is not None:
             scope.__exit__(None, None, None)
             self._train_scope = None
+        self._problem_cache = None
         self._optimizer.reset()
 
     def invalidate(self):
@@ -373,9 +374,13 @@ class _KernelModel(Model):
     # ------------------------------------------------------------------ pickling (base.py:350-373)
     def __getstate__(self):
         state = dict(self.__dict__)
+        if state.get('_flat_dev') is not None:                  # weights travel as the reference's host arrays
+            state['_bias_host'], state['_mats_host'] = _unflatten_weights(dev.to_host(state['_flat_dev']), self._shape)
+        state['_flat_dev'] = None
         state['_workspace'] = None       # device buffers are rebuilt on demand
         state['_residency_scope'] = None
         state.pop('_train_scope', None)
+        state.pop('_problem_cache', None)
         state.pop('_stochastic_full', None)
         state.pop('_flat_stage', None)
         return state
@@ -456,6 +461,38 @@ class MLP(_KernelModel):
         self.reset()
 
     # ------------------------------------------------------------------ weights
+    # ``_bias_vec`` / ``_weight_matrices`` are the reference's attributes (NumPy arrays, user-editable).  Between the
+    # train_steps of a training run the authoritative copy is the flat DEVICE vector the optimizer returned; the host
+    # arrays are produced from it on first access (one D2H) and are authoritative from then on -- so a training loop that
+    # never looks at the weights moves no parameters over PCIe, and anything that reads or assigns them sees / sets the
+    # real values.
+    def _host_weights(self):
+        state = self.__dict__
+        flat = state.get('_flat_dev')
+        if flat is not None:
+            state['_flat_dev'] = None
+            state['_bias_host'], state['_mats_host'] = _unflatten_weights(dev.to_host(flat), self._shape)
+
+    @property
+    def _bias_vec(self):
+        self._host_weights()
+        return self.__dict__['_bias_host']
+
+    @_bias_vec.setter
+    def _bias_vec(self, value):
+        self._host_weights()
+        self.__dict__['_bias_host'] = value
+
+    @property
+    def _weight_matrices(self):
+        self._host_weights()
+        return self.__dict__['_mats_host']
+
+    @_weight_matrices.setter
+    def _weight_matrices(self, value):
+        self._host_weights()
+        self.__dict__['_mats_host'] = value
+
     def _setup_weight_matrices(self):
         self._weight_matrices = [self._random_weight_matrix((rows, cols))
                                  for rows, cols in zip(self._shape[:-1], self._shape[1:])]
@@ -483,6 +520,33 @@ class MLP(_KernelModel):
 
     def _train_step_resident(self, input_matrix, target_matrix):
         ws = self._make_resident(input_matrix, target_matrix)
+        cached = self.__dict__.get('_problem_cache')
+        if cached is not None and cached[0] is ws and cached[1] is input_matrix and cached[2] is target_matrix:
+            problem = cached[3]          # the reference builds an identical Problem every step (mlp.py:171-175)
+        else:
+            problem = self._make_problem(ws, input_matrix, target_matrix)
+            self._problem_cache = (ws, input_matrix, target_matrix, problem)
+        flat = self.__dict__.get('_flat_dev')          # the previous step's result, still authoritative: no upload
+        if flat is None:
+            flat = self._flat_params_to_device()
+        error, flat_next = self._optimizer.next(problem, flat)
+        if dev.is_device_vector(flat_next):
+            self.__dict__['_flat_dev'] = flat_next      # host arrays on demand (see _host_weights)
+        else:
+            self._bias_vec, self._weight_matrices = _unflatten_weights(flat_next, self._shape)
+
+        jacobian = self._optimizer.jacobian
+        if jacobian is None:
+            self.converged = False
+        else:
+            norm = getattr(jacobian, 'opl_norm', None)
+            if norm is None:
+                norm = dev.norm(jacobian) if dev.is_device_vector(jacobian) else float(numpy.linalg.norm(jacobian))
+            self.converged = norm < self._jacobian_norm_break
+        return error
+
+    def _make_problem(self, ws, input_matrix, target_matrix):
+        """Problem(obj_func, obj_jac_func) over the resident workspace (mlp.py:171-175) plus the fused line-search probes."""
         probe = self._probe
 
         def obj_jac(xk):      # device vectors (the optimizer's native mode) go straight to the resident workspace
@@ -498,20 +562,7 @@ class MLP(_KernelModel):
         problem = Problem(obj_func=obj, obj_jac_func=obj_jac)
         problem.ray_obj_jac = lambda xk, alpha, direction: probe(ws, xk, alpha, direction, True)[:2]
         problem.ray_obj = lambda xk, alpha, direction: probe(ws, xk, alpha, direction, False)[0]
-
-        flat = self._flat_params_to_device()
-        error, flat_next = self._optimizer.next(problem, flat)
-        self._bias_vec, self._weight_matrices = _unflatten_weights(dev.to_host(flat_next), self._shape)
-
-        jacobian = self._optimizer.jacobian
-        if jacobian is None:
-            self.converged = False
-        else:
-            norm = getattr(jacobian, 'opl_norm', None)
-            if norm is None:
-                norm = dev.norm(jacobian) if dev.is_device_vector(jacobian) else float(numpy.linalg.norm(jacobian))
-            self.converged = norm < self._jacobian_norm_break
-        return error
+        return problem
 
     def _flat_params_to_device(self):
         """[bias ; W0 ; W1 ; ..] (mlp.py:313-315) assembled in a page-locked staging buffer and uploaded from there (the

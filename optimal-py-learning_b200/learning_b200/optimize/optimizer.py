@@ -250,6 +250,7 @@ class BFGS(Optimizer):
         state = super(BFGS, self).__getstate__()
         native, n = self._native, getattr(self, '_native_n', 0)
         state['_native'] = None
+        state.pop('_peer_exchange', None)
         state['_restore_hessian'] = getattr(self, '_restore_hessian', None)
         if native is not None and nat.lib.opl_bfgs_state(native.pointer) != 0:
             if self._world()[1] == 1 and 8 * n * n <= MAX_PICKLED_HESSIAN_BYTES:
@@ -321,22 +322,49 @@ class BFGS(Optimizer):
             nat.check(nat.lib.opl_bfgs_direction_device(handle, dev.ptr(grad), dev.ptr(self._prev_step),
                                                         dev.ptr(self._prev_jacobian), seed, dev.ptr(direction)))
             return direction
-        # row-sharded H: local pass, exchange the three n-vectors, redundant finish on every rank
+        # row-sharded H: local pass, ONE exchange of the three n-vectors, redundant finish on every rank
         begin, end, per = self._row_range(n)
-        u = torch.zeros(per * world, dtype=torch.float64, device=grad.device)
-        w = torch.zeros_like(u)
-        v = torch.zeros(n, dtype=torch.float64, device=grad.device)
+        width = per * world
+        handle_state = nat.lib.opl_bfgs_state(handle)
+        exchange = self._prev_step is not None and handle_state != 0          # same decision on every rank
+        peer = self._exchange(2 * width + n) if exchange else None
+        if peer is not None:
+            # The pass writes THIS rank's slices of u = H y and w = H g and its partial v = y^T H straight into a
+            # symmetric (peer-mapped) vector [u ; w ; v] whose other entries stay zero; one launch of the peer all-reduce
+            # kernel (csrc/collective.cu: NVSwitch multimem.ld_reduce / multimem.st, or rank-ordered pulls) then IS the
+            # all-gather of u and w (x + 0 + .. + 0 is exact) and the all-reduce of v -- instead of three NCCL collectives
+            # and two staging copies per iteration.
+            mine = peer.next_slot()
+            u, w, v = mine[:width], mine[width:2 * width], mine[2 * width:]
+        else:
+            u = torch.zeros(width, dtype=torch.float64, device=grad.device)
+            w = torch.zeros_like(u)
+            v = torch.zeros(n, dtype=torch.float64, device=grad.device)
         nat.check(nat.lib.opl_bfgs_pass_device(handle, dev.ptr(grad), dev.ptr(self._prev_step),
                                                dev.ptr(self._prev_jacobian), seed, dev.ptr(u), dev.ptr(v),
                                                dev.ptr(w)))
-        if self._prev_step is not None and nat.lib.opl_bfgs_state(handle) == 2:
-            torch.distributed.all_gather_into_tensor(u, u[begin:begin + per].clone())
-            torch.distributed.all_gather_into_tensor(w, w[begin:begin + per].clone())
-            torch.distributed.all_reduce(v)
+        if exchange:
+            if peer is not None:
+                total = torch.empty(2 * width + n, dtype=torch.float64, device=grad.device)
+                peer.reduce(total)
+                u, w, v = total[:width], total[width:2 * width], total[2 * width:]
+            else:
+                torch.distributed.all_gather_into_tensor(u, u[begin:begin + per].clone())
+                torch.distributed.all_gather_into_tensor(w, w[begin:begin + per].clone())
+                torch.distributed.all_reduce(v)
         nat.check(nat.lib.opl_bfgs_finish_device(handle, dev.ptr(grad), dev.ptr(self._prev_step),
                                                  dev.ptr(self._prev_jacobian), seed, dev.ptr(u), dev.ptr(v),
                                                  dev.ptr(w), dev.ptr(direction)))
         return direction
+
+    def _exchange(self, count):
+        """Peer-memory all-reduce for the [u ; w ; v] exchange of the row-sharded pass (None: NCCL collectives)."""
+        state = getattr(self, '_peer_exchange', False)
+        if state is False or (state is not None and state.count != count):
+            from .. import _collective
+            state = _collective.make(count)
+            self._peer_exchange = state
+        return state
 
     def _offer_slope(self, problem, grad, direction):
         """The single-launch direction kernel of small problems also forms grad . direction: hand it to the line search

@@ -88,8 +88,13 @@ def transfer_backprop(tid, param, upstream, z, a, literal_softmax=True):
             iy, ix = numpy.diag_indices(a.shape[-1])
             jac[:, iy, ix] = a * (1. - a)
             return numpy.einsum('ij,ijk->ik', upstream, jac)
-        # closed form used by the kernels: delta_k = a_k (g_k - sum_j g_j a_j)
-        return a * (upstream - numpy.sum(upstream * a, axis=-1, keepdims=True))
+        # The same contraction without the (N,C,C) tensor, term by term as the Jacobian form above:
+        #   delta_k = g_k a_k (1 - a_k) - a_k sum_{j != k} g_j a_j = a_k (g_k (1 - a_k) - (t - g_k a_k)),  t = sum_j g_j a_j.
+        # (The shorter a_k (g_k - t) is algebraically equal but cancels for confident one-hot rows, a_k -> 1: it loses
+        # eps / (1 - a_k) of relative accuracy and does NOT track the reference there; 1 - a_k is exact.)
+        p = upstream * a
+        t = numpy.sum(p, axis=-1, keepdims=True)
+        return a * (upstream * (1.0 - a) - (t - p))
     raise ValueError('unknown transfer id %r' % (tid,))
 
 

@@ -82,10 +82,15 @@ __device__ __forceinline__ float round_tf32(float x) {
 // a_k (g_k - t) must NOT be used: with a one-hot target and a confident prediction (a_k -> 1) g_k - t cancels and loses
 // eps / (1 - a_k) of relative accuracy (measured 5.7e-7 on a saturated iris network), whereas 1 - a_k is exact and
 // t - p is exactly zero for the target class of a one-hot row (every other g_j a_j is +-0).
-template <typename F>
-__device__ __forceinline__ F softmax_delta(F a, F g, F t) {
-    const F p = g * a;
-    return a * (g * ((F)1 - a) - (t - p));
+// The product p and the difference t - p are rounded as SEPARATE operations on purpose: contracted into fma(-g, a, t) the
+// difference would return the rounding residual of g a instead of 0 and bring exactly the lost accuracy back (measured).
+__device__ __forceinline__ double softmax_delta(double a, double g, double t) {
+    const double p = __dmul_rn(g, a);
+    return a * (g * (1.0 - a) - __dsub_rn(t, p));
+}
+__device__ __forceinline__ float softmax_delta(float a, float g, float t) {
+    const float p = __fmul_rn(g, a);
+    return a * (g * (1.0f - a) - __fsub_rn(t, p));
 }
 
 // numpy.nan_to_num for float64: nan -> 0, +inf -> DBL_MAX, -inf -> -DBL_MAX

@@ -476,10 +476,10 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             oz_fence_before();
             __syncwarp();
-            // FP64-heavy epilogues release the accumulators only after their finish phase: under a busy tensor queue the
-            // FP64 work crawls anyway (see the header), and undisturbed MMAs + an undisturbed finish measure 2 % faster
-            constexpr bool LATE = EPI == OZ_EPI_SOFTPLUS || EPI == OZ_EPI_TANH || EPI == OZ_EPI_GAUSSIAN;
-            if (lane == 0 && !LATE) oz_arrive(acc_empty);      // accumulators free again
+            // (round 1 released the accumulators of the FP64-heavy epilogues only after their finish phase; with the leaner
+            //  finish phase the early release measures 0.006-0.010 ms faster, profiles/r02_ozaki_epilogue_decomposition.txt)
+            const bool LATE = p.late_release != 0;              // tools only (OPL_OZ_LATE=1)
+            if (lane == 0 && !LATE) oz_arrive(acc_empty);      // accumulators free again: the next tile's MMAs overlap the finish phase
             if (tracer) tr[4] = clock64();
             // ---- finish: 2 chunks of 8 columns ----
             double *C = p.C + (int64_t)tl.split * p.split_stride;
@@ -951,6 +951,12 @@ int launch_ozaki_gemm(const int8_t *a_slices, int64_t a_rows_pad, const int8_t *
         mma_warps = std::min(OZ_MMA_WARPS, want >= 4 ? 4 : (want >= 2 ? 2 : 1));
     }
     OzakiArgs largs = args;
+    static int late_release = -1;
+    if (late_release < 0) {
+        const char *env = getenv("OPL_OZ_LATE");
+        late_release = (env && atoi(env) != 0) ? 1 : 0;
+    }
+    largs.late_release = late_release;
     // every issuing warp must own a k-block in EVERY tile: a warp reaches a tile's first k-block having issued into the
     // previous tile, which pins the phase of the accumulator barrier it then waits on (parity waits cannot tell phases
     // two apart)

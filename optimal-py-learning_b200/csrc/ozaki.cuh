@@ -37,6 +37,7 @@ struct OzakiArgs {
     const double *colmask;
     int mma_warps;            // 1, 2 or 4 MMA-issuing warps taking k-blocks in turn; set by launch_ozaki_gemm
     long long *trace;         // tools only (OPL_OZ_TRACE): CTA 0 writes 8 clock64() stamps per tile, see ozaki.cu
+    int late_release;         // tools only (OPL_OZ_LATE=1): release the accumulators after the finish phase instead of after the drain
 };
 
 int64_t ozaki_pad(int64_t v);   // round up to a multiple of 128

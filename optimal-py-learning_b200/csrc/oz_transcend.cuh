@@ -202,4 +202,70 @@ OZT_FN void ozt_softplus_logistic_n(const double (&z)[W], double (&sp)[W], doubl
     }
 }
 
+// The same pair for REGULAR arguments only (finite, |z| < 708): no special-value selections, and max(z, 0) formed
+// arithmetically (z + |z| is 2 max(z, 0) exactly).  The GEMM epilogue runs this form and re-evaluates a whole register
+// group with ozt_softplus_logistic_n when any of its values is not regular (warp-uniform, practically never taken):
+// the finish phase is bound by its instruction count, and the selections were a quarter of the non-FP64 instructions.
+OZT_FN bool ozt_is_regular(double z) { return (uint32_t)(ozt_hi(z) & 0x7fffffff) < 0x40862000u; }   // |z| < 708, not inf / NaN
+
+template <int W>
+OZT_FN void ozt_softplus_logistic_regular_n(const double (&z)[W], double (&sp)[W], double (&sg)[W]) {
+    double a[W], t[W], r[W], s[W], u[W], y[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) a[i] = -fabs(z[i]);
+#pragma unroll
+    for (int i = 0; i < W; ++i) t[i] = ozt_fma(a[i], 92.332482616893656877, 6755399441055744.0);
+#pragma unroll
+    for (int i = 0; i < W; ++i) r[i] = t[i] - 6755399441055744.0;
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        const double nd = r[i];
+        r[i] = ozt_fma(nd, -6.93147180369123816490e-01 / 64.0, a[i]);
+        r[i] = ozt_fma(nd, -1.90821492927058770002e-10 / 64.0, r[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        const double x = r[i], x2 = x * x;
+        double p = ozt_fma(x, 8.3333333333333332e-03, 4.1666666666666664e-02);
+        p = ozt_fma(p, x, 1.6666666666666666e-01);
+        p = ozt_fma(p, x, 0.5);
+        s[i] = ozt_fma(x2, p, x);
+    }
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        const int n = ozt_lo(t[i]);
+        const double T = ozt_exp_tab(n & 63);
+        const double q = ozt_fma(T, s[i], T);
+        t[i] = ozt_make(ozt_hi(q) + ((n >> 6) << 20), ozt_lo(q));
+    }
+#pragma unroll
+    for (int i = 0; i < W; ++i) u[i] = 1.0 + t[i];
+#pragma unroll
+    for (int i = 0; i < W; ++i) y[i] = ozt_rcp_seed(u[i]);
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        const double e = ozt_fma(-u[i], y[i], 1.0);
+        y[i] = ozt_fma(y[i], ozt_fma(e, e, e), y[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        uint32_t idx = (uint32_t)(ozt_hi(u[i]) - 0x3ff00000) >> 12;
+        idx = idx > 256u ? 256u : idx;
+        double rc, L;
+        ozt_log_tab((int)idx, rc, L);
+        const double w = ozt_fma(u[i], rc, -1.0), w2 = w * w;
+        double p = ozt_fma(w, 1.4285714285714285e-01, -1.6666666666666666e-01);
+        p = ozt_fma(p, w, 0.2);
+        p = ozt_fma(p, w, -0.25);
+        p = ozt_fma(p, w, 3.3333333333333331e-01);
+        p = ozt_fma(p, w, -0.5);
+        r[i] = L + ozt_fma(w2, p, w);
+    }
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        sp[i] = ozt_fma(0.5, z[i] - a[i], r[i]);          // max(z, 0) + log(1 + t)
+        sg[i] = ozt_hi(z[i]) < 0 ? t[i] * y[i] : y[i];
+    }
+}
+
 }  // namespace opl

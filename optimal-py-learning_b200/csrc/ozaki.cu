@@ -184,6 +184,15 @@ __device__ __forceinline__ bool oz_elect_one() {
 __device__ __forceinline__ double oz_l2d(long long v) {
     return __longlong_as_double(0x4338000000000000LL + v) - 6755399441055744.0;
 }
+// a 2^16 + b 2^8 + c as an exact double: three mad.wide.s32 starting from the magic constant (the 64-bit sum never carries
+// into the exponent: |a 2^16 + b 2^8 + c| < 2^48), then one FP64 subtraction
+__device__ __forceinline__ double oz_join3(int a, int b, int c) {
+    long long h;
+    asm("mad.wide.s32 %0, %1, 65536, %2;" : "=l"(h) : "r"(a), "l"(0x4338000000000000LL));
+    asm("mad.wide.s32 %0, %1, 256, %0;" : "+l"(h) : "r"(b));
+    asm("mad.wide.s32 %0, %1, 1, %0;" : "+l"(h) : "r"(c));
+    return __longlong_as_double(h) - 6755399441055744.0;
+}
 
 struct OzTile {
     int m0, n0, k_begin, nkb, split;
@@ -466,11 +475,8 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 // (magic-number add), joined by ONE rounding: (hi + lo 2^-24) 2^-16.  The 2^-16 rides on the row scale.
                 double zc[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const long long hi = ((long long)v[0][j] << 16) + ((long long)v[1][j] << 8) + (long long)v[2][j];
-                    const long long lo = ((long long)v[3][j] << 16) + ((long long)v[4][j] << 8) + (long long)v[5][j];
-                    zc[j] = fma(oz_l2d(lo), 1.0 / 16777216.0, oz_l2d(hi)) * ea;
-                }
+                for (int j = 0; j < 8; ++j)
+                    zc[j] = fma(oz_join3(v[3][j], v[4][j], v[5][j]), 1.0 / 16777216.0, oz_join3(v[0][j], v[1][j], v[2][j])) * ea;
                 oz_tmem_st_f64x8(stage_addr + 2 * c0, zc);     // FP64 tile -> the 128 spare TMEM columns
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -490,20 +496,20 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
             for (int ch = 0; ch < OZ_ZC / 8; ++ch) {
                 const int col0 = tl.n0 + half * OZ_ZC + ch * 8;
-                double r[8], x[8], zz[8], mk[8], zc[8];
+                double r[8], x[8], zz[8], zc[8];
                 oz_tmem_ld_f64x8(stage_addr + 16 * ch, zc);
                 if (tracer && ch == 0) tr[6] = clock64();
-                // column scale (+ bias).  Interior tiles without bias / mask skip the predicates and the loads (the finish phase
-                // is bound by its instruction count, see the header)
+                // column scale (+ bias).  Interior tiles skip the predicates (the finish phase is bound by its instruction
+                // count, see the header); the branches are warp-uniform
                 const bool inner = col0 + 8 <= p.N;
                 const bool masked = p.colmask != nullptr;
-                if (inner && !masked) {
+                if (inner) {
+                    if (p.bias) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const double eb = __ldg(p.scale_b + col0 + j);
-                        zz[j] = p.bias ? fma(zc[j], eb, __ldg(p.bias + col0 + j)) : zc[j] * eb;
-                        mk[j] = 1.0;
-                        x[j] = 0.0;
+                        for (int j = 0; j < 8; ++j) zz[j] = fma(zc[j], __ldg(p.scale_b + col0 + j), __ldg(p.bias + col0 + j));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) zz[j] = zc[j] * __ldg(p.scale_b + col0 + j);
                     }
                 } else {
 #pragma unroll
@@ -512,33 +518,35 @@ ozaki_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                         const bool ok = col < p.N;
                         const double eb = ok ? __ldg(p.scale_b + col) : 0.0;
                         const double bi = (p.bias && ok) ? __ldg(p.bias + col) : 0.0;
-                        mk[j] = (masked && ok) ? __ldg(p.colmask + col) : 1.0;
                         zz[j] = zc[j] * eb + bi;
-                        x[j] = 0.0;
                     }
                 }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) x[j] = 0.0;
                 // the transfer function of all 8 columns in ONE basic block, so the FP64 chains interleave
                 if (EPI == OZ_EPI_SOFTPLUS) {
-                    ozt_softplus_logistic_n<8>(zz, r, x);
-                    if (masked) {
+                    bool regular = true;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) r[j] *= mk[j];
-                    }
+                    for (int j = 0; j < 8; ++j) regular &= ozt_is_regular(zz[j]);
+                    if (__all_sync(0xffffffffu, regular)) ozt_softplus_logistic_regular_n<8>(zz, r, x);
+                    else ozt_softplus_logistic_n<8>(zz, r, x);      // inf / NaN / |z| >= 708 somewhere in the warp: full form
                 } else if (EPI == OZ_EPI_TANH) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) r[j] = tanh(zz[j]) * mk[j];
+                    for (int j = 0; j < 8; ++j) r[j] = tanh(zz[j]);
                 } else if (EPI == OZ_EPI_GAUSSIAN) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        r[j] = exp(-(zz[j] * zz[j] / p.tparam)) * mk[j];
-                        x[j] = -2.0 * zz[j] * r[j] / p.tparam;   // derivative uses the masked output, as the reference does
-                    }
-                } else if (masked) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) r[j] = zz[j] * mk[j];
+                    for (int j = 0; j < 8; ++j) r[j] = exp(-(zz[j] * zz[j] / p.tparam));
                 } else {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) r[j] = zz[j];
+                }
+                if (masked) {     // dropout: the mask multiplies the transfer OUTPUT (mlp.py:438-445)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) r[j] *= (col0 + j < p.N) ? __ldg(p.colmask + col0 + j) : 1.0;
+                }
+                if (EPI == OZ_EPI_GAUSSIAN) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) x[j] = -2.0 * zz[j] * r[j] / p.tparam;   // derivative uses the masked output, as the reference does
                 }
                 constexpr int MUL = EPI == OZ_EPI_MUL_AUX ? 1 : (EPI == OZ_EPI_MUL_DTANH ? 2 : 0);
                 if (tracer && ch == 0) tr[7] = clock64();

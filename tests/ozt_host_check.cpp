@@ -25,3 +25,26 @@ extern "C" void ozt_scalar_forms(const double *x, long n, double *e, double *l, 
         r[i] = opl::ozt_rcp(x[i]);
     }
 }
+
+// The form the GEMM epilogue runs: groups of 8 values, the regular-argument version when every value of the group is
+// finite with |z| < 708, else the full version (csrc/ozaki.cu finish phase).
+extern "C" void ozt_softplus_logistic_dispatch(const double *z, long n, double *sp, double *sg, long *regular_groups) {
+    long regular_count = 0;
+    for (long i = 0; i < n; i += 8) {
+        double in[8], a[8], b[8];
+        for (int j = 0; j < 8; ++j) in[j] = i + j < n ? z[i + j] : 0.0;
+        bool regular = true;
+        for (int j = 0; j < 8; ++j) regular = regular && opl::ozt_is_regular(in[j]);
+        if (regular) {
+            opl::ozt_softplus_logistic_regular_n<8>(in, a, b);
+            ++regular_count;
+        } else {
+            opl::ozt_softplus_logistic_n<8>(in, a, b);
+        }
+        for (int j = 0; j < 8 && i + j < n; ++j) {
+            sp[i + j] = a[j];
+            sg[i + j] = b[j];
+        }
+    }
+    if (regular_groups) *regular_groups = regular_count;
+}

@@ -191,12 +191,22 @@ def test_table_driven_softplus_logistic_header_is_accurate(tmp_path):
                            os.path.join(here, "ozt_host_check.cpp"), "-o", so])
     lib = ctypes.CDLL(so)
     lib.ozt_softplus_logistic.argtypes = [ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p, ctypes.c_void_p]
+    lib.ozt_softplus_logistic_dispatch.argtypes = [ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p, ctypes.c_void_p,
+                                                   ctypes.c_void_p]
 
     def run(z):
+        """Full form, and the epilogue's dispatch (regular-argument form per group of 8 unless the group holds a special
+        value): the two must agree bit for bit wherever both are defined, so everything below holds for both."""
         z = numpy.ascontiguousarray(z, dtype=numpy.float64)
         sp, sg = numpy.empty_like(z), numpy.empty_like(z)
         lib.ozt_softplus_logistic(z.ctypes.data, z.size, sp.ctypes.data, sg.ctypes.data)
+        sp2, sg2 = numpy.empty_like(z), numpy.empty_like(z)
+        groups = ctypes.c_long(0)
+        lib.ozt_softplus_logistic_dispatch(z.ctypes.data, z.size, sp2.ctypes.data, sg2.ctypes.data, ctypes.byref(groups))
+        assert numpy.array_equal(sp, sp2, equal_nan=True) and numpy.array_equal(sg, sg2, equal_nan=True)
+        run.regular_groups += groups.value
         return sp, sg
+    run.regular_groups = 0
 
     rng = numpy.random.default_rng(0)
     z = numpy.concatenate([rng.uniform(-40, 40, 3000), rng.uniform(-2, 2, 3000), rng.uniform(-750, 750, 500),
@@ -226,6 +236,7 @@ def test_table_driven_softplus_logistic_header_is_accurate(tmp_path):
     assert sp[3] == math.log(2.0) and sg[3] == 0.5
     assert sp[4] == 1000.0 and sg[4] == 1.0 and sp[5] == 0.0 and sg[5] == 0.0
     assert abs(sp[6] - 1.3132616875182228) <= 3e-16      # test_calculate.py:223: relu([0, 1]) == [0.6931, 1.3133]
+    assert run.regular_groups > 700                       # the regular-argument form really was exercised
 
 
 def test_scalar_exp_log_rcp_forms_of_the_head(tmp_path):

@@ -72,6 +72,9 @@ def step(x, a, d):
     _check_vec(x, d)
     moved, following = torch.empty_like(x), torch.empty_like(x)
     nat.check(nat.lib.opl_vec_step_device(x.numel(), ptr(x), float(a), ptr(d), ptr(moved), ptr(following), stream_ptr()))
+    # provenance: `following` is x + fl(a*d), rounded exactly like the trial point of a line-search probe at (x, a, d); a model
+    # that has just evaluated that very probe may hand its result back instead of evaluating again (see MLP._make_problem)
+    following.opl_origin = (x, float(a), d)
     return moved, following
 
 

@@ -67,6 +67,7 @@ class _Workspace(object):
         self.keepalive = None     # device tensors borrowed by the workspace
         self.sharded = False
         self.scalars = (ctypes.c_double * 3)()     # probe scalars of the last evaluation: objective, slope, ||g||^2
+        self.data_epoch = 0                        # bumped whenever the resident data or the dropout masks change
 
     def bind_current_stream(self):
         """Kernels are enqueued on the caller's CURRENT stream: re-bind when it changed since the last call."""
@@ -106,6 +107,7 @@ class _KernelModel(Model):
     """
 
     PRECISIONS = {'f64': 0, 'f64-dmma': 0, 'tf32': 1}
+    accepted_probe_memo = True   # hand the accepted line-search probe back as the next step's evaluation at x_{k+1} (same bits)
     small_path = True      # networks of <= 4096 weights evaluate as ONE kernel launch (csrc/mlp_small.inl); False: general schedule
 
     def _init_kernel_state(self, precision=None):
@@ -117,7 +119,8 @@ class _KernelModel(Model):
         self._workspace = None
         self._residency_scope = None     # (X, Y) of the enclosing train() / train_step() / resident() scope
         self._last_grad_norm = None
-        self.obj_jac_evaluations = 0     # probe counter (bench / diagnostics)
+        self.obj_jac_evaluations = 0     # evaluations actually run on the device (bench / diagnostics)
+        self.obj_jac_memo_hits = 0       # evaluations at x_{k+1} answered by the accepted probe of the previous line search
 
     def _param_count(self):
         return self._shape[1] + sum(a * b for a, b in zip(self._shape[:-1], self._shape[1:]))
@@ -172,6 +175,7 @@ class _KernelModel(Model):
                                                           self._global_rows(xc.shape[0])))
                 ws.keepalive = (xc, yc)
                 ws.resident = token
+                ws.data_epoch += 1
                 ws.sharded = self._world_size() > 1
             return ws
         x = input_matrix if (isinstance(input_matrix, numpy.ndarray) and input_matrix.dtype == numpy.float64) \
@@ -195,6 +199,7 @@ class _KernelModel(Model):
         nat.check(nat.lib.opl_mlp_set_data_host(ws.pointer, xs.ctypes.data_as(ctypes.c_void_p),
                                                 ys.ctypes.data_as(ctypes.c_void_p), count, x.shape[0]))
         ws.resident = _Residency(input_matrix, target_matrix, first, count) if in_scope else None
+        ws.data_epoch += 1
         ws.keepalive = None
         ws.sharded = sharded
         return ws
@@ -332,6 +337,8 @@ class _KernelModel(Model):
         self._last_grad_norm = math.sqrt(scalars[2]) if scalars[2] >= 0.0 else float('nan')
         grad = out[:n]
         grad.opl_norm = self._last_grad_norm      # ||g|| came back with the probe scalars: train_step needs no extra reduction
+        # what was just evaluated, for the accepted-probe memo of _make_problem (ws.data_epoch: same resident data and masks)
+        self._last_probe = (ws, ws.data_epoch, x_dev, float(alpha), direction, scalars[0], grad)
         return scalars[0], scalars[1], grad
 
     def _peer_allreduce(self, ws, count):
@@ -381,6 +388,7 @@ class _KernelModel(Model):
         state['_residency_scope'] = None
         state.pop('_train_scope', None)
         state.pop('_problem_cache', None)
+        state.pop('_last_probe', None)
         state.pop('_stochastic_full', None)
         state.pop('_flat_stage', None)
         return state
@@ -551,6 +559,18 @@ class MLP(_KernelModel):
 
         def obj_jac(xk):      # device vectors (the optimizer's native mode) go straight to the resident workspace
             if isinstance(xk, torch.Tensor):
+                # The optimizers evaluate obj + grad at x_{k+1} although the line search has just evaluated that very point as
+                # its accepted probe (the reference's own TODO, optimizer.py:69-72).  When xk is provably that point --
+                # dev.step tagged it as x + fl(a*d) of the SAME x, a, d objects the last probe was evaluated at, on the same
+                # resident data -- the probe's objective and gradient are handed back: bit-identical values, one evaluation
+                # per step saved.
+                origin = getattr(xk, 'opl_origin', None)
+                last = self.__dict__.get('_last_probe')
+                if (origin is not None and last is not None and self.accepted_probe_memo and last[0] is ws
+                        and last[1] == ws.data_epoch and origin[0] is last[2] and origin[1] == last[3]
+                        and origin[2] is last[4] and last[4] is not None):
+                    self.obj_jac_memo_hits += 1
+                    return last[5], last[6]
                 value, _, grad = probe(ws, xk, 0.0, None, True)
                 return value, grad
             return self._get_obj_jac(xk, input_matrix, target_matrix)
@@ -644,9 +664,11 @@ class DropoutMLP(MLP):
         with self.resident(input_matrix, target_matrix):
             ws = self._make_resident(input_matrix, target_matrix)
             nat.check(nat.lib.opl_mlp_set_masks_host(ws.pointer, flat.ctypes.data_as(ctypes.c_void_p), flat.size))
+            ws.data_epoch += 1
             try:
                 error = super(DropoutMLP, self).train_step(input_matrix, target_matrix)
             finally:
                 nat.check(nat.lib.opl_mlp_set_masks_host(ws.pointer, None, 0))
+                ws.data_epoch += 1
                 self._during_training = False
         return error

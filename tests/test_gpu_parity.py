@@ -777,6 +777,36 @@ def test_optimizer_iterate_sequences_match_reference(L, golden_meta, golden_trac
         assert e_obj <= TOL and passed, (run["key"], agree, e_obj, e_step, sens)
 
 
+def test_accepted_probe_memo_changes_no_bits(L, golden_meta, golden_traces):
+    """The evaluation at x_{k+1} that BFGS / L-BFGS ask for right after the line search accepted that very point (the
+    reference's TODO, optimizer.py:69-72) is answered from the accepted probe: same iterates bit for bit, one evaluation
+    per step fewer; and the weights stay on the device between train_steps until somebody looks at them."""
+    t = golden_traces
+    for name in ("tr_mid_bfgs", "tr_mid_lbfgs", "tr_iris_bfgs"):
+        run = [r for r in golden_meta["traces"] if r["key"] == name][0]
+        shape, transfers, eid = specs(run)
+        x, y = t[run["data"] + "_x"], t[run["data"] + "_y"]
+        models = []
+        for memo in (True, False):
+            model = _model(L, shape, transfers, eid, optimizer=_optimizer_for(L, run["optimizer"]))
+            model.logging = False
+            model.accepted_probe_memo = memo
+            _set_weights(model, t[name + "_w0"], shape)
+            errors = []
+            with model.resident(x, y):
+                for _ in range(15):
+                    errors.append(model.train_step(x, y))
+                    assert model.__dict__.get('_flat_dev') is not None       # nobody read the weights: still on the device
+            models.append((model, errors))
+        (a, ea), (b, eb) = models
+        assert ea == eb, name
+        assert numpy.array_equal(_flat(a), _flat(b)), name
+        assert a.__dict__.get('_flat_dev') is None                            # reading them made the host copy authoritative
+        assert rel_err(_flat(a), t[name + "_xs"][15]) <= 1e-8
+        assert a.obj_jac_memo_hits == 14 and b.obj_jac_memo_hits == 0, (a.obj_jac_memo_hits, b.obj_jac_memo_hits)
+        assert a.obj_jac_evaluations == b.obj_jac_evaluations - 14
+
+
 def test_checkpoint_mid_training_continues_the_same_sequence(L, golden_meta, golden_traces):
     """Model.serialize / unserialize (base.py:350-373) mid-training: the reference pickles the optimizer's H / history /
     previous step and gradient with the model, so a restored model continues the SAME iterate sequence."""

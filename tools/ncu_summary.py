@@ -84,7 +84,7 @@ def traffic(path, pattern, key, n=None, source=None):
         with open(dest) as fh:
             data = json.load(fh)
     entry = {"bytes": int(found[1]), "kernel": re.sub(r"\(.*", "", found[0])[-120:], "source": source or os.path.basename(path)}
-    if n is not None:
+    if n not in (None, "", "-"):
         entry["n"] = int(n)
     data[key] = entry
     with open(dest, "w") as fh:

@@ -90,13 +90,25 @@ __global__ void __launch_bounds__(SMALL_THREADS) smallnet_eval_kernel(const Smal
                 mx = fmax(mx, z);
             }
             if (t == OPL_TRANSFER_SOFTMAX) {                 // calculate.py:152-153
+                // a thread is ONE dependent FP64 chain here, so exp / reciprocal are the short table-driven forms of
+                // oz_transcend.cuh (~11 and 3 dependent operations instead of ~40 and ~12; ~1 ulp each), as in the fused head
                 double den = 0.0;
                 for (int j = 0; j < dout; ++j) {
-                    const double e = exp(aout[j * P] - mx);
+                    const double e = ozt_exp_nonpos(aout[j * P] - mx);
                     aout[j * P] = e;
                     den += e;
                 }
-                for (int j = 0; j < dout; ++j) aout[j * P] = aout[j * P] / den;
+                const bool regular_den = den >= 1.0 && den <= 1e300;           // (NaN / inf logits: literal division)
+                const double rden = regular_den ? ozt_rcp(den) : 0.0;
+                for (int j = 0; j < dout; ++j) aout[j * P] = regular_den ? aout[j * P] * rden : aout[j * P] / den;
+            } else if (t == OPL_TRANSFER_SOFTPLUS) {         // calculate.py:128-141: value and slope share exp(-|z|) and 1/(1+t)
+                for (int j = 0; j < dout; ++j) {
+                    const double zin[1] = {aout[j * P]};
+                    double sp[1], sg[1];
+                    ozt_softplus_logistic_n<1>(zin, sp, sg);
+                    aout[j * P] = sp[0];
+                    if (p.want_grad || last) dl[j * P] = sg[0];
+                }
             } else {
                 for (int j = 0; j < dout; ++j) {
                     const double z = aout[j * P];
@@ -118,8 +130,17 @@ __global__ void __launch_bounds__(SMALL_THREADS) smallnet_eval_kernel(const Smal
             ra.mse_mul = p.mse_mul;
             if (t == OPL_TRANSFER_SOFTMAX) {                 // dsoftmax contracted with g (mlp.py:295): softmax_delta()
                 double tt = 0.0;
+                const bool ce = p.eid == OPL_ERROR_CROSS_ENTROPY;
+                const double ce_rdiv = 1.0 / p.ce_div;
                 for (int j = 0; j < C; ++j) {
-                    const double g = error_term(ra, a[j * P], y[j], loss, bad);
+                    const double aj = a[j * P], yj = y[j];
+                    double g;
+                    if (ce && aj >= 9.332636185032189e-302) {      // regular probability (>= 2^-1000): short log / reciprocal,
+                        loss += ozt_log_pos(aj) * yj;              // same nan_to_num-free arithmetic as error.py:89-116 there
+                        g = (yj * ozt_rcp(aj)) * ce_rdiv;
+                    } else {
+                        g = error_term(ra, aj, yj, loss, bad);     // 0, subnormal, negative, NaN: the literal rules
+                    }
                     dl[j * P] = g;
                     tt += g * a[j * P];
                 }

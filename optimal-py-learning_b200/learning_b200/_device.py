@@ -16,8 +16,17 @@ def is_device_vector(value):
     return isinstance(value, torch.Tensor)
 
 
+def current_stream_handle():
+    """cudaStream_t of the caller's current torch stream on the current device, as an int.  (torch.cuda.current_stream()
+    costs ~15 us of Python per call -- four of them were a third of a small model's train_step; the raw query is ~0.3 us.)"""
+    try:
+        return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
+    except AttributeError:       # a torch build without the raw query
+        return torch.cuda.current_stream().cuda_stream
+
+
 def stream_ptr():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return ctypes.c_void_p(current_stream_handle())
 
 
 def ptr(tensor):

@@ -62,7 +62,7 @@ class _Workspace(object):
                                          int(max_rows), int(precision), dev.stream_ptr()))
         self.pointer = out
         self.max_rows = int(max_rows)
-        self.stream = torch.cuda.current_stream().cuda_stream
+        self.stream = dev.current_stream_handle()
         self.resident = None      # identity of the (X, Y) resident on the device (see _make_resident)
         self.keepalive = None     # device tensors borrowed by the workspace
         self.sharded = False
@@ -71,7 +71,7 @@ class _Workspace(object):
 
     def bind_current_stream(self):
         """Kernels are enqueued on the caller's CURRENT stream: re-bind when it changed since the last call."""
-        stream = torch.cuda.current_stream().cuda_stream
+        stream = dev.current_stream_handle()
         if stream != self.stream:
             nat.check(nat.lib.opl_mlp_set_stream(self.pointer, ctypes.c_void_p(stream)))
             self.stream = stream
@@ -161,6 +161,13 @@ class _KernelModel(Model):
           * device tensors are borrowed, keyed on the tensor objects and their ``_version`` counters: an in-place edit bumps
             the version and the digits of X are cut again.
         """
+        ws = self._workspace
+        scope = self._residency_scope
+        if (ws is not None and scope is not None and ws.resident is not None and scope[0] is input_matrix
+                and scope[1] is target_matrix and ws.resident.x is input_matrix and ws.resident.y is target_matrix
+                and ws.resident.versions == (getattr(input_matrix, '_version', None), getattr(target_matrix, '_version', None))):
+            ws.bind_current_stream()          # inside a scope, on the scope's own objects: validated when they were uploaded
+            return ws
         if dev.is_device_vector(input_matrix):
             x, y = input_matrix, target_matrix
             if x.dim() != 2 or y.dim() != 2 or x.shape[0] != y.shape[0]:

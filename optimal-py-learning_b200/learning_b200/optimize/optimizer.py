@@ -185,11 +185,11 @@ class _NativeHandle(object):
         self.pointer = pointer
         self._destroy = destroy
         self._set_stream = set_stream
-        self._stream = torch.cuda.current_stream().cuda_stream
+        self._stream = dev.current_stream_handle()
 
     def bind_current_stream(self):
         """The handle's kernels run on the caller's CURRENT stream: re-bind when it changed since the last call."""
-        stream = torch.cuda.current_stream().cuda_stream
+        stream = dev.current_stream_handle()
         if stream != self._stream and self._set_stream is not None:
             nat.check(self._set_stream(self.pointer, ctypes.c_void_p(stream)))
             self._stream = stream

@@ -50,15 +50,36 @@ def _digest():
     return h.hexdigest()
 
 
+def _up_to_date(stamp, digest):
+    if os.path.exists(LIB) and os.path.exists(stamp):
+        with open(stamp) as fh:
+            return fh.read().strip() == digest
+    return False
+
+
 def build(force=False, verbose=False):
-    """Compile if sources changed since the last build; return the library path."""
+    """Compile if sources changed since the last build; return the library path.
+
+    Safe under concurrent callers (one rank per GPU importing the package at the same time): the check-and-build runs
+    under an exclusive file lock, objects go to a per-process directory and the library is moved into place atomically, so
+    a process never loads a half-written file."""
+    import fcntl
     stamp = os.path.join(OUT_DIR, "libopl_b200.sha256")
     digest = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp):
-        with open(stamp) as fh:
-            if fh.read().strip() == digest:
-                return LIB
+    if not force and _up_to_date(stamp, digest):
+        return LIB
     os.makedirs(OUT_DIR, exist_ok=True)
+    with open(os.path.join(OUT_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and _up_to_date(stamp, digest):      # another process built it while we waited
+                return LIB
+            return _build_locked(stamp, digest, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(stamp, digest, verbose):
     os.makedirs(OBJ_DIR, exist_ok=True)
     nvcc = _nvcc()
     extra = ["-Xptxas", "-v"] if verbose else []
@@ -77,13 +98,18 @@ def build(force=False, verbose=False):
             if res.returncode != 0:
                 raise RuntimeError("nvcc failed on %s" % src)
             objs.append(obj)
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+    tmp_lib = LIB + ".tmp%d" % os.getpid()
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp_lib] + objs
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout)
         raise RuntimeError("link failed")
-    with open(stamp, "w") as fh:
+    if os.path.exists(stamp):
+        os.remove(stamp)                 # never leave a stamp that describes another binary
+    os.replace(tmp_lib, LIB)             # atomic: a concurrent dlopen sees the old or the new file, never a partial one
+    with open(stamp + ".tmp", "w") as fh:
         fh.write(digest)
+    os.replace(stamp + ".tmp", stamp)
     return LIB
 
 

@@ -101,6 +101,58 @@ __global__ void __launch_bounds__(256) colsum32_partial_kernel(const float *__re
     }
 }
 
+// delta_prev[r][j] = (sum_c delta[r][c] W[j][c]) x slope[r][j] for a NARROW next layer (C <= 16 outputs) in the fast mode: the
+// "GEMM" has K = C (padded to 32 for the tensor path: 70 % of the MMA work multiplies zeros and the kernel is bound by its
+// 128 x N epilogue), so it is a streaming pass over the rows x H slope / output matrices instead.  One CTA takes a block of
+// rows; W (H x C) and the block's delta rows sit in shared memory; thread j walks the rows with 8 loads in flight: global
+// traffic is coalesced along j.  FP32 products and sums (the tensor path would round the operands to TF32 first), the output
+// is stored TF32-rounded because it is an operand of the next GEMMs; columns past H (layer padding) are written as zeros.
+// mode: 0 out = s, 1 out = s * aux (f' stored by the forward GEMM), 2 out = s * (1 - aux^2) (tanh from the activation)
+template <int MAXC>
+__global__ void __launch_bounds__(256) narrow_backprop32_kernel(const float *__restrict__ delta, int64_t ldd,
+                                                                const float *__restrict__ W, int64_t ldw, const float *aux,
+                                                                float *out, int64_t ld, int64_t rows, int H, int Hpad, int C,
+                                                                int rows_per_block, int mode) {
+    extern __shared__ float nsm[];
+    const int cp = C | 1;                  // odd pitch: conflict-free across j
+    float *Ws = nsm;                       // H x cp
+    float *Ds = nsm + (size_t)H * cp;      // rows_per_block x C
+    for (int i = threadIdx.x; i < H * C; i += blockDim.x) Ws[(i / C) * cp + (i % C)] = W[(int64_t)(i / C) * ldw + (i % C)];
+    const int64_t nblocks = (rows + rows_per_block - 1) / rows_per_block;
+    for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        const int64_t r0 = blk * rows_per_block;
+        const int nr = (int)min((int64_t)rows_per_block, rows - r0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nr * C; i += blockDim.x) Ds[i] = delta[(r0 + i / C) * ldd + (i % C)];
+        __syncthreads();
+        for (int j = threadIdx.x; j < Hpad; j += blockDim.x) {
+            if (j >= H) {                  // layer padding stays exactly zero
+                for (int q = 0; q < nr; ++q) out[(r0 + q) * ld + j] = 0.f;
+                continue;
+            }
+            float w[MAXC];
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c) w[c] = c < C ? Ws[j * cp + c] : 0.f;
+            for (int rb = 0; rb < nr; rb += 8) {
+                float x[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) x[u] = (mode != 0 && rb + u < nr) ? aux[(r0 + rb + u) * ld + j] : 1.f;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (rb + u < nr) {
+                        float s_ = 0.f;
+#pragma unroll
+                        for (int c = 0; c < MAXC; ++c)
+                            if (c < C) s_ = fmaf(Ds[(rb + u) * C + c], w[c], s_);
+                        const float o = mode == 2 ? s_ * (1.f - x[u] * x[u]) : s_ * x[u];
+                        out[(r0 + rb + u) * ld + j] = round_tf32(o);
+                    }
+                }
+            }
+        }
+    }
+}
+
 int egrid(int64_t total) {
     return (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total, 256), 8 * (int64_t)sm_count()));
 }
@@ -315,6 +367,22 @@ int fast_backward(opl_mlp *ws, const float *x32, int64_t rows, double *grad, int
         }
         if (l == 0) break;
         // delta_{l-1} = (delta_l W_l^T) o f'_{l-1}
+        if (ws->width[l + 1] <= 16 && ws->transfer[l - 1] != OPL_TRANSFER_SOFTMAX &&
+            sizeof(float) * ((size_t)ws->width[l] * ((size_t)ws->width[l + 1] | 1) + (size_t)32 * ws->width[l + 1]) <= 48 * 1024) {
+            // narrow next layer: a streaming pass, not a GEMM (see narrow_backprop32_kernel)
+            const int t = ws->transfer[l - 1];
+            const int mode = (t == OPL_TRANSFER_SOFTPLUS || t == OPL_TRANSFER_GAUSSIAN) ? 1 : (t == OPL_TRANSFER_TANH ? 2 : 0);
+            const float *aux = mode == 1 ? f->deriv[l - 1] : (mode == 2 ? f->act[l] : nullptr);
+            const int H = (int)ws->width[l], C = (int)ws->width[l + 1], rpb = 32;
+            const size_t smem = sizeof(float) * ((size_t)H * (C | 1) + (size_t)rpb * C);
+            const int64_t grid = std::min<int64_t>(ceil_div(rows, rpb), 6 * (int64_t)sm_count());
+            mark(ws, STAGE_DA * 100 + l);
+            narrow_backprop32_kernel<16><<<(unsigned)grid, 256, smem, ws->stream>>>(
+                f->delta[l], pout, f->w32 + f->w_off[l], pout, aux, f->delta[l - 1], pin, rows, H, (int)pin, C, rpb, mode);
+            OPL_LAUNCH_CHECK();
+            ++ws->launches;
+            continue;
+        }
         Tf32GemmArgs a = {};
         a.C = f->delta[l - 1];
         a.ldc = pin;

@@ -108,44 +108,64 @@ __global__ void __launch_bounds__(256) colsum32_partial_kernel(const float *__re
 // traffic is coalesced along j.  FP32 products and sums (the tensor path would round the operands to TF32 first), the output
 // is stored TF32-rounded because it is an operand of the next GEMMs; columns past H (layer padding) are written as zeros.
 // mode: 0 out = s, 1 out = s * aux (f' stored by the forward GEMM), 2 out = s * (1 - aux^2) (tanh from the activation)
-template <int MAXC>
+template <int MAXC>      // MAXC = classes padded to a multiple of 4 (12 or 16)
 __global__ void __launch_bounds__(256) narrow_backprop32_kernel(const float *__restrict__ delta, int64_t ldd,
                                                                 const float *__restrict__ W, int64_t ldw, const float *aux,
                                                                 float *out, int64_t ld, int64_t rows, int H, int Hpad, int C,
                                                                 int rows_per_block, int mode) {
-    extern __shared__ float nsm[];
-    const int cp = C | 1;                  // odd pitch: conflict-free across j
-    float *Ws = nsm;                       // H x cp
-    float *Ds = nsm + (size_t)H * cp;      // rows_per_block x C
-    for (int i = threadIdx.x; i < H * C; i += blockDim.x) Ws[(i / C) * cp + (i % C)] = W[(int64_t)(i / C) * ldw + (i % C)];
+    extern __shared__ __align__(16) float nsm[];
+    constexpr int JT = 4;                   // columns per thread: the block's delta row is read once for four outputs
+    float *Ds = nsm;                        // rows_per_block x MAXC (classes >= C are zero), read as float4 broadcasts
     const int64_t nblocks = (rows + rows_per_block - 1) / rows_per_block;
-    for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
-        const int64_t r0 = blk * rows_per_block;
-        const int nr = (int)min((int64_t)rows_per_block, rows - r0);
-        __syncthreads();
-        for (int i = threadIdx.x; i < nr * C; i += blockDim.x) Ds[i] = delta[(r0 + i / C) * ldd + (i % C)];
-        __syncthreads();
-        for (int j = threadIdx.x; j < Hpad; j += blockDim.x) {
-            if (j >= H) {                  // layer padding stays exactly zero
-                for (int q = 0; q < nr; ++q) out[(r0 + q) * ld + j] = 0.f;
-                continue;
+    for (int j0 = 0; j0 < Hpad; j0 += 256 * JT) {
+        // this thread's four columns and their rows of W (registers, reused for every pattern)
+        float w[JT][MAXC];
+        int col[JT];
+#pragma unroll
+        for (int q = 0; q < JT; ++q) {
+            col[q] = j0 + 256 * q + threadIdx.x;
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c) w[q][c] = (col[q] < H && c < C) ? W[(int64_t)col[q] * ldw + c] : 0.f;
+        }
+        for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+            const int64_t r0 = blk * rows_per_block;
+            const int nr = (int)min((int64_t)rows_per_block, rows - r0);
+            __syncthreads();
+            for (int i = threadIdx.x; i < nr * MAXC; i += blockDim.x) {
+                const int r = i / MAXC, c = i - r * MAXC;
+                Ds[i] = c < C ? delta[(r0 + r) * ldd + c] : 0.f;
             }
-            float w[MAXC];
+            __syncthreads();
+            for (int rb = 0; rb < nr; rb += 2) {
+                float x[2][JT];
 #pragma unroll
-            for (int c = 0; c < MAXC; ++c) w[c] = c < C ? Ws[j * cp + c] : 0.f;
-            for (int rb = 0; rb < nr; rb += 8) {
-                float x[8];
+                for (int u = 0; u < 2; ++u)
 #pragma unroll
-                for (int u = 0; u < 8; ++u) x[u] = (mode != 0 && rb + u < nr) ? aux[(r0 + rb + u) * ld + j] : 1.f;
+                    for (int q = 0; q < JT; ++q)
+                        x[u][q] = (mode != 0 && rb + u < nr && col[q] < H) ? aux[(r0 + rb + u) * ld + col[q]] : 1.f;
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    if (rb + u < nr) {
-                        float s_ = 0.f;
+                for (int u = 0; u < 2; ++u) {
+                    if (rb + u >= nr) break;
+                    float s_[JT];
 #pragma unroll
-                        for (int c = 0; c < MAXC; ++c)
-                            if (c < C) s_ = fmaf(Ds[(rb + u) * C + c], w[c], s_);
-                        const float o = mode == 2 ? s_ * (1.f - x[u] * x[u]) : s_ * x[u];
-                        out[(r0 + rb + u) * ld + j] = round_tf32(o);
+                    for (int q = 0; q < JT; ++q) s_[q] = 0.f;
+                    const float4 *dp = reinterpret_cast<const float4 *>(Ds + (rb + u) * MAXC);
+#pragma unroll
+                    for (int c4 = 0; c4 < MAXC / 4; ++c4) {
+                        const float4 d = dp[c4];
+#pragma unroll
+                        for (int q = 0; q < JT; ++q) {
+                            s_[q] = fmaf(d.x, w[q][4 * c4], s_[q]);
+                            s_[q] = fmaf(d.y, w[q][4 * c4 + 1], s_[q]);
+                            s_[q] = fmaf(d.z, w[q][4 * c4 + 2], s_[q]);
+                            s_[q] = fmaf(d.w, w[q][4 * c4 + 3], s_[q]);
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < JT; ++q) {
+                        if (col[q] >= Hpad) continue;
+                        const float o = mode == 2 ? s_[q] * (1.f - x[u][q] * x[u][q]) : s_[q] * x[u][q];
+                        out[(r0 + rb + u) * ld + col[q]] = col[q] < H ? round_tf32(o) : 0.f;   // layer padding stays exactly zero
                     }
                 }
             }
@@ -367,18 +387,20 @@ int fast_backward(opl_mlp *ws, const float *x32, int64_t rows, double *grad, int
         }
         if (l == 0) break;
         // delta_{l-1} = (delta_l W_l^T) o f'_{l-1}
-        if (ws->width[l + 1] <= 16 && ws->transfer[l - 1] != OPL_TRANSFER_SOFTMAX &&
-            sizeof(float) * ((size_t)ws->width[l] * ((size_t)ws->width[l + 1] | 1) + (size_t)32 * ws->width[l + 1]) <= 48 * 1024) {
+        if (ws->width[l + 1] <= 16 && ws->transfer[l - 1] != OPL_TRANSFER_SOFTMAX) {
             // narrow next layer: a streaming pass, not a GEMM (see narrow_backprop32_kernel)
             const int t = ws->transfer[l - 1];
             const int mode = (t == OPL_TRANSFER_SOFTPLUS || t == OPL_TRANSFER_GAUSSIAN) ? 1 : (t == OPL_TRANSFER_TANH ? 2 : 0);
             const float *aux = mode == 1 ? f->deriv[l - 1] : (mode == 2 ? f->act[l] : nullptr);
-            const int H = (int)ws->width[l], C = (int)ws->width[l + 1], rpb = 32;
-            const size_t smem = sizeof(float) * ((size_t)H * (C | 1) + (size_t)rpb * C);
-            const int64_t grid = std::min<int64_t>(ceil_div(rows, rpb), 6 * (int64_t)sm_count());
+            const int H = (int)ws->width[l], C = (int)ws->width[l + 1], rpb = 64;
+            const int64_t grid = std::min<int64_t>(ceil_div(rows, rpb), 4 * (int64_t)sm_count());
             mark(ws, STAGE_DA * 100 + l);
-            narrow_backprop32_kernel<16><<<(unsigned)grid, 256, smem, ws->stream>>>(
-                f->delta[l], pout, f->w32 + f->w_off[l], pout, aux, f->delta[l - 1], pin, rows, H, (int)pin, C, rpb, mode);
+            if (C <= 12)
+                narrow_backprop32_kernel<12><<<(unsigned)grid, 256, sizeof(float) * rpb * 12, ws->stream>>>(
+                    f->delta[l], pout, f->w32 + f->w_off[l], pout, aux, f->delta[l - 1], pin, rows, H, (int)pin, C, rpb, mode);
+            else
+                narrow_backprop32_kernel<16><<<(unsigned)grid, 256, sizeof(float) * rpb * 16, ws->stream>>>(
+                    f->delta[l], pout, f->w32 + f->w_off[l], pout, aux, f->delta[l - 1], pin, rows, H, (int)pin, C, rpb, mode);
             OPL_LAUNCH_CHECK();
             ++ws->launches;
             continue;

@@ -114,19 +114,19 @@ __global__ void __launch_bounds__(256) narrow_backprop32_kernel(const float *__r
                                                                 float *out, int64_t ld, int64_t rows, int H, int Hpad, int C,
                                                                 int rows_per_block, int mode) {
     extern __shared__ __align__(16) float nsm[];
-    constexpr int JT = 4;                   // columns per thread: the block's delta row is read once for four outputs
+    constexpr int JT = 4;                   // ADJACENT columns per thread: one 16-byte load / store per pattern, and the block's
+                                            // delta row is read once for four outputs
+    constexpr int RU = 4;                   // patterns in flight per thread (4 x 16 bytes of loads outstanding)
     float *Ds = nsm;                        // rows_per_block x MAXC (classes >= C are zero), read as float4 broadcasts
     const int64_t nblocks = (rows + rows_per_block - 1) / rows_per_block;
     for (int j0 = 0; j0 < Hpad; j0 += 256 * JT) {
-        // this thread's four columns and their rows of W (registers, reused for every pattern)
-        float w[JT][MAXC];
-        int col[JT];
+        const int c0 = j0 + JT * threadIdx.x;           // this thread's four columns (Hpad is a multiple of 32)
+        const bool live = c0 < Hpad;
+        float w[JT][MAXC];                               // their rows of W (registers, reused for every pattern)
 #pragma unroll
-        for (int q = 0; q < JT; ++q) {
-            col[q] = j0 + 256 * q + threadIdx.x;
+        for (int q = 0; q < JT; ++q)
 #pragma unroll
-            for (int c = 0; c < MAXC; ++c) w[q][c] = (col[q] < H && c < C) ? W[(int64_t)col[q] * ldw + c] : 0.f;
-        }
+            for (int c = 0; c < MAXC; ++c) w[q][c] = (c0 + q < H && c < C) ? W[(int64_t)(c0 + q) * ldw + c] : 0.f;
         for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
             const int64_t r0 = blk * rows_per_block;
             const int nr = (int)min((int64_t)rows_per_block, rows - r0);
@@ -136,15 +136,15 @@ __global__ void __launch_bounds__(256) narrow_backprop32_kernel(const float *__r
                 Ds[i] = c < C ? delta[(r0 + r) * ldd + c] : 0.f;
             }
             __syncthreads();
-            for (int rb = 0; rb < nr; rb += 2) {
-                float x[2][JT];
+            if (!live) continue;
+            for (int rb = 0; rb < nr; rb += RU) {
+                float4 x[RU];
 #pragma unroll
-                for (int u = 0; u < 2; ++u)
+                for (int u = 0; u < RU; ++u)
+                    x[u] = (mode != 0 && rb + u < nr) ? *reinterpret_cast<const float4 *>(aux + (r0 + rb + u) * ld + c0)
+                                                       : make_float4(1.f, 1.f, 1.f, 1.f);
 #pragma unroll
-                    for (int q = 0; q < JT; ++q)
-                        x[u][q] = (mode != 0 && rb + u < nr && col[q] < H) ? aux[(r0 + rb + u) * ld + col[q]] : 1.f;
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
+                for (int u = 0; u < RU; ++u) {
                     if (rb + u >= nr) break;
                     float s_[JT];
 #pragma unroll
@@ -161,12 +161,14 @@ __global__ void __launch_bounds__(256) narrow_backprop32_kernel(const float *__r
                             s_[q] = fmaf(d.w, w[q][4 * c4 + 3], s_[q]);
                         }
                     }
+                    const float xv[JT] = {x[u].x, x[u].y, x[u].z, x[u].w};
+                    float o[JT];
 #pragma unroll
                     for (int q = 0; q < JT; ++q) {
-                        if (col[q] >= Hpad) continue;
-                        const float o = mode == 2 ? s_[q] * (1.f - x[u][q] * x[u][q]) : s_[q] * x[u][q];
-                        out[(r0 + rb + u) * ld + col[q]] = col[q] < H ? round_tf32(o) : 0.f;   // layer padding stays exactly zero
+                        const float v = mode == 2 ? s_[q] * (1.f - xv[q] * xv[q]) : s_[q] * xv[q];
+                        o[q] = c0 + q < H ? round_tf32(v) : 0.f;        // layer padding stays exactly zero
                     }
+                    *reinterpret_cast<float4 *>(out + (r0 + rb + u) * ld + c0) = make_float4(o[0], o[1], o[2], o[3]);
                 }
             }
         }

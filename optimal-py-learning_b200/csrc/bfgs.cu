@@ -40,8 +40,13 @@ struct PassArgs {
     const double *s, *u, *v;   // pending update vectors (length n)
     const double *coef;        // device: rho, kappa, gamma
     const double *y2, *g2;     // new pair (length n)
-    double *u2, *w2;           // out, indexed by global row
+    double *u2, *w2;           // out, indexed by global row (col_splits == 1)
     double *vpart;             // out, [panels][n]
+    // 2-D decomposition for SHORT shards (row-sharded H over several GPUs): blockIdx.y selects a column range, the row
+    // products of the ranges go to upart / wpart [col_splits][rows_local] and are folded in range order afterwards
+    int col_splits;
+    int64_t cols_per_split;    // multiple of PASS_COLS
+    double *upart, *wpart;
 };
 
 // Sum 8 per-lane values across the warp with 9 (instead of 40) 64-bit shuffles.
@@ -108,7 +113,9 @@ __global__ void __launch_bounds__(PASS_THREADS, 2) bfgs_pass_kernel(const PassAr
     }
     __syncthreads();
 
-    for (int64_t c0 = 0; c0 < n; c0 += PASS_COLS) {
+    const int64_t c_begin = (int64_t)blockIdx.y * p.cols_per_split;
+    const int64_t c_end = p.col_splits > 1 ? min(n, c_begin + p.cols_per_split) : n;
+    for (int64_t c0 = c_begin; c0 < c_end; c0 += PASS_COLS) {
         int64_t col[4];
         if (VEC == 2) {
             col[0] = c0 + 2 * lane;
@@ -226,10 +233,29 @@ __global__ void __launch_bounds__(PASS_THREADS, 2) bfgs_pass_kernel(const PassAr
         __syncwarp();
         __syncthreads();
         for (int r = tid; r < nr; r += PASS_THREADS) {
-            const int64_t gi = p.row_begin + r0 + r;
-            p.u2[gi] = acc_u[r];
-            p.w2[gi] = acc_w[r];
+            if (p.col_splits > 1) {
+                p.upart[(int64_t)blockIdx.y * p.rows_local + r0 + r] = acc_u[r];
+                p.wpart[(int64_t)blockIdx.y * p.rows_local + r0 + r] = acc_w[r];
+            } else {
+                const int64_t gi = p.row_begin + r0 + r;
+                p.u2[gi] = acc_u[r];
+                p.w2[gi] = acc_w[r];
+            }
         }
+    }
+}
+
+// row products of a 2-D pass: u2[row] = sum over the column ranges, in range order (bit-reproducible)
+__global__ void bfgs_fold_rows_kernel(const double *__restrict__ upart, const double *__restrict__ wpart, int splits,
+                                      int64_t rows_local, int64_t row_begin, double *__restrict__ u2, double *__restrict__ w2) {
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < rows_local; r += (int64_t)gridDim.x * blockDim.x) {
+        double su = 0.0, sw = 0.0;
+        for (int k = 0; k < splits; ++k) {
+            su += upart[(int64_t)k * rows_local + r];
+            sw += wpart[(int64_t)k * rows_local + r];
+        }
+        u2[row_begin + r] = su;
+        w2[row_begin + r] = sw;
     }
 }
 
@@ -458,6 +484,9 @@ struct opl_bfgs {
     double *dots = nullptr;
     int dot_blocks = 0;
     int64_t panels = 0, rows_per_panel = 0;
+    int col_splits = 1;
+    int64_t cols_per_split = 0;
+    double *upart = nullptr, *wpart = nullptr;
     int64_t launches = 0;
     // small-problem path: slope g.d of the last direction through mapped pinned memory
     double *slope_dev = nullptr;
@@ -477,6 +506,10 @@ int ensure_matrix(opl_bfgs *b) {
     const int64_t rows = b->row_end - b->row_begin;
     if (!b->H) OPL_CUDA(cudaMalloc(&b->H, sizeof(double) * (size_t)rows * (size_t)b->n));
     if (!b->vpart) OPL_CUDA(cudaMalloc(&b->vpart, sizeof(double) * (size_t)b->panels * (size_t)b->n));
+    if (b->col_splits > 1 && !b->upart) {
+        OPL_CUDA(cudaMalloc(&b->upart, sizeof(double) * (size_t)b->col_splits * (size_t)rows));
+        OPL_CUDA(cudaMalloc(&b->wpart, sizeof(double) * (size_t)b->col_splits * (size_t)rows));
+    }
     return OPL_OK;
 }
 
@@ -501,12 +534,23 @@ int run_pass(opl_bfgs *b, const double *y2, const double *g2, bool products, dou
     a.u2 = u2;
     a.w2 = w2;
     a.vpart = b->vpart;
+    a.col_splits = b->col_splits;
+    a.cols_per_split = b->cols_per_split;
+    a.upart = b->upart;
+    a.wpart = b->wpart;
     const size_t smem = sizeof(double) * (size_t)(5 * b->rows_per_panel + PASS_WARPS * PASS_COLS);
     const bool vec = (b->n % 2 == 0) && ((reinterpret_cast<uintptr_t>(b->H) & 15u) == 0);
-    if (vec) bfgs_pass_kernel<2><<<(unsigned)b->panels, PASS_THREADS, smem, b->stream>>>(a);
-    else bfgs_pass_kernel<1><<<(unsigned)b->panels, PASS_THREADS, smem, b->stream>>>(a);
+    const dim3 grid((unsigned)b->panels, (unsigned)b->col_splits);
+    if (vec) bfgs_pass_kernel<2><<<grid, PASS_THREADS, smem, b->stream>>>(a);
+    else bfgs_pass_kernel<1><<<grid, PASS_THREADS, smem, b->stream>>>(a);
     OPL_LAUNCH_CHECK();
     ++b->launches;
+    if (products && b->col_splits > 1) {
+        bfgs_fold_rows_kernel<<<vgrid(a.rows_local), 256, 0, b->stream>>>(b->upart, b->wpart, b->col_splits, a.rows_local,
+                                                                           b->row_begin, u2, w2);
+        OPL_LAUNCH_CHECK();
+        ++b->launches;
+    }
     if (products) {
         rc = launch_reduce_partials(b->vpart, (int)b->panels, b->n, b->n, v2, b->stream, &b->launches);
         if (rc != OPL_OK) return rc;
@@ -553,11 +597,28 @@ int opl_bfgs_create(opl_bfgs **out, int64_t n, int64_t row_begin, int64_t row_en
     b->row_end = row_end;
     b->stream = (cudaStream_t)cuda_stream;
     const int64_t rows = row_end - row_begin;
-    int64_t panels = std::min<int64_t>(ceil_div(rows, 8), 2 * (int64_t)sm_count());
+    const int64_t slots = 2 * (int64_t)sm_count();        // two resident CTAs per SM
+    int64_t panels = std::min<int64_t>(ceil_div(rows, 8), slots);
     int64_t rpp = ceil_div(ceil_div(rows, panels), 8) * 8;
     if (rpp > 1024) rpp = 1024;
     b->rows_per_panel = rpp;
     b->panels = ceil_div(rows, rpp);
+    // A SHORT shard (H row-sharded over several GPUs: 10416 rows per GPU at n = 83328 on 8) would give every CTA a panel of
+    // only ~40 rows: the per-chunk synchronisation and the column-sum fold are then amortised over 40 x 128 elements, a
+    // third of the row slots of the last warp iteration is empty and [panels][n] column partials cost 5 % extra traffic
+    // (measured: 0.73 of the aggregate HBM rate at 8 GPUs against 0.96 on one).  Tall panels x column ranges instead.
+    if (rpp < 192 && n >= 8 * PASS_COLS && rows >= 64) {
+        const int64_t tall = 288;                           // = the single-GPU panel height at n = 83328
+        const int64_t panels_r = ceil_div(rows, tall);
+        int64_t splits = std::max<int64_t>(1, std::min<int64_t>(slots / panels_r, n / (4 * PASS_COLS)));
+        if (splits > 1) {
+            b->rows_per_panel = tall;
+            b->panels = panels_r;
+            b->col_splits = (int)splits;
+            b->cols_per_split = ceil_div(ceil_div(n, splits), PASS_COLS) * PASS_COLS;
+            b->col_splits = (int)ceil_div(n, b->cols_per_split);
+        }
+    }
     b->dot_blocks = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 1024), (int64_t)sm_count()));
     cudaError_t e = cudaSuccess;
     double **vecs[] = {&b->y, &b->s_pend, &b->u_pend, &b->v_pend, &b->u, &b->v, &b->w};
@@ -583,7 +644,7 @@ int opl_bfgs_create(opl_bfgs **out, int64_t n, int64_t row_begin, int64_t row_en
 int opl_bfgs_destroy(opl_bfgs *b) {
     if (!b) return OPL_OK;
     cudaStreamSynchronize(b->stream);
-    double *all[] = {b->H, b->y, b->s_pend, b->u_pend, b->v_pend, b->u, b->v, b->w, b->coef, b->vpart, b->dots};
+    double *all[] = {b->H, b->y, b->s_pend, b->u_pend, b->v_pend, b->u, b->v, b->w, b->coef, b->vpart, b->dots, b->upart, b->wpart};
     for (double *p : all) cudaFree(p);
     cudaFree(b->slope_dev);
     cudaFreeHost(b->mapped_host);

@@ -134,58 +134,63 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// four columns at a time with the switch OUTSIDE the element loop, so the four transcendental chains sit in one basic
-// block and interleave (a per-element switch serialises them)
-__device__ __forceinline__ void epi_apply4(const Tf32GemmArgs &p, const float (&z)[4], const float (&aux)[4], float (&r)[4],
-                                           float (&ao)[4]) {
+// NC columns at a time with the switch OUTSIDE the element loops and every stage of the transcendental chain written as
+// its own loop over the NC elements, so NC independent chains sit in one basic block and interleave.  (Round 1 did this
+// for four elements inside a loop over groups; the switch between the groups kept the compiler from interleaving more
+// than four chains, and with two epilogue warps per scheduler the MUFU -> FMUL -> MUFU chain latency, not the issue rate,
+// bounded the forward GEMM's epilogue.)
+template <int NC>
+__device__ __forceinline__ void epi_apply(const Tf32GemmArgs &p, const float (&z)[NC], const float (&aux)[NC], float (&r)[NC],
+                                          float (&ao)[NC]) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) ao[e] = 0.f;
+    for (int e = 0; e < NC; ++e) ao[e] = 0.f;
     switch (p.epi) {
         case TEPI_TANH:
 #pragma unroll
-            for (int e = 0; e < 4; ++e) r[e] = tanhf(z[e]);
+            for (int e = 0; e < NC; ++e) r[e] = tanhf(z[e]);
             break;
         case TEPI_SOFTPLUS: {
             // softplus = max(z, 0) + log(1 + t), logistic = z >= 0 ? 1/(1 + t) : t/(1 + t) with t = exp(-|z|): three MUFU
             // operations (EX2, RCP, LG2) and ~10 FP32 instructions per element instead of ~65 for expf + log1pf + an
-            // IEEE division -- the epilogue warps were the bottleneck of the forward GEMM (1.6x its plain time).  The
-            // approximations are good to 2^-21 relative, the stored results are rounded to TF32 (2^-11).  NaN and
-            // +-inf come out as in the library version (softplus(inf) = inf, logistic(-inf) = 0).
-            float t[4], u[4], ru[4];
+            // IEEE division.  The approximations are good to 2^-21 relative, the stored results are rounded to TF32
+            // (2^-11).  NaN and +-inf come out as in the library version (softplus(inf) = inf, logistic(-inf) = 0).
+            float t[NC], u[NC], ru[NC];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) t[e] = __expf(-fabsf(z[e]));
+            for (int e = 0; e < NC; ++e) t[e] = __expf(-fabsf(z[e]));
 #pragma unroll
-            for (int e = 0; e < 4; ++e) u[e] = 1.0f + t[e];
+            for (int e = 0; e < NC; ++e) u[e] = 1.0f + t[e];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ru[e]) : "f"(u[e]));
+            for (int e = 0; e < NC; ++e) asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ru[e]) : "f"(u[e]));
 #pragma unroll
-            for (int e = 0; e < 4; ++e) ao[e] = z[e] >= 0.f ? ru[e] : t[e] * ru[e];
+            for (int e = 0; e < NC; ++e) ao[e] = z[e] >= 0.f ? ru[e] : t[e] * ru[e];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
+            for (int e = 0; e < NC; ++e) u[e] = __log2f(u[e]) * 0.6931471805599453f;
+#pragma unroll
+            for (int e = 0; e < NC; ++e) {
                 // log(1 + t): LG2 has an absolute error of 2^-22, so below t = 2^-8 the series t - t^2/2 takes over
-                const float l = t[e] < 0.00390625f ? t[e] * (1.0f - 0.5f * t[e]) : __log2f(u[e]) * 0.6931471805599453f;
+                const float l = t[e] < 0.00390625f ? t[e] * (1.0f - 0.5f * t[e]) : u[e];
                 r[e] = fmaxf(z[e], 0.f) + l;
             }
             break;
         }
         case TEPI_GAUSSIAN:
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
+            for (int e = 0; e < NC; ++e) {
                 r[e] = expf(-(z[e] * z[e] / p.tparam));
                 ao[e] = -2.0f * z[e] * r[e] / p.tparam;
             }
             break;
         case TEPI_MUL_AUX:
 #pragma unroll
-            for (int e = 0; e < 4; ++e) r[e] = z[e] * aux[e];
+            for (int e = 0; e < NC; ++e) r[e] = z[e] * aux[e];
             break;
         case TEPI_MUL_DTANH:
 #pragma unroll
-            for (int e = 0; e < 4; ++e) r[e] = z[e] * (1.0f - aux[e] * aux[e]);
+            for (int e = 0; e < NC; ++e) r[e] = z[e] * (1.0f - aux[e] * aux[e]);
             break;
         default:
 #pragma unroll
-            for (int e = 0; e < 4; ++e) r[e] = z[e];
+            for (int e = 0; e < NC; ++e) r[e] = z[e];
     }
 }
 
@@ -348,19 +353,29 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int col0 = tl.n0 + c0;
                 if (CW == 32 ? col0 < p.N : (row < p.M && col0 < p.N)) {     // (the patch path needs the whole warp)
                     float out[CW], aux_o[CW];
+                    constexpr int NC = 16;                       // columns whose transfer-function chains interleave
 #pragma unroll
-                    for (int q = 0; q < CW / 4; ++q) {
-                        float4 ax = make_float4(0.f, 0.f, 0.f, 0.f), bs = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (need_aux_in && row < p.M) ax = *reinterpret_cast<const float4 *>(p.aux_in + (int64_t)row * p.ldaux + col0 + 4 * q);
-                        if (p.bias) bs = *reinterpret_cast<const float4 *>(p.bias + col0 + 4 * q);
-                        const float axv[4] = {ax.x, ax.y, ax.z, ax.w}, bsv[4] = {bs.x, bs.y, bs.z, bs.w};
-                        float zq[4], rq[4], aq[4];
+                    for (int g0 = 0; g0 < CW; g0 += NC) {
+                        float zq[NC], axv[NC], rq[NC], aq[NC];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) zq[e] = __uint_as_float(v[4 * q + e]) + bsv[e];
-                        epi_apply4(p, zq, axv, rq, aq);
+                        for (int q = 0; q < NC / 4; ++q) {
+                            float4 ax = make_float4(0.f, 0.f, 0.f, 0.f), bs = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (need_aux_in && row < p.M)
+                                ax = *reinterpret_cast<const float4 *>(p.aux_in + (int64_t)row * p.ldaux + col0 + g0 + 4 * q);
+                            if (p.bias) bs = *reinterpret_cast<const float4 *>(p.bias + col0 + g0 + 4 * q);
+                            axv[4 * q] = ax.x;
+                            axv[4 * q + 1] = ax.y;
+                            axv[4 * q + 2] = ax.z;
+                            axv[4 * q + 3] = ax.w;
+                            zq[4 * q] = __uint_as_float(v[g0 + 4 * q]) + bs.x;
+                            zq[4 * q + 1] = __uint_as_float(v[g0 + 4 * q + 1]) + bs.y;
+                            zq[4 * q + 2] = __uint_as_float(v[g0 + 4 * q + 2]) + bs.z;
+                            zq[4 * q + 3] = __uint_as_float(v[g0 + 4 * q + 3]) + bs.w;
+                        }
+                        epi_apply<NC>(p, zq, axv, rq, aq);
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int j = 4 * q + e;
+                        for (int e = 0; e < NC; ++e) {
+                            const int j = g0 + e;
                             float r = p.round_out ? round_tf32(rq[e]) : rq[e];
                             float ao = aq[e];
                             if (col0 + j >= p.n_valid) {      // layer padding stays exactly zero

@@ -529,12 +529,12 @@ def test_bfgs_direction_sequence_against_oracle(L, golden_qn, n, seed_mode):
     nat.check(nat.lib.opl_bfgs_destroy(handle))
 
 
-def test_bfgs_row_sharded_pass_equals_whole(L):
+@pytest.mark.parametrize("n,cut", [(301, 160), (1500, 700), (3000, 1000)])   # the last two: short shards of a wide H take
+def test_bfgs_row_sharded_pass_equals_whole(L, n, cut):                      # the 2-D (row panel x column range) pass
     """Two row shards driven on one GPU (pass -> exchange -> finish) reproduce the single-device
     direction: the contract of the row-sharded multi-GPU path."""
     import torch
     from learning_b200 import _native as nat, _device as dev
-    n, cut = 301, 160
     rng = numpy.random.default_rng(4)
     whole = _bfgs_handle(L, n)
     parts = [_bfgs_handle(L, n, 0, cut), _bfgs_handle(L, n, cut, n)]

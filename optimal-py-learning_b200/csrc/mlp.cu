@@ -633,6 +633,33 @@ __global__ void loss_final_kernel(const double *partial, int nparts, int eid, do
     }
 }
 
+// The fused head's two folds in ONE launch: the per-CTA dW partials (one warp per output element, lanes over the CTAs,
+// fixed order) and -- block 0, afterwards -- the per-CTA loss partials with the objective's scale and the domain flag.
+__global__ void __launch_bounds__(256) head_fold_kernel(const double *__restrict__ partial, int splits, int64_t stride,
+                                                        int64_t count, double *__restrict__ out,
+                                                        const double *__restrict__ loss_partial, int eid, double n_rows,
+                                                        double n_cols, double *__restrict__ obj_out, const int *flag) {
+    __shared__ double scratch[33];
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp; i < count; i += nwarps) {
+        double s = 0.0;
+        for (int k = lane; k < splits; k += 32) s += partial[(int64_t)k * stride + i];
+        s = warp_sum(s);
+        if (lane == 0) out[i] = s;
+    }
+    if (blockIdx.x == 0) {
+        double s = 0.0;
+        for (int i = threadIdx.x; i < splits; i += blockDim.x) s += loss_partial[i];
+        s = block_sum(s, scratch);
+        if (threadIdx.x == 0) {
+            obj_out[0] = eid == OPL_ERROR_MSE ? s / (n_rows * n_cols) : -(s / n_rows);
+            obj_out[1] = *flag ? 1.0 : 0.0;
+        }
+    }
+}
+
 // column sums of a rows x cols matrix, stage 1: partial[blockIdx.y][col]
 __global__ void colsum_partial_kernel(const double *__restrict__ D, int64_t rows, int cols, int64_t rows_per_block,
                                       double *__restrict__ partial) {
@@ -1164,6 +1191,18 @@ int fused_head(opl_mlp *ws, const double *w, const double *y, int64_t rows, bool
         }
     }
     ++ws->launches;
+    if (want_grad && grid >= 16) {
+        // one launch folds the per-CTA dW partials AND the loss partials (objective + domain flag)
+        mark(ws, STAGE_DW_REDUCE * 100 + L - 1);
+        const int64_t count = (int64_t)H * C;
+        const int64_t fgrid = std::min<int64_t>(ceil_div(count * 32, 256), 4 * (int64_t)sm_count());
+        head_fold_kernel<<<(unsigned)fgrid, 256, 0, ws->stream>>>(ws->partials, grid, count, count, grad + ws->w_off[L - 1],
+                                                                  ws->loss_partial, ws->error_id, (double)ws->norm_rows,
+                                                                  (double)C, obj_out, ws->flag);
+        OPL_LAUNCH_CHECK();
+        ++ws->launches;
+        return OPL_OK;
+    }
     mark(ws, STAGE_LOSS * 100);
     loss_final_kernel<<<1, 256, 0, ws->stream>>>(ws->loss_partial, grid, ws->error_id, (double)ws->norm_rows, (double)C, obj_out, ws->flag);
     OPL_LAUNCH_CHECK();

@@ -635,19 +635,26 @@ __global__ void loss_final_kernel(const double *partial, int nparts, int eid, do
 
 // The fused head's two folds in ONE launch: the per-CTA dW partials (one warp per output element, lanes over the CTAs,
 // fixed order) and -- block 0, afterwards -- the per-CTA loss partials with the objective's scale and the domain flag.
+// (partial2 / out2: an optional second family of per-CTA partials -- the bias gradient's column sums when the head's
+// delta_prev is delta_0)
 __global__ void __launch_bounds__(256) head_fold_kernel(const double *__restrict__ partial, int splits, int64_t stride,
                                                         int64_t count, double *__restrict__ out,
                                                         const double *__restrict__ loss_partial, int eid, double n_rows,
-                                                        double n_cols, double *__restrict__ obj_out, const int *flag) {
+                                                        double n_cols, double *__restrict__ obj_out, const int *flag,
+                                                        const double *__restrict__ partial2 = nullptr, int64_t stride2 = 0,
+                                                        int64_t count2 = 0, double *__restrict__ out2 = nullptr) {
     __shared__ double scratch[33];
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t i = warp; i < count; i += nwarps) {
+    for (int64_t i = warp; i < count + count2; i += nwarps) {
+        const bool second = i >= count;
+        const double *src = second ? partial2 + (i - count) : partial + i;
+        const int64_t st = second ? stride2 : stride;
         double s = 0.0;
-        for (int k = lane; k < splits; k += 32) s += partial[(int64_t)k * stride + i];
+        for (int k = lane; k < splits; k += 32) s += src[(int64_t)k * st];
         s = warp_sum(s);
-        if (lane == 0) out[i] = s;
+        if (lane == 0) (second ? out2 + (i - count) : out + i)[0] = s;
     }
     if (blockIdx.x == 0) {
         double s = 0.0;
@@ -1233,15 +1240,16 @@ int evaluate(opl_mlp *ws, const double *x_dev, double alpha, const double *dir_d
     }
     int tgrid = (int)std::min<int64_t>(ceil_div(n, 256), 4 * (int64_t)sm_count());
     mark(ws, STAGE_TRIAL * 100);
-    trial_point_kernel<<<tgrid, 256, 0, ws->stream>>>(n, x_dev, alpha, dir_dev, ws->w_trial, ws->flag);
-    OPL_LAUNCH_CHECK();
-    ++ws->launches;
     int rc;
     if (ws->precision == OPL_PRECISION_TF32) {
-        rc = fast_evaluate(ws, want_grad, grad_out_dev);
+        rc = fast_trial_convert(ws, x_dev, alpha, dir_dev);      // trial point + padded TF32 copy of the weights: one launch
+        if (rc == OPL_OK) rc = fast_evaluate(ws, want_grad, grad_out_dev);
         mark(ws, STAGE_END * 100);
         return rc;
     }
+    trial_point_kernel<<<tgrid, 256, 0, ws->stream>>>(n, x_dev, alpha, dir_dev, ws->w_trial, ws->flag);
+    OPL_LAUNCH_CHECK();
+    ++ws->launches;
     const int64_t w0_count = ws->width[0] * ws->width[1];
     const int mgrid = (int)std::min<int64_t>(ceil_div(w0_count, 256), 4 * (int64_t)sm_count());
     if (ws->masks) {   // (X o m) W0 == X (diag(m) W0) exactly for a 0/1 mask

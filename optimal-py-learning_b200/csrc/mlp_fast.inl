@@ -261,6 +261,54 @@ int fast_convert_x(opl_mlp *ws, const double *x_dev, int64_t rows, float *dst) {
 
 int fast_set_x(opl_mlp *ws) { return fast_convert_x(ws, ws->x, ws->rows, ws->fast->x32); }
 
+// Trial point AND its padded FP32 / TF32-rounded copy in one launch (the fast mode's evaluation started with four: the trial
+// point, then one pad-convert per weight matrix and the bias): w = x + fl(alpha dir) into the FP64 trial vector (the head and
+// the bias read it), every element also rounded to TF32 into its padded slot of w32.
+struct FastTrialArgs {
+    int layers;
+    int64_t bias_len;                 // d1
+    int64_t src_off[9], cols[9], dst_off[9], dst_pitch[9];
+};
+__global__ void __launch_bounds__(256) fast_trial_convert_kernel(int64_t n, const double *__restrict__ x, double alpha,
+                                                                 const double *__restrict__ dir, double *__restrict__ w,
+                                                                 float *__restrict__ w32, const FastTrialArgs a, int *flag) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *flag = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = dir ? __dadd_rn(x[i], __dmul_rn(alpha, dir[i])) : x[i];
+        w[i] = v;
+        const float r = round_tf32((float)v);
+        if (i < a.bias_len) {
+            w32[i] = r;
+        } else {
+            int l = 0;
+            while (l + 1 < a.layers && i >= a.src_off[l + 1]) ++l;
+            const int64_t k = i - a.src_off[l];
+            const int64_t row = k / a.cols[l], col = k - row * a.cols[l];
+            w32[a.dst_off[l] + row * a.dst_pitch[l] + col] = r;
+        }
+    }
+}
+
+// one launch for the evaluation path (padding rows / columns of w32 were cleared at creation and are never written)
+int fast_trial_convert(opl_mlp *ws, const double *x_dev, double alpha, const double *dir_dev) {
+    FastState *f = ws->fast;
+    if (ws->layers > 9) return fail(OPL_E_ARG, "fast mode: at most 9 layers");
+    FastTrialArgs a = {};
+    a.layers = ws->layers;
+    a.bias_len = ws->width[1];
+    for (int l = 0; l < ws->layers; ++l) {
+        a.src_off[l] = ws->w_off[l];
+        a.cols[l] = ws->width[l + 1];
+        a.dst_off[l] = f->w_off[l];
+        a.dst_pitch[l] = f->pw[l + 1];
+    }
+    const int grid = (int)std::min<int64_t>(ceil_div(ws->n, 256), 4 * (int64_t)sm_count());
+    fast_trial_convert_kernel<<<grid, 256, 0, ws->stream>>>(ws->n, x_dev, alpha, dir_dev, ws->w_trial, f->w32, a, ws->flag);
+    OPL_LAUNCH_CHECK();
+    ++ws->launches;
+    return OPL_OK;
+}
+
 int fast_convert_w(opl_mlp *ws, const double *w) {
     FastState *f = ws->fast;
     // bias as a 1 x d1 matrix, then every weight matrix into its padded slot
@@ -798,6 +846,19 @@ int fast_fused_head(opl_mlp *ws, bool want_grad, double *grad, double *obj_out) 
     narrow_head_tf32_kernel<<<grid, FH_THREADS, smem, ws->stream>>>(a);
     OPL_LAUNCH_CHECK();
     ++ws->launches;
+    if (want_grad && grid >= 16) {
+        // one launch folds the per-CTA dW partials, the bias-gradient column sums and the loss partials
+        mark(ws, STAGE_DW_REDUCE * 100 + L - 1);
+        const int64_t count = (int64_t)H * C, count2 = bias_here ? H : 0;
+        const int64_t fgrid = std::min<int64_t>(ceil_div((count + count2) * 32, 256), 4 * (int64_t)sm_count());
+        head_fold_kernel<<<(unsigned)fgrid, 256, 0, ws->stream>>>(ws->partials, grid, count, count, grad + ws->w_off[L - 1],
+                                                                  ws->loss_partial, ws->error_id, (double)ws->norm_rows,
+                                                                  (double)C, obj_out, ws->flag, a.colsum_partial, (int64_t)H,
+                                                                  count2, grad);
+        OPL_LAUNCH_CHECK();
+        ++ws->launches;
+        return OPL_OK;
+    }
     mark(ws, STAGE_LOSS * 100);
     loss_final_kernel<<<1, 256, 0, ws->stream>>>(ws->loss_partial, grid, ws->error_id, (double)ws->norm_rows, (double)C, obj_out, ws->flag);
     OPL_LAUNCH_CHECK();
@@ -818,8 +879,7 @@ int fast_fused_head(opl_mlp *ws, bool want_grad, double *grad, double *obj_out) 
 
 int fast_evaluate(opl_mlp *ws, bool want_grad, double *grad_out_dev) {
     FastState *f = ws->fast;
-    int rc = fast_convert_w(ws, ws->w_trial);
-    if (rc != OPL_OK) return rc;
+    int rc = OPL_OK;
     if (fast_head_ok(ws)) {
         rc = fast_forward(ws, f->x32, ws->rows, want_grad, ws->layers - 1);
         if (rc != OPL_OK) return rc;

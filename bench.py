@@ -456,6 +456,10 @@ def run_gpu(args):
     # ---- BFGS fused update + products pass at n = 83328 (H row-sharded over the ranks) ----------
     del xd, yd
     bfgs = run_bfgs(args, torch, dist, nat, dev, world, rank, barrier, max_over_ranks)
+    # ---- 8 GPUs: BASELINE configs[3] at its full size -- n = 336128 weights, H = 904 GB FP64 as 113 GB per GPU ----
+    bfgs_config4 = None
+    if world == 8 and not args.no_config4:
+        bfgs_config4 = run_bfgs_config4(args, torch, dist, nat, dev, world, rank, barrier, max_over_ranks)
 
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
@@ -497,6 +501,15 @@ def run_gpu(args):
                  "peak": peaks["hbm_gbs"] * world, "peak_source": peak_src + (" x %d GPUs" % world if world > 1 else ""),
                  "unit": "GB/s", "frac": bfgs["value"] / (peaks["hbm_gbs"] * world),
                  "algorithmic_bytes_per_iter": 2.0 * bfgs["n"] * bfgs["n"] * 8, "traffic": None}
+    if bfgs_config4 is not None:
+        if "skipped" in bfgs_config4:
+            bfgs_roof["config4"] = bfgs_config4
+        else:
+            bfgs_roof["config4"] = {"workload": "configs[3]: MLP (1024,256,256,32), n = 336128 weights, H = 904 GB FP64 row-sharded over 8 GPUs "
+                                                "(113 GB per GPU), one-launch [u ; w ; v] exchange",
+                                    "n": bfgs_config4["n"], "ms_per_iter": bfgs_config4["ms_per_iter"], "gbs": bfgs_config4["value"],
+                                    "frac": bfgs_config4["value"] / (peaks["hbm_gbs"] * world), "finite": bfgs_config4["finite"],
+                                    "algorithmic_bytes_per_iter": 2.0 * bfgs_config4["n"] ** 2 * 8}
     tr = ncu_traffic("bfgs_pass")
     if tr:
         bfgs_roof["traffic"] = tr.get("bytes")
@@ -808,9 +821,25 @@ def run_fast_mode(args, torch, L, nat, dev, xd, yd, wd, obj_f64, grad_f64):
                       "TMEM accumulators, tcgen05.ld epilogue"}
 
 
-def run_bfgs(args, torch, dist, nat, dev, world, rank, barrier, max_over_ranks):
+def run_bfgs_config4(args, torch, dist, nat, dev, world, rank, barrier, max_over_ranks):
+    """configs[3] at full size on 8 GPUs; skipped (and said so) when a rank lacks the memory for its 113 GB shard."""
+    n = 1024 * 256 + 256 + 256 * 256 + 256 * 32          # 336128
+    torch.cuda.empty_cache()
+    free, _ = torch.cuda.mem_get_info()
+    need = (n // world + 1) * n * 8 + (6 << 30)
+    ok = torch.tensor([1 if free >= need else 0], dtype=torch.int32, device="cuda")
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if not bool(ok.item()):
+        return {"skipped": "a rank has %.1f GB free, the shard needs %.1f GB" % (free / 1e9, need / 1e9)}
+    try:
+        return run_bfgs(args, torch, dist, nat, dev, world, rank, barrier, max_over_ranks, n=n, steps=5, warmup=3)
+    except Exception as exc:       # every rank takes the same path: allocation failures are symmetric
+        return {"skipped": "config 4 BFGS run failed: %s" % (exc,)}
+
+
+def run_bfgs(args, torch, dist, nat, dev, world, rank, barrier, max_over_ranks, n=None, steps=None, warmup=None):
     """Time the fused BFGS pass (apply pending rank-2 update in place + H.[y g] + y^T.H) + finish."""
-    n = args.bfgs_n
+    n = args.bfgs_n if n is None else n
     per = -(-n // world)
     begin, end = min(n, rank * per), min(n, (rank + 1) * per)
     handle = ctypes.c_void_p()
@@ -852,8 +881,8 @@ def run_bfgs(args, torch, dist, nat, dev, world, rank, barrier, max_over_ranks):
         nat.check(nat.lib.opl_bfgs_finish_device(handle, dev.ptr(g), dev.ptr(s), dev.ptr(g_prev), 0, dev.ptr(pu),
                                                  dev.ptr(pv), dev.ptr(pw), dev.ptr(d)))
 
-    steps = max(3, min(args.steps, 10))
-    for i in range(max(3, args.warmup)):
+    steps = max(3, min(args.steps, 10)) if steps is None else steps
+    for i in range(max(3, args.warmup) if warmup is None else warmup):
         step(i)
     barrier()
     l0 = nat.lib.opl_bfgs_launch_count(handle)
@@ -888,6 +917,7 @@ def main():
     ap.add_argument("--bfgs-n", type=int, default=BFGS_N)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-config1", action="store_true")
+    ap.add_argument("--no-config4", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -318,6 +318,8 @@ struct HeadArgsT {
     double *loss_partial;   // gridDim.x
     double *colmax;         // H: max |delta_prev[:, j]| (atomicMax on bit patterns) or null
     double *colsum_partial; // gridDim.x x H: column sums of delta_prev (the bias gradient when delta_prev is delta_0) or null
+    double *delta_out;      // DA == false: rows x C delta_L written out (delta_prev is then formed by the digit kernel), else unused
+    double *classmax;       // DA == false: C entries, max |delta_L[:, c]| (atomicMax on bit patterns)
     int64_t rows;
     int64_t ld;
     int H, C, R;            // R rows per block step
@@ -363,7 +365,10 @@ __device__ __forceinline__ double2 head_store2(float *p, double a, double b) {
     do {                                                                                    \
         if (p.trace && blockIdx.x == 0 && threadIdx.x == 0 && step_no < 16) p.trace[step_no * 8 + (k)] = clock64(); \
     } while (0)
-template <typename T, int MT, int R, int HEAD_WARPS, bool CSUM>    // MT = hidden tiles (8 units) per warp: H <= 8 MT HEAD_WARPS
+// DA == false: the head does NOT form delta_prev = (delta_L W^T) o slope (a third of its DMMA work, the slope matrix read and the
+// delta_prev write): it writes delta_L (rows x C) and the per-class maxima instead, and the digit kernel of the weight-gradient
+// GEMM forms delta_prev on the fly (ozaki_slice_delta_prev, csrc/ozaki.cu).  `backward` then only means "accumulate dW".
+template <typename T, int MT, int R, int HEAD_WARPS, bool CSUM, bool DA = true>    // MT = hidden tiles (8 units) per warp: H <= 8 MT HEAD_WARPS
 __global__ void __launch_bounds__(HEAD_WARPS * 32, R == 16 ? 2 : 1) narrow_head_kernel(const HeadArgsT<T> p) {
     extern __shared__ double hsm[];
     __shared__ double scratch[33];
@@ -377,8 +382,10 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, R == 16 ? 2 : 1) narrow_head_
     T *As0 = reinterpret_cast<T *>(Zs + R * ldD);   // 2 x R x ldA
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
     const bool softmax = p.tid == OPL_TRANSFER_SOFTMAX;
-    const bool backward = p.delta_prev != nullptr;
+    const bool backward = DA ? p.delta_prev != nullptr : p.dw_partial != nullptr;
     const int h2 = H / EPC;                    // 16-byte chunks per row (H is a multiple of 8)
+    double lmax = 0.0;                         // DA == false: max |delta_L| of this lane's class over the CTA's patterns
+    bool lbad = false;
     const int64_t nblocks = (p.rows + R - 1) / R;
     auto fetch = [&](int64_t blk, int buf) {   // cp.async the block's activations (rows past the end := 0)
         const int64_t r0 = blk * R;
@@ -416,8 +423,8 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, R == 16 ? 2 : 1) narrow_head_
         const int nr = (int)min((int64_t)R, p.rows - r0);
         const T *As = As0 + (size_t)buf * R * ldA;
         // slope values of this step's delta_prev tiles: requested now, used after the row stage
-        double2 x[MT][RM];
-        if (backward && p.mode != 0) {
+        double2 x[DA ? MT : 1][RM];
+        if (DA && backward && p.mode != 0) {
 #pragma unroll
             for (int i = 0; i < MT; ++i) {
                 const int col = 8 * (warp + HEAD_WARPS * i) + 2 * t;
@@ -519,9 +526,19 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, R == 16 ? 2 : 1) narrow_head_
         if (!backward) continue;
     head_backward:
         HEAD_STAMP(5);
+        if (!DA) {   // delta_L of this step (Zs, zero outside the live patterns / classes) -> global, and its per-class maxima
+            const int hw = lane >> 4, cl = lane & 15, rr = warp * 2 + hw;
+            if (rr < nr && cl < C) {
+                const double d = Zs[rr * ldD + cl];
+                p.delta_out[(r0 + rr) * C + cl] = d;
+                const double ad = fabs(d);
+                lbad |= !(ad <= 1.7976931348623157e308);
+                lmax = fmax(lmax, ad);
+            }
+        }
         // ---- delta_prev = (delta_L W^T) o slope ----
 #pragma unroll
-        for (int i = 0; i < MT; ++i) {
+        for (int i = 0; i < (DA ? MT : 0); ++i) {
             const int nt = warp + HEAD_WARPS * i;        // hidden tile
             if (8 * nt >= H) break;
             const int col = 8 * nt + 2 * t;
@@ -536,11 +553,11 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, R == 16 ? 2 : 1) narrow_head_
                 if (row < nr) {
                     double o0 = c0, o1 = c1;
                     if (p.mode == 1) {
-                        o0 *= x[i][mt].x;
-                        o1 *= x[i][mt].y;
+                        o0 *= x[DA ? i : 0][mt].x;
+                        o1 *= x[DA ? i : 0][mt].y;
                     } else if (p.mode == 2) {
-                        o0 *= 1.0 - x[i][mt].x * x[i][mt].x;
-                        o1 *= 1.0 - x[i][mt].y * x[i][mt].y;
+                        o0 *= 1.0 - x[DA ? i : 0][mt].x * x[DA ? i : 0][mt].x;
+                        o1 *= 1.0 - x[DA ? i : 0][mt].y * x[DA ? i : 0][mt].y;
                     }
                     const double2 st = head_store2(p.delta_prev + (r0 + row) * p.ld + col, o0, o1);
                     const double a0 = fabs(st.x), a1 = fabs(st.y);
@@ -599,7 +616,7 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, R == 16 ? 2 : 1) narrow_head_
                     p.colsum_partial[(size_t)blockIdx.x * H + 8 * mt + 2 * t + 1] = s1;
                 }
             }
-            if (p.colmax) {                               // columns 8 mt + 2t, +1: fold the 8 row groups, then one atomic
+            if (DA && p.colmax) {                         // columns 8 mt + 2t, +1: fold the 8 row groups, then one atomic
                 double m0 = cmax[i][0], m1 = cmax[i][1];
 #pragma unroll
                 for (int o = 4; o < 32; o <<= 1) {
@@ -614,6 +631,9 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, R == 16 ? 2 : 1) narrow_head_
             }
         }
     }
+    if (!DA && backward && (lane & 15) < C)
+        atomicMax(reinterpret_cast<unsigned long long *>(p.classmax) + (lane & 15),
+                  lbad ? 0x7ff8000000000000ULL : (unsigned long long)__double_as_longlong(lmax));
     loss = block_sum(loss, scratch);
     if (threadIdx.x == 0) p.loss_partial[blockIdx.x] = loss;
 }
@@ -797,6 +817,7 @@ struct opl_mlp {
     std::vector<int64_t> mask_off;  // offset of layer l's mask (l = 0 input, l >= 1 hidden outputs)
     int64_t launches = 0;
     // one-launch path for small networks (mlp_small.inl)
+    bool direct_delta_digits = true;     // two-layer INT8 schedule: delta_0 only as digits (OPL_DIRECT_DELTA=0: materialise it)
     bool small_path = true;
     bool small_configured = false;
     size_t small_smem = 0;
@@ -1130,6 +1151,16 @@ int head_rows_per_step(const opl_mlp *ws) {
     return r16 ? 16 : 32;
 }
 
+// Can the head leave delta_{L-2} to the digit kernel of the weight-gradient GEMM (ozaki_slice_delta_prev)?  Two-layer networks
+// whose first layer's weight gradient runs on the INT8 engine: delta_0 is then needed ONLY as that GEMM's digit operand (the
+// bias gradient is the ones row of the other operand), and the slope of the hidden transfer is bounded by one.
+bool head_skips_delta_prev(const opl_mlp *ws, int64_t rows) {
+    if (ws->layers != 2 || ws->masks || !ws->direct_delta_digits) return false;
+    const int t = ws->transfer[0];
+    if (t != OPL_TRANSFER_SOFTPLUS && t != OPL_TRANSFER_TANH && t != OPL_TRANSFER_LINEAR) return false;
+    return int8_dw_ok(ws, 0, ws->x, rows) && rows == ws->rows;
+}
+
 // fused head: objective (and, when want_grad, dW_{L-1} and delta_{L-2}); the caller continues back-propagation at L-2
 int fused_head(opl_mlp *ws, const double *w, const double *y, int64_t rows, bool want_grad, double *grad, double *obj_out) {
     const int L = ws->layers, R = head_rows_per_step(ws);
@@ -1156,19 +1187,27 @@ int fused_head(opl_mlp *ws, const double *w, const double *y, int64_t rows, bool
     a.mse_mul = 2.0 / ((double)ws->norm_rows * (double)C);
     a.flag = ws->flag;
     a.loss_partial = ws->loss_partial;
+    const bool no_da = want_grad && R == 16 && head_skips_delta_prev(ws, rows);
     if (want_grad) {
         const int t = ws->transfer[L - 2];
         a.mode = (t == OPL_TRANSFER_SOFTPLUS || t == OPL_TRANSFER_GAUSSIAN) ? 1 : (t == OPL_TRANSFER_TANH ? 2 : 0);
         a.aux = a.mode == 1 ? ws->deriv[L - 2] : (a.mode == 2 ? ws->act[L - 1] : nullptr);
-        a.delta_prev = ws->delta[L - 2];
         a.dw_partial = ws->partials;
-        a.colmax = int8_arm_delta_max(ws, L - 2, rows);
+        if (no_da) {
+            a.delta_out = ws->delta[L - 1];          // rows x C: delta_L
+            a.classmax = ws->int8->classmax;
+            OPL_CUDA(cudaMemsetAsync(a.classmax, 0, sizeof(double) * 16, ws->stream));
+        } else {
+            a.delta_prev = ws->delta[L - 2];
+            a.colmax = int8_arm_delta_max(ws, L - 2, rows);
+        }
     }
     static bool configured_dev[64] = {};     // cudaFuncSetAttribute is per device
     bool &configured = configured_dev[current_device_slot()];
     if (!configured) {
         OPL_CUDA(cudaFuncSetAttribute(narrow_head_kernel<double, 2, 32, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_smem(256, 32)));
         OPL_CUDA(cudaFuncSetAttribute(narrow_head_kernel<double, 4, 16, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_smem(256, 16)));
+        OPL_CUDA(cudaFuncSetAttribute(narrow_head_kernel<double, 4, 16, 8, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_smem(256, 16)));
         configured = true;
     }
     static long long *head_trace = nullptr;
@@ -1181,6 +1220,8 @@ int fused_head(opl_mlp *ws, const double *w, const double *y, int64_t rows, bool
     mark(ws, STAGE_HEAD * 100 + L - 1);
     if (R == 32)
         narrow_head_kernel<double, 2, 32, 16, false><<<grid, 512, smem, ws->stream>>>(a);
+    else if (no_da)
+        narrow_head_kernel<double, 4, 16, 8, false, false><<<grid, 256, smem, ws->stream>>>(a);
     else
         narrow_head_kernel<double, 4, 16, 8, false><<<grid, 256, smem, ws->stream>>>(a);
     OPL_LAUNCH_CHECK();
@@ -1262,7 +1303,19 @@ int evaluate(opl_mlp *ws, const double *x_dev, double alpha, const double *dir_d
         if (rc != OPL_OK) return rc;
         rc = fused_head(ws, ws->w_trial, ws->y, ws->rows, want_grad, grad_out_dev, grad_out_dev + n);
         if (rc != OPL_OK) return rc;
-        if (want_grad) rc = backward(ws, ws->w_trial, ws->x, ws->rows, grad_out_dev, ws->layers - 2);
+        if (want_grad && head_rows_per_step(ws) == 16 && head_skips_delta_prev(ws, ws->rows)) {
+            // two-layer network: delta_0 exists only as the digit operand of the dW_0 GEMM, cut from (delta_L, W_1, slope)
+            const int t = ws->transfer[0];
+            DeltaOnTheFly otf;
+            otf.deltaL = ws->delta[1];
+            otf.C = (int)ws->width[2];
+            otf.W = ws->w_trial + ws->w_off[1];
+            otf.mode = t == OPL_TRANSFER_SOFTPLUS ? 1 : (t == OPL_TRANSFER_TANH ? 2 : 0);
+            otf.aux = otf.mode == 1 ? ws->deriv[0] : (otf.mode == 2 ? ws->act[1] : nullptr);
+            rc = int8_dw_layer(ws, 0, ws->x, ws->rows, grad_out_dev, &otf);
+        } else if (want_grad) {
+            rc = backward(ws, ws->w_trial, ws->x, ws->rows, grad_out_dev, ws->layers - 2);
+        }
     } else {
         rc = forward(ws, ws->w_trial, ws->x, ws->rows, want_grad, true);
         if (rc != OPL_OK) return rc;
@@ -1412,6 +1465,7 @@ int opl_mlp_create(opl_mlp **out, int32_t n_widths, const int64_t *widths, const
     OPL_TRY(cudaMalloc(&ws->ticket, sizeof(unsigned int)));
     OPL_TRY(cudaMemset(ws->ticket, 0, sizeof(unsigned int)));
     if (const char *env = getenv("OPL_SMALL_PATH")) ws->small_path = atoi(env) != 0;
+    if (const char *env = getenv("OPL_DIRECT_DELTA")) ws->direct_delta_digits = atoi(env) != 0;
 #undef OPL_TRY
     if (precision == OPL_PRECISION_TF32) {
         int rc = fast_create(ws);

@@ -30,6 +30,7 @@ struct Int8State {
     int8_t *d_dig = nullptr;           // delta_l^T: [S][pad(dout)][rows_pad]
     double *d_scale = nullptr;
     double *colmax = nullptr;          // column-max scratch
+    double *classmax = nullptr;        // 16 entries: max |delta_L[:, c]| of the fused head when it leaves delta_prev to the digit kernel
     double *dmax = nullptr;            // max |delta_l[:, j]| gathered by the kernel that writes delta_l (atomicMax), or unused
     int dmax_layer = -1;               // layer whose delta the maxima in dmax belong to (-1: none)
     int64_t colmax_len = 0;
@@ -63,6 +64,7 @@ void int8_free(Int8State *s) {
     cudaFree(s->d_scale);
     cudaFree(s->colmax);
     cudaFree(s->dmax);
+    cudaFree(s->classmax);
     delete s;
 }
 
@@ -135,6 +137,7 @@ int int8_create(opl_mlp *ws, int64_t *partials_needed) {
     s->colmax_len = 4 * (int64_t)sm_count() * std::max<int64_t>(std::max(d_cols, at_rows), ozaki_pad(ws->width[0] + 1));
     OPL_CUDA(cudaMalloc(&s->colmax, sizeof(double) * (size_t)s->colmax_len));
     OPL_CUDA(cudaMalloc(&s->dmax, sizeof(double) * (size_t)d_cols));
+    OPL_CUDA(cudaMalloc(&s->classmax, sizeof(double) * 16));
     return OPL_OK;
 }
 
@@ -273,8 +276,17 @@ int int8_da_layer(opl_mlp *ws, int l, const double *w, int64_t rows) {
     return launch_ozaki_gemm(s->a_dig, mp, s->w_dig, np, kp, g, ws->stream, &ws->launches);
 }
 
+// delta_l is not materialised: its transposed digits are cut from (delta_{l+1}, W_{l+1}, slope) by ozaki_slice_delta_prev
+struct DeltaOnTheFly {
+    const double *deltaL;   // rows x C
+    int C;
+    const double *W;        // d_{l+1} x C
+    const double *aux;      // rows x d_{l+1}
+    int mode;
+};
+
 // dW_l = A_l^T delta_l (+ db = 1^T delta_0 for l = 0) into the flat gradient
-int int8_dw_layer(opl_mlp *ws, int l, const double *in, int64_t rows, double *grad) {
+int int8_dw_layer(opl_mlp *ws, int l, const double *in, int64_t rows, double *grad, const DeltaOnTheFly *otf = nullptr) {
     Int8State *s = ws->int8;
     const double *colmax_raw = s->dmax_layer == l ? s->dmax : nullptr;
     s->dmax_layer = -1;
@@ -284,7 +296,12 @@ int int8_dw_layer(opl_mlp *ws, int l, const double *in, int64_t rows, double *gr
     const int64_t m = din + lead_rows, mp = ozaki_pad(m);
     // B operand: delta_l (rows x dout) -> digits of its transpose, one scale per unit (max over the patterns)
     mark(ws, STAGE_DIGITS * 100 + 50 + l);
-    int rc = ozaki_slice_cols_transposed(ws->delta[l], rows, dout, dout, s->d_dig, s->d_scale, s->colmax, s->colmax_len, 0, np, colmax_raw,
+    int rc;
+    if (otf)
+        rc = ozaki_slice_delta_prev(otf->deltaL, otf->C, otf->W, otf->aux, otf->mode, rows, dout, dout, s->classmax, s->d_dig, s->d_scale,
+                                    np, ws->stream, &ws->launches);
+    else
+        rc = ozaki_slice_cols_transposed(ws->delta[l], rows, dout, dout, s->d_dig, s->d_scale, s->colmax, s->colmax_len, 0, np, colmax_raw,
                                          ws->stream, &ws->launches);
     if (rc != OPL_OK) return rc;
     const int8_t *a_dig = s->xt_dig;

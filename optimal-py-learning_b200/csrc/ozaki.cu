@@ -800,6 +800,109 @@ __global__ void __launch_bounds__(256) slice_cols_transposed_kernel(const double
     }
 }
 
+// Digits of delta_prev^T WITHOUT delta_prev: for a narrow last layer (C <= 16 outputs) the matrix
+//     delta_prev[r][j] = (sum_c deltaL[r][c] W[j][c]) x slope(aux[r][j])
+// is a rank-C product, so the weight-gradient GEMM's B operand can be cut straight from deltaL (rows x C), W (H x C) and the
+// slope matrix: the fused head then neither forms nor stores delta_prev (a third of its DMMA work, 2 x rows x H x 8 bytes of
+// traffic), and this kernel reads the slope matrix instead of delta_prev -- the same bytes as the plain digit pass.
+// Scales: a column's maximum is not known before its values are, so the scale comes from the rigorous bound
+//     |delta_prev[r][j]| <= sum_c max_r|deltaL[r][c]| |W[j][c]|        (|slope| <= 1 for softplus', 1 - tanh^2 and linear)
+// with the per-class maxima gathered by the head (atomicMax on bit patterns).  The bound is loose by the cancellation inside
+// the sum (measured ~2-4x, i.e. 1-2 of the 48 digit bits): the digits stay an error-free transformation relative to it.
+// A non-finite value poisons the column's scale (NaN pattern by atomicMax), as the plain pass does.
+// Block = 128 rows x 32 columns (as slice_cols_transposed_kernel); the block's deltaL rows sit in shared memory (broadcast
+// reads), a thread keeps its column's row of W in registers.  mode: 0 slope 1, 1 aux = f', 2 aux = tanh activation.
+template <int MAXC>
+__global__ void __launch_bounds__(256, 4) slice_delta_prev_transposed_kernel(const double *__restrict__ deltaL, int C,
+                                                                          const double *__restrict__ W, const double *aux,
+                                                                          int64_t rows, int64_t cols, int64_t ld, int mode,
+                                                                          const double *__restrict__ classmax,
+                                                                          double *scale, int8_t *__restrict__ out,
+                                                                          int64_t cols_pad, int64_t rows_pad, int64_t row_off) {
+    __shared__ uint32_t tile[OZ_S][32][33];
+    __shared__ __align__(16) double dl[128][MAXC];
+    const int64_t c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t c = c0 + tx;
+    double w[MAXC];
+    double bound = 0.0;
+#pragma unroll
+    for (int k = 0; k < MAXC; ++k) {
+        w[k] = (c < cols && k < C) ? W[c * C + k] : 0.0;
+        if (k < C) bound += classmax[k] * fabs(w[k]);        // NaN pattern in classmax -> NaN bound -> NaN scale
+    }
+    const double sc = oz_scale_of(bound);
+    unsigned long long *scale_bits = reinterpret_cast<unsigned long long *>(scale + row_off);
+    if (c < cols && blockIdx.x == 0 && ty == 0) atomicMax(scale_bits + c, (unsigned long long)__double_as_longlong(sc));
+    const double inv = sc == sc ? 1.0 / sc : 0.0;
+    bool bad = false;
+    for (int64_t r0 = blockIdx.x * 128; r0 < rows_pad; r0 += (int64_t)gridDim.x * 128) {
+        // the slope values are this kernel's HBM stream: the loads of group g + 1 are issued before group g is computed
+        double a[2][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t r = r0 + (ty * 4) * 4 + j;
+            a[0][j] = (mode != 0 && r < rows && c < cols) ? aux[r * ld + c] : 1.0;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 128 * MAXC; i += 256) {
+            const int r = i / MAXC, k = i - r * MAXC;
+            dl[r][k] = (r0 + r < rows && k < C) ? deltaL[(r0 + r) * C + k] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int wq = ty * 4 + g;             // word index along rows: rows r0 + 4 wq ..
+            uint32_t wd[OZ_S];
+            double v[4];
+            if (g < 3) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int64_t r = r0 + (wq + 1) * 4 + j;
+                    a[(g + 1) & 1][j] = (mode != 0 && r < rows && c < cols) ? aux[r * ld + c] : 1.0;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int rl = wq * 4 + j;
+                const int64_t r = r0 + rl;
+                const double2 *dp = reinterpret_cast<const double2 *>(&dl[rl][0]);      // 16-byte broadcast loads
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int k2 = 0; k2 < MAXC / 2; ++k2) {
+                    const double2 d = dp[k2];
+                    s0 = fma(d.x, w[2 * k2], s0);
+                    s1 = fma(d.y, w[2 * k2 + 1], s1);
+                }
+                const double s_ = s0 + s1;
+                double val = 0.0;
+                if (r < rows && c < cols) {
+                    val = mode == 2 ? s_ * (1.0 - a[g & 1][j] * a[g & 1][j]) : s_ * a[g & 1][j];
+                    bad |= !(fabs(val) <= 1.7976931348623157e308);
+                }
+                v[j] = val * inv;
+            }
+            oz_digits4(v, wd);
+#pragma unroll
+            for (int s = 0; s < OZ_S; ++s) tile[s][tx][wq] = wd[s];
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < OZ_S * 32 * 8; idx += 256) {
+            const int s = idx >> 8, cc = (idx >> 3) & 31, seg = idx & 7;
+            const int64_t oc = c0 + cc + row_off, r = r0 + seg * 16;
+            if (c0 + cc < cols && r < rows_pad) {
+                uint4 q;
+                q.x = tile[s][cc][seg * 4 + 0];
+                q.y = tile[s][cc][seg * 4 + 1];
+                q.z = tile[s][cc][seg * 4 + 2];
+                q.w = tile[s][cc][seg * 4 + 3];
+                *reinterpret_cast<uint4 *>(out + ((int64_t)s * cols_pad + oc) * rows_pad + r) = q;
+            }
+        }
+    }
+    if (bad && c < cols) atomicMax(scale_bits + c, 0x7ff8000000000000ULL);      // poison: the product becomes NaN
+}
+
 PFN_cuTensorMapEncodeTiled_v12000 oz_encode_fn() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
     if (!fn) {
@@ -911,6 +1014,24 @@ int ozaki_slice_cols_transposed(const double *src, int64_t rows, int64_t cols, i
         src, rows, cols, ld, scale + row_off, nullptr, slices, cp, rp, row_off, nullptr);
     OPL_LAUNCH_CHECK();
     if (launches) *launches += 3;
+    return OPL_OK;
+}
+
+int ozaki_slice_delta_prev(const double *deltaL, int C, const double *W, const double *aux, int mode, int64_t rows, int64_t cols,
+                           int64_t ld, const double *classmax, int8_t *slices, double *scale, int64_t m_pad,
+                           cudaStream_t stream, int64_t *launches) {
+    if (C < 1 || C > 16) return fail(OPL_E_ARG, "ozaki_slice_delta_prev: C must be in [1, 16]");
+    const int64_t cp = m_pad > 0 ? m_pad : ozaki_pad(cols), rp = ozaki_pad(rows);
+    OPL_CUDA(cudaMemsetAsync(scale, 0, sizeof(double) * (size_t)cols, stream));     // scales arrive by atomicMax on their bit patterns
+    const dim3 grid((unsigned)ceil_div(rp, 128), (unsigned)ceil_div(cols, 32));
+    if (C <= 12)
+        slice_delta_prev_transposed_kernel<12><<<grid, 256, 0, stream>>>(deltaL, C, W, aux, rows, cols, ld, mode, classmax, scale,
+                                                                         slices, cp, rp, 0);
+    else
+        slice_delta_prev_transposed_kernel<16><<<grid, 256, 0, stream>>>(deltaL, C, W, aux, rows, cols, ld, mode, classmax, scale,
+                                                                         slices, cp, rp, 0);
+    OPL_LAUNCH_CHECK();
+    if (launches) ++*launches;
     return OPL_OK;
 }
 

@@ -54,6 +54,12 @@ int ozaki_slice_rows(const double *src, int64_t rows, int64_t cols, int64_t ld, 
 int ozaki_slice_cols_transposed(const double *src, int64_t rows, int64_t cols, int64_t ld, int8_t *slices, double *scale,
                                 double *scratch, int64_t scratch_len, int64_t row_off, int64_t m_pad, const double *colmax_raw,
                                 cudaStream_t stream, int64_t *launches);
+// digits of delta_prev^T = ((deltaL W^T) o slope)^T formed on the fly from deltaL (rows x C, C <= 16), W (cols x C) and the slope
+// matrix aux (rows x cols, pitch ld; mode 0 none, 1 aux = f', 2 aux = tanh activation); classmax[c] = max_r |deltaL[r][c]| (raw
+// bit patterns as gathered by atomicMax).  Same output layout as ozaki_slice_cols_transposed: INT8 [S][m_pad][pad(rows)], scale[cols].
+int ozaki_slice_delta_prev(const double *deltaL, int C, const double *W, const double *aux, int mode, int64_t rows, int64_t cols,
+                           int64_t ld, const double *classmax, int8_t *slices, double *scale, int64_t m_pad,
+                           cudaStream_t stream, int64_t *launches);
 // row 0 of a transposed digit array [S][m_pad][pad(rows)] := a row of ones (scale[0] = 4): the bias-gradient row
 int ozaki_ones_row(int8_t *slices, double *scale, int64_t rows, int64_t m_pad, cudaStream_t stream, int64_t *launches);
 // FP64 fold of split-K partials is done by the caller (launch_reduce_partials)

@@ -165,6 +165,30 @@ def test_engines_agree_and_fused_head_matches_plain_schedule(L):
     assert rel_err(a._get_obj(w.copy(), x, y), ob) <= 1e-12
 
 
+@pytest.mark.parametrize("hidden", [(2, 0), (1, 0), (0, 0)])          # softplus / tanh / linear hidden layer
+def test_delta_digits_formed_on_the_fly_match_the_materialised_schedule(L, hidden, monkeypatch):
+    """Two-layer networks on the INT8 engine: the fused head leaves delta_0 = (delta_L W_1^T) o f' to the digit kernel of the
+    dW_0 GEMM (csrc/ozaki.cu ozaki_slice_delta_prev: digits cut straight from delta_L, W_1 and the slope matrix, scales from a
+    rigorous bound instead of the column maxima).  Against the oracle, and against the schedule that materialises delta_0
+    (OPL_DIRECT_DELTA=0), including weights 1e6 apart in scale between the classes (a loose bound must only cost digits)."""
+    rng = numpy.random.default_rng(11)
+    shape, transfers, eid = (200, 128, 10), [hidden, (4, 0)], 1
+    x, y = mo.random_classification(3000, 200, 10, rng)
+    w = mo.random_params(shape, rng)
+    w[128 + 200 * 128:].reshape(128, 10)[:, ::3] *= 1e-6               # some classes' weights six orders smaller
+    want_obj, want_grad = mo.objective_gradient(w, shape, transfers, eid, x, y, literal_softmax=False)
+    direct = _model(L, shape, transfers, eid)
+    obj_d, grad_d = direct._get_obj_jac(w.copy(), x, y)
+    monkeypatch.setenv("OPL_DIRECT_DELTA", "0")
+    plain = _model(L, shape, transfers, eid)
+    obj_p, grad_p = plain._get_obj_jac(w.copy(), x, y)
+    monkeypatch.delenv("OPL_DIRECT_DELTA")
+    assert rel_err(obj_d, want_obj) <= TOL and rel_err(grad_d, want_grad) <= TOL, rel_err(grad_d, want_grad)
+    assert rel_err(obj_p, want_obj) <= TOL and rel_err(grad_p, want_grad) <= TOL
+    assert obj_d == obj_p and rel_err(grad_d, grad_p) <= 1e-11, rel_err(grad_d, grad_p)
+    print("delta digits on the fly: grad vs oracle %.1e, vs materialised schedule %.1e" % (rel_err(grad_d, want_grad), rel_err(grad_d, grad_p)))
+
+
 @pytest.mark.parametrize("precision", ["f64", "f64-dmma"])
 def test_saturated_head_keeps_reference_semantics(L, precision):
     """Degenerate numerics on the fused-head / INT8 path: logits so large that target-class probabilities underflow to

@@ -1288,9 +1288,22 @@ int evaluate(opl_mlp *ws, const double *x_dev, double alpha, const double *dir_d
         mark(ws, STAGE_END * 100);
         return rc;
     }
-    trial_point_kernel<<<tgrid, 256, 0, ws->stream>>>(n, x_dev, alpha, dir_dev, ws->w_trial, ws->flag);
-    OPL_LAUNCH_CHECK();
-    ++ws->launches;
+    bool fused_trial = false;
+    if (ws->int8) ws->int8->w0_digits_ready = false;
+    if (!ws->masks && int8_fwd_ok(ws, 0, ws->x, ws->rows)) {
+        // INT8 forward layer 0: the trial point and the digits of W_0^T in one cooperative launch
+        Int8State *s8 = ws->int8;
+        rc = ozaki_trial_w0_digits(x_dev, dir_dev, alpha, ws->w_trial, n, ws->w_off[0], ws->width[0], ws->width[1], s8->w_dig,
+                                   s8->w_scale, s8->colmax, s8->colmax_len, ozaki_pad(ws->width[1]), ws->flag, ws->stream,
+                                   &ws->launches, &fused_trial);
+        if (rc != OPL_OK) return rc;
+        s8->w0_digits_ready = fused_trial;
+    }
+    if (!fused_trial) {
+        trial_point_kernel<<<tgrid, 256, 0, ws->stream>>>(n, x_dev, alpha, dir_dev, ws->w_trial, ws->flag);
+        OPL_LAUNCH_CHECK();
+        ++ws->launches;
+    }
     const int64_t w0_count = ws->width[0] * ws->width[1];
     const int mgrid = (int)std::min<int64_t>(ceil_div(w0_count, 256), 4 * (int64_t)sm_count());
     if (ws->masks) {   // (X o m) W0 == X (diag(m) W0) exactly for a 0/1 mask

@@ -33,6 +33,7 @@ struct Int8State {
     double *classmax = nullptr;        // 16 entries: max |delta_L[:, c]| of the fused head when it leaves delta_prev to the digit kernel
     double *dmax = nullptr;            // max |delta_l[:, j]| gathered by the kernel that writes delta_l (atomicMax), or unused
     int dmax_layer = -1;               // layer whose delta the maxima in dmax belong to (-1: none)
+    bool w0_digits_ready = false;      // the evaluation's first launch already cut the digits of W_0^T (ozaki_trial_w0_digits)
     int64_t colmax_len = 0;
 };
 // Padding: the digit kernels write zeros along the CONTRACTION index themselves (pad columns of a row-digit array,
@@ -192,10 +193,15 @@ int int8_forward_layer(opl_mlp *ws, int l, const double *w, const double *in, in
     const int64_t kp = ozaki_pad(din), np = ozaki_pad(dout), mp = ozaki_pad(rows);
     const bool last = l == ws->layers - 1;
     // B operand: W_l (din x dout row-major) -> digits of its transpose, one scale per output unit
-    mark(ws, STAGE_DIGITS * 100 + l);
-    int rc = ozaki_slice_cols_transposed(w + ws->w_off[l], din, dout, dout, s->w_dig, s->w_scale, s->colmax, s->colmax_len, 0,
+    int rc = OPL_OK;
+    if (l == 0 && s->w0_digits_ready) {
+        s->w0_digits_ready = false;              // cut together with the trial point
+    } else {
+        mark(ws, STAGE_DIGITS * 100 + l);
+        rc = ozaki_slice_cols_transposed(w + ws->w_off[l], din, dout, dout, s->w_dig, s->w_scale, s->colmax, s->colmax_len, 0,
                                          np, nullptr, ws->stream, &ws->launches);
-    if (rc != OPL_OK) return rc;
+        if (rc != OPL_OK) return rc;
+    }
     const int8_t *a_dig = s->x_dig;
     const double *a_scale = s->x_scale;
     int64_t a_rows_pad = ozaki_pad(s->x_rows);

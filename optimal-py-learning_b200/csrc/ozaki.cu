@@ -903,6 +903,115 @@ __global__ void __launch_bounds__(256, 4) slice_delta_prev_transposed_kernel(con
     if (bad && c < cols) atomicMax(scale_bits + c, 0x7ff8000000000000ULL);      // poison: the product becomes NaN
 }
 
+// Trial point AND the digits of W_0^T in one cooperative launch (an evaluation used to start with two: the trial-point kernel,
+// then the cooperative max + digit kernel of W_0): every block forms w = x + fl(alpha dir) for its 128 x 32 patch of W_0, writes
+// it to the trial vector and takes the patch's column maxima; the blocks also share the rest of the parameter vector (bias, the
+// other layers); after the grid barrier the column maxima are folded and the patch is cut into digits (MODE 3 of
+// slice_cols_transposed_kernel, same arithmetic and layout).
+struct TrialW0Args {
+    const double *x, *dir;     // parameters, direction (may be null)
+    double alpha;
+    double *w;                 // trial vector out (n entries)
+    int64_t n, off;            // W_0 starts at `off` of the flat vector
+    int64_t rows, cols;        // W_0 is rows x cols row-major (d0 x d1)
+    double *scale;             // cols scales out
+    int8_t *out;               // digits of W_0^T: [S][cols_pad][rows_pad]
+    int64_t cols_pad, rows_pad;
+    double *partial;           // gridDim.x x cols column maxima
+    int *flag;                 // domain flag of the evaluation, reset here
+};
+
+__global__ void __launch_bounds__(256) trial_w0_digits_kernel(const TrialW0Args a) {
+    __shared__ uint32_t tile[OZ_S][32][33];
+    __shared__ double smax[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t c0 = blockIdx.y * 32, c = c0 + tx;
+    const int64_t rb = blockIdx.x * 128;
+    const double *x0 = a.x + a.off, *d0 = a.dir ? a.dir + a.off : nullptr;
+    double *w0 = a.w + a.off;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *a.flag = 0;
+    // ---- the rest of the vector (everything outside W_0), shared by all blocks ----
+    {
+        const int64_t nb = (int64_t)gridDim.x * gridDim.y, b = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
+        const int64_t w0_len = a.rows * a.cols, rest = a.n - w0_len;
+        for (int64_t i = b * 256 + threadIdx.x; i < rest; i += nb * 256) {
+            const int64_t e = i < a.off ? i : i + w0_len;
+            a.w[e] = a.dir ? __dadd_rn(a.x[e], __dmul_rn(a.alpha, a.dir[e])) : a.x[e];
+        }
+    }
+    // ---- pass 1: trial values of this patch, written out, and their column maxima ----
+    double m = 0.0;
+    bool bad = false;
+    if (c < a.cols)
+        for (int64_t r = rb + ty; r < min(a.rows, rb + 128); r += 8) {
+            const int64_t e = r * a.cols + c;
+            const double v = d0 ? __dadd_rn(x0[e], __dmul_rn(a.alpha, d0[e])) : x0[e];
+            w0[e] = v;
+            const double av = fabs(v);
+            bad |= !(av <= 1.7976931348623157e308);
+            m = fmax(m, av);
+        }
+    smax[ty][tx] = bad ? __longlong_as_double(0x7ff8000000000000LL) : m;
+    __syncthreads();
+    if (ty == 0 && c < a.cols) {
+        double t = 0.0;
+        bool nan = false;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const double v = smax[k][tx];
+            nan |= v != v;
+            t = fmax(t, v);
+        }
+        a.partial[blockIdx.x * a.cols + c] = nan ? __longlong_as_double(0x7ff8000000000000LL) : t;
+    }
+    __threadfence();
+    cooperative_groups::this_grid().sync();
+    double sc = 1.0;
+    if (c < a.cols) {
+        double t = 0.0;
+        bool nan = false;
+        for (unsigned k = 0; k < gridDim.x; ++k) {
+            const double v = __ldcg(a.partial + k * a.cols + c);
+            nan |= v != v;
+            t = fmax(t, v);
+        }
+        sc = nan ? __longlong_as_double(0x7ff8000000000000LL) : oz_scale_of(t);
+        if (blockIdx.x == 0 && ty == 0) a.scale[c] = sc;
+    }
+    const double inv = sc == sc ? 1.0 / sc : 0.0;
+    // ---- pass 2: digits of the patch (it was written by this very block: visible after the barrier) ----
+    const int64_t r0 = rb;
+    if (r0 < a.rows_pad) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int wq = ty * 4 + g;
+            uint32_t wd[OZ_S];
+            double v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t r = r0 + wq * 4 + j;
+                v[j] = (r < a.rows && c < a.cols) ? __ldcg(w0 + r * a.cols + c) * inv : 0.0;
+            }
+            oz_digits4(v, wd);
+#pragma unroll
+            for (int s = 0; s < OZ_S; ++s) tile[s][tx][wq] = wd[s];
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < OZ_S * 32 * 8; idx += 256) {
+            const int s = idx >> 8, cc = (idx >> 3) & 31, seg = idx & 7;
+            const int64_t oc = c0 + cc, r = r0 + seg * 16;
+            if (c0 + cc < a.cols && r < a.rows_pad) {
+                uint4 q;
+                q.x = tile[s][cc][seg * 4 + 0];
+                q.y = tile[s][cc][seg * 4 + 1];
+                q.z = tile[s][cc][seg * 4 + 2];
+                q.w = tile[s][cc][seg * 4 + 3];
+                *reinterpret_cast<uint4 *>(a.out + ((int64_t)s * a.cols_pad + oc) * a.rows_pad + r) = q;
+            }
+        }
+    }
+}
+
 PFN_cuTensorMapEncodeTiled_v12000 oz_encode_fn() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
     if (!fn) {
@@ -1014,6 +1123,44 @@ int ozaki_slice_cols_transposed(const double *src, int64_t rows, int64_t cols, i
         src, rows, cols, ld, scale + row_off, nullptr, slices, cp, rp, row_off, nullptr);
     OPL_LAUNCH_CHECK();
     if (launches) *launches += 3;
+    return OPL_OK;
+}
+
+// *done = true when the fused launch ran (the grid must be co-resident); otherwise nothing was enqueued and the caller runs the
+// trial-point kernel and the plain digit pass
+int ozaki_trial_w0_digits(const double *x, const double *dir, double alpha, double *w, int64_t n, int64_t off, int64_t rows,
+                          int64_t cols, int8_t *slices, double *scale, double *scratch, int64_t scratch_len, int64_t m_pad,
+                          int *flag, cudaStream_t stream, int64_t *launches, bool *done) {
+    *done = false;
+    const int64_t rp = ozaki_pad(rows), cp = m_pad > 0 ? m_pad : ozaki_pad(cols);
+    const int64_t gx = ceil_div(rp, 128), gy = ceil_div(cols, 32);
+    static int per_sm = -1;
+    if (per_sm < 0) {
+        int v = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, trial_w0_digits_kernel, 256, 0) != cudaSuccess) v = 0;
+        per_sm = v;
+    }
+    if (rows <= 256 || gx * gy > (int64_t)per_sm * sm_count() || gx * cols > scratch_len) return OPL_OK;
+    TrialW0Args a = {};
+    a.x = x;
+    a.dir = dir;
+    a.alpha = alpha;
+    a.w = w;
+    a.n = n;
+    a.off = off;
+    a.rows = rows;
+    a.cols = cols;
+    a.scale = scale;
+    a.out = slices;
+    a.cols_pad = cp;
+    a.rows_pad = rp;
+    a.partial = scratch;
+    a.flag = flag;
+    void *params[] = {(void *)&a};
+    OPL_CUDA(cudaLaunchCooperativeKernel((const void *)trial_w0_digits_kernel, dim3((unsigned)gx, (unsigned)gy), dim3(256), params, 0,
+                                         stream));
+    if (launches) ++*launches;
+    *done = true;
     return OPL_OK;
 }
 

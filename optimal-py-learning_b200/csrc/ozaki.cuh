@@ -54,6 +54,12 @@ int ozaki_slice_rows(const double *src, int64_t rows, int64_t cols, int64_t ld, 
 int ozaki_slice_cols_transposed(const double *src, int64_t rows, int64_t cols, int64_t ld, int8_t *slices, double *scale,
                                 double *scratch, int64_t scratch_len, int64_t row_off, int64_t m_pad, const double *colmax_raw,
                                 cudaStream_t stream, int64_t *launches);
+// trial point w = x + fl(alpha dir) (whole flat vector, n entries) AND the digits of W_0^T (W_0 = w[off : off + rows cols],
+// rows x cols row-major; output as ozaki_slice_cols_transposed) in ONE cooperative launch; also resets the evaluation's
+// domain flag.  *done = false: the grid does not fit, nothing was enqueued.
+int ozaki_trial_w0_digits(const double *x, const double *dir, double alpha, double *w, int64_t n, int64_t off, int64_t rows,
+                          int64_t cols, int8_t *slices, double *scale, double *scratch, int64_t scratch_len, int64_t m_pad,
+                          int *flag, cudaStream_t stream, int64_t *launches, bool *done);
 // digits of delta_prev^T = ((deltaL W^T) o slope)^T formed on the fly from deltaL (rows x C, C <= 16), W (cols x C) and the slope
 // matrix aux (rows x cols, pitch ld; mode 0 none, 1 aux = f', 2 aux = tanh activation); classmax[c] = max_r |deltaL[r][c]| (raw
 // bit patterns as gathered by atomicMax).  Same output layout as ozaki_slice_cols_transposed: INT8 [S][m_pad][pad(rows)], scale[cols].

@@ -812,10 +812,10 @@ __global__ void __launch_bounds__(256) slice_cols_transposed_kernel(const double
 // A non-finite value poisons the column's scale (NaN pattern by atomicMax), as the plain pass does.
 // Block = 128 rows x 32 columns (as slice_cols_transposed_kernel); the block's deltaL rows sit in shared memory (broadcast
 // reads), a thread keeps its column's row of W in registers.  mode: 0 slope 1, 1 aux = f', 2 aux = tanh activation.
-template <int MAXC>
+template <int MAXC, int MODE>
 __global__ void __launch_bounds__(256, 4) slice_delta_prev_transposed_kernel(const double *__restrict__ deltaL, int C,
                                                                           const double *__restrict__ W, const double *aux,
-                                                                          int64_t rows, int64_t cols, int64_t ld, int mode,
+                                                                          int64_t rows, int64_t cols, int64_t ld,
                                                                           const double *__restrict__ classmax,
                                                                           double *scale, int8_t *__restrict__ out,
                                                                           int64_t cols_pad, int64_t rows_pad, int64_t row_off) {
@@ -836,48 +836,104 @@ __global__ void __launch_bounds__(256, 4) slice_delta_prev_transposed_kernel(con
     if (c < cols && blockIdx.x == 0 && ty == 0) atomicMax(scale_bits + c, (unsigned long long)__double_as_longlong(sc));
     const double inv = sc == sc ? 1.0 / sc : 0.0;
     bool bad = false;
+    const int64_t plane = cols_pad * rows_pad;
     for (int64_t r0 = blockIdx.x * 128; r0 < rows_pad; r0 += (int64_t)gridDim.x * 128) {
-        // the slope values are this kernel's HBM stream: the loads of group g + 1 are issued before group g is computed
-        double a[2][4];
+        if (r0 + 128 <= rows && c0 + 32 <= cols) {
+            // ---- interior tile: no bounds tests, pointers stepped instead of re-derived (the kernel was bound by its
+            //      integer / predicate instructions, ~60 of 119 per element; profiles/r02_ncu_eval_kernels.txt) ----
+            const double *ap = aux + (r0 + ty * 16) * ld + c;     // the slope values are this kernel's HBM stream
+            double a[2][4];
+            if (MODE != 0) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int64_t r = r0 + (ty * 4) * 4 + j;
-            a[0][j] = (mode != 0 && r < rows && c < cols) ? aux[r * ld + c] : 1.0;
+                for (int j = 0; j < 4; ++j, ap += ld) a[0][j] = *ap;
+            }
+            __syncthreads();
+            if (MAXC == C) {                                       // rows r0 .. r0 + 127 of delta_L are one contiguous block
+                const double *src = deltaL + r0 * MAXC;
+                double *dst = &dl[0][0];
+#pragma unroll
+                for (int i = 0; i < (128 * MAXC + 255) / 256; ++i) {
+                    const int e = i * 256 + (int)threadIdx.x;
+                    if ((128 * MAXC) % 256 == 0 || e < 128 * MAXC) dst[e] = src[e];
+                }
+            } else {
+                for (int i = threadIdx.x; i < 128 * MAXC; i += 256) {
+                    const int r = i / MAXC, k = i - r * MAXC;
+                    dl[r][k] = k < C ? deltaL[(r0 + r) * C + k] : 0.0;
+                }
+            }
+            __syncthreads();
+            double chk = 0.0;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                uint32_t wd[OZ_S];
+                double v[4];
+                if (MODE != 0 && g < 3) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j, ap += ld) a[(g + 1) & 1][j] = *ap;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const double2 *dp = reinterpret_cast<const double2 *>(&dl[ty * 16 + g * 4 + j][0]);   // 16-byte broadcasts
+                    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                    for (int k2 = 0; k2 < MAXC / 2; ++k2) {
+                        const double2 d = dp[k2];
+                        s0 = fma(d.x, w[2 * k2], s0);
+                        s1 = fma(d.y, w[2 * k2 + 1], s1);
+                    }
+                    const double s_ = s0 + s1;
+                    const double val = MODE == 2 ? s_ * (1.0 - a[g & 1][j] * a[g & 1][j]) : (MODE == 1 ? s_ * a[g & 1][j] : s_);
+                    v[j] = val * inv;
+                }
+                chk = fma((v[0] + v[1]) + (v[2] + v[3]), 0.0, chk);   // inf or NaN anywhere -> NaN
+                oz_digits4(v, wd);
+#pragma unroll
+                for (int s = 0; s < OZ_S; ++s) tile[s][tx][ty * 4 + g] = wd[s];
+            }
+            bad |= chk != chk;
+            __syncthreads();
+            // every thread owns one 16-byte segment of one output row, in each of the digit planes
+            const int cc = threadIdx.x >> 3, seg = threadIdx.x & 7;
+            int8_t *op = out + (c0 + cc + row_off) * rows_pad + r0 + seg * 16;
+#pragma unroll
+            for (int s = 0; s < OZ_S; ++s, op += plane) {
+                uint4 q;
+                q.x = tile[s][cc][seg * 4 + 0];
+                q.y = tile[s][cc][seg * 4 + 1];
+                q.z = tile[s][cc][seg * 4 + 2];
+                q.w = tile[s][cc][seg * 4 + 3];
+                *reinterpret_cast<uint4 *>(op) = q;
+            }
+            continue;
         }
+        // ---- edge tile ----
         __syncthreads();
         for (int i = threadIdx.x; i < 128 * MAXC; i += 256) {
             const int r = i / MAXC, k = i - r * MAXC;
             dl[r][k] = (r0 + r < rows && k < C) ? deltaL[(r0 + r) * C + k] : 0.0;
         }
         __syncthreads();
-#pragma unroll
+#pragma unroll 1
         for (int g = 0; g < 4; ++g) {
             const int wq = ty * 4 + g;             // word index along rows: rows r0 + 4 wq ..
             uint32_t wd[OZ_S];
             double v[4];
-            if (g < 3) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int64_t r = r0 + (wq + 1) * 4 + j;
-                    a[(g + 1) & 1][j] = (mode != 0 && r < rows && c < cols) ? aux[r * ld + c] : 1.0;
-                }
-            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int rl = wq * 4 + j;
                 const int64_t r = r0 + rl;
-                const double2 *dp = reinterpret_cast<const double2 *>(&dl[rl][0]);      // 16-byte broadcast loads
-                double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-                for (int k2 = 0; k2 < MAXC / 2; ++k2) {
-                    const double2 d = dp[k2];
-                    s0 = fma(d.x, w[2 * k2], s0);
-                    s1 = fma(d.y, w[2 * k2 + 1], s1);
-                }
-                const double s_ = s0 + s1;
                 double val = 0.0;
                 if (r < rows && c < cols) {
-                    val = mode == 2 ? s_ * (1.0 - a[g & 1][j] * a[g & 1][j]) : s_ * a[g & 1][j];
+                    double s0 = 0.0, s1 = 0.0;             // same summation order as the interior tiles
+#pragma unroll
+                    for (int k2 = 0; k2 < MAXC / 2; ++k2) {
+                        s0 = fma(dl[rl][2 * k2], w[2 * k2], s0);
+                        s1 = fma(dl[rl][2 * k2 + 1], w[2 * k2 + 1], s1);
+                    }
+                    const double s_ = s0 + s1;
+                    const double av = MODE != 0 ? aux[r * ld + c] : 1.0;
+                    val = MODE == 2 ? s_ * (1.0 - av * av) : (MODE == 1 ? s_ * av : s_);
                     bad |= !(fabs(val) <= 1.7976931348623157e308);
                 }
                 v[j] = val * inv;
@@ -1171,12 +1227,23 @@ int ozaki_slice_delta_prev(const double *deltaL, int C, const double *W, const d
     const int64_t cp = m_pad > 0 ? m_pad : ozaki_pad(cols), rp = ozaki_pad(rows);
     OPL_CUDA(cudaMemsetAsync(scale, 0, sizeof(double) * (size_t)cols, stream));     // scales arrive by atomicMax on their bit patterns
     const dim3 grid((unsigned)ceil_div(rp, 128), (unsigned)ceil_div(cols, 32));
-    if (C <= 12)
-        slice_delta_prev_transposed_kernel<12><<<grid, 256, 0, stream>>>(deltaL, C, W, aux, rows, cols, ld, mode, classmax, scale,
-                                                                         slices, cp, rp, 0);
-    else
-        slice_delta_prev_transposed_kernel<16><<<grid, 256, 0, stream>>>(deltaL, C, W, aux, rows, cols, ld, mode, classmax, scale,
-                                                                         slices, cp, rp, 0);
+#define OPL_DP_LAUNCH(CE, MD)                                                                                               \
+    slice_delta_prev_transposed_kernel<CE, MD><<<grid, 256, 0, stream>>>(deltaL, C, W, aux, rows, cols, ld, classmax, scale, \
+                                                                         slices, cp, rp, 0)
+#define OPL_DP_MODES(CE)                                                       \
+    do {                                                                       \
+        if (mode == 1) OPL_DP_LAUNCH(CE, 1);                                   \
+        else if (mode == 2) OPL_DP_LAUNCH(CE, 2);                              \
+        else OPL_DP_LAUNCH(CE, 0);                                             \
+    } while (0)
+    // class count rounded up to an even template width; exact widths stage delta_L as one contiguous copy
+    if (C <= 4) OPL_DP_MODES(4);
+    else if (C <= 8) OPL_DP_MODES(8);
+    else if (C <= 10) OPL_DP_MODES(10);
+    else if (C <= 12) OPL_DP_MODES(12);
+    else OPL_DP_MODES(16);
+#undef OPL_DP_MODES
+#undef OPL_DP_LAUNCH
     OPL_LAUNCH_CHECK();
     if (launches) ++*launches;
     return OPL_OK;

@@ -64,6 +64,11 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, boo
     int n = valid ? 16 : 0;   // src-size 0 => zero fill
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gsrc), "r"(n));
 }
+// same with the destination as a shared-window address (callers that step through a row keep it in a register)
+__device__ __forceinline__ void cp_async16_s(unsigned smem_addr, const void *gsrc, bool valid) {
+    int n = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_addr), "l"(gsrc), "r"(n));
+}
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc, bool valid) {
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     int n = valid ? 8 : 0;

@@ -361,10 +361,15 @@ __device__ __forceinline__ double2 head_store2(float *p, double a, double b) {
 // Two shapes: R = 32 patterns per step with 16 warps (one CTA per SM) or R = 16 with 8 warps (two CTAs per SM, whose
 // latency-bound row stages and DMMA phases overlap each other).
 // tools only (OPL_HEAD_TRACE): phase stamps of CTA 0, thread 0; evaluated in place so that nothing stays live
+// (compiled in with -DOPL_HEAD_TRACE_BUILD only: the eight predicate tests per step were 5 % of the kernel's instructions)
+#ifdef OPL_HEAD_TRACE_BUILD
 #define HEAD_STAMP(k)                                                                       \
     do {                                                                                    \
         if (p.trace && blockIdx.x == 0 && threadIdx.x == 0 && step_no < 16) p.trace[step_no * 8 + (k)] = clock64(); \
     } while (0)
+#else
+#define HEAD_STAMP(k) ((void)0)
+#endif
 // DA == false: the head does NOT form delta_prev = (delta_L W^T) o slope (a third of its DMMA work, the slope matrix read and the
 // delta_prev write): it writes delta_L (rows x C) and the per-class maxima instead, and the digit kernel of the weight-gradient
 // GEMM forms delta_prev on the fly (ozaki_slice_delta_prev, csrc/ozaki.cu).  `backward` then only means "accumulate dW".
@@ -388,12 +393,16 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, R == 16 ? 2 : 1) narrow_head_
     bool lbad = false;
     const int64_t nblocks = (p.rows + R - 1) / R;
     auto fetch = [&](int64_t blk, int buf) {   // cp.async the block's activations (rows past the end := 0)
+        // a warp per row, lanes along the row: no index division, one address per row (the i / h2 form of this loop was 38 %
+        // of the kernel's instructions; profiles/r02_head_instruction_mix.txt)
         const int64_t r0 = blk * R;
-        T *dst = As0 + (size_t)buf * R * ldA;
-        for (int i = threadIdx.x; i < R * h2; i += HEAD_THREADS) {
-            const int r = i / h2, c2 = i - r * h2;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(As0) + (unsigned)(buf * R * ldA) * (unsigned)sizeof(T);
+#pragma unroll
+        for (int r = warp; r < R; r += HEAD_WARPS) {
             const bool ok = r0 + r < p.rows;
-            cp_async16(dst + (size_t)r * ldA + EPC * c2, p.A + (ok ? (r0 + r) * p.ld + EPC * c2 : 0), ok);
+            const T *src = p.A + (ok ? (r0 + r) * p.ld : 0) + EPC * lane;
+            unsigned d = dst + (unsigned)(r * ldA + EPC * lane) * (unsigned)sizeof(T);
+            for (int c2 = lane; c2 < h2; c2 += 32, src += EPC * 32, d += 512) cp_async16_s(d, ok ? src : p.A, ok);
         }
         cp_async_commit();
     };
@@ -421,7 +430,7 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, R == 16 ? 2 : 1) narrow_head_
         HEAD_STAMP(0);
         const int64_t r0 = blk * R;
         const int nr = (int)min((int64_t)R, p.rows - r0);
-        const T *As = As0 + (size_t)buf * R * ldA;
+        const T *As = As0 + buf * R * ldA;
         // slope values of this step's delta_prev tiles: requested now, used after the row stage
         double2 x[DA ? MT : 1][RM];
         if (DA && backward && p.mode != 0) {
@@ -454,14 +463,15 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, R == 16 ? 2 : 1) narrow_head_
             // the two resident CTAs share, 3.9 cycles per DMMA per SM, not by the chain latency)
             double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
             const int kq = H >> 3;                                // DMMA steps per half
-            const T *ap = As + (size_t)(8 * mt + g) * ldA + 4 * kh * kq + t;
-            const double *bp = Ws + (size_t)(4 * kh * kq + t) * ldW + 8 * nt + g;
+            const T *ap = As + (8 * mt + g) * ldA + 4 * kh * kq + t;
+            const double *bp = Ws + (4 * kh * kq + t) * ldW + 8 * nt + g;
             int k = 0;
-            for (; k + 1 < kq; k += 2) {
-                dmma_8x8x4(c0, c1, (double)ap[4 * k], bp[4 * k * ldW]);
-                dmma_8x8x4(e0, e1, (double)ap[4 * k + 4], bp[(4 * k + 4) * ldW]);
+#pragma unroll 4
+            for (; k + 1 < kq; k += 2, ap += 8, bp += 8 * ldW) {
+                dmma_8x8x4(c0, c1, (double)ap[0], bp[0]);
+                dmma_8x8x4(e0, e1, (double)ap[4], bp[4 * ldW]);
             }
-            if (k < kq) dmma_8x8x4(c0, c1, (double)ap[4 * k], bp[4 * k * ldW]);
+            if (k < kq) dmma_8x8x4(c0, c1, (double)ap[0], bp[0]);
             c0 += e0;
             c1 += e1;
             double *zp = Zs + (8 * mt + g) * ldD + 8 * nt + 2 * t;
@@ -577,13 +587,13 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, R == 16 ? 2 : 1) narrow_head_
         for (int i = 0; i < MT; ++i) {
             const int mt = warp + HEAD_WARPS * i;        // hidden tile
             if (8 * mt >= H) break;
-            const T *ap = As + (size_t)t * ldA + 8 * mt + g;
+            const T *ap = As + t * ldA + 8 * mt + g;
+            const int ldA4 = 4 * ldA;
 #pragma unroll
             for (int n = 0; n < 2; ++n) {
                 const double *bp = Zs + t * ldD + 8 * n + g;
 #pragma unroll
-                for (int k = 0; k < R / 4; ++k)
-                    dmma_8x8x4(dw[i][n][0], dw[i][n][1], (double)ap[(size_t)4 * k * ldA], bp[4 * k * ldD]);
+                for (int k = 0; k < R / 4; ++k) dmma_8x8x4(dw[i][n][0], dw[i][n][1], (double)ap[k * ldA4], bp[4 * k * ldD]);
             }
         }
         HEAD_STAMP(7);
@@ -1212,6 +1222,14 @@ int fused_head(opl_mlp *ws, const double *w, const double *y, int64_t rows, bool
     }
     static long long *head_trace = nullptr;
     const char *trace_path = getenv("OPL_HEAD_TRACE");
+#ifndef OPL_HEAD_TRACE_BUILD
+    if (trace_path) {
+        static bool told = false;
+        if (!told) fprintf(stderr, "opl_b200: OPL_HEAD_TRACE needs a library built with -DOPL_HEAD_TRACE_BUILD; ignored\n");
+        told = true;
+        trace_path = nullptr;
+    }
+#endif
     if (trace_path && !head_trace) {
         OPL_CUDA(cudaMalloc(&head_trace, sizeof(long long) * 128));
         OPL_CUDA(cudaMemset(head_trace, 0, sizeof(long long) * 128));

@@ -550,13 +550,14 @@ __global__ void __launch_bounds__(FH_THREADS, 3) narrow_head_tf32_kernel(const H
     const bool backward = p.delta_prev != nullptr;
     const int h4 = H >> 2;                    // 16-byte chunks per row
     const int64_t nblocks = (p.rows + FH_R - 1) / FH_R;
-    auto fetch = [&](int64_t blk, int buf) {
+    auto fetch = [&](int64_t blk, int buf) {   // a warp per row, lanes along the row (as narrow_head_kernel)
         const int64_t r0 = blk * FH_R;
-        float *dst = As0 + (size_t)buf * FH_R * ldA;
-        for (int i = threadIdx.x; i < FH_R * h4; i += FH_THREADS) {
-            const int r = i / h4, c4 = i - r * h4;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(As0) + (unsigned)(buf * FH_R * ldA) * 4u;
+        for (int r = warp; r < FH_R; r += FH_THREADS / 32) {
             const bool ok = r0 + r < p.rows;
-            cp_async16(dst + (size_t)r * ldA + 4 * c4, p.A + (ok ? (r0 + r) * p.ld + 4 * c4 : 0), ok);
+            const float *src = p.A + (ok ? (r0 + r) * p.ld : 0) + 4 * lane;
+            unsigned d = dst + (unsigned)(r * ldA + 4 * lane) * 4u;
+            for (int c4 = lane; c4 < h4; c4 += 32, src += 128, d += 512) cp_async16_s(d, ok ? src : p.A, ok);
         }
         cp_async_commit();
     };

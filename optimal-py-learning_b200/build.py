@@ -28,6 +28,8 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function",
     "-I", os.path.join(ROOT, "include"), "-I", CSRC,
 ]
+# tools only (e.g. OPL_EXTRA_NVCC_FLAGS=-DOPL_HEAD_TRACE_BUILD): part of the digest, so the library is rebuilt when it changes
+NVCC_FLAGS += os.environ.get("OPL_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _nvcc():

@@ -320,6 +320,7 @@ struct HeadArgsT {
     double *colsum_partial; // gridDim.x x H: column sums of delta_prev (the bias gradient when delta_prev is delta_0) or null
     double *delta_out;      // DA == false: rows x C delta_L written out (delta_prev is then formed by the digit kernel), else unused
     double *classmax;       // DA == false: C entries, max |delta_L[:, c]| (atomicMax on bit patterns)
+    T *deriv_out;           // ZIN: rows x H slope values f'(z) out (row stride ld), or null (objective only)
     int64_t rows;
     int64_t ld;
     int H, C, R;            // R rows per block step
@@ -373,8 +374,14 @@ __device__ __forceinline__ double2 head_store2(float *p, double a, double b) {
 // DA == false: the head does NOT form delta_prev = (delta_L W^T) o slope (a third of its DMMA work, the slope matrix read and the
 // delta_prev write): it writes delta_L (rows x C) and the per-class maxima instead, and the digit kernel of the weight-gradient
 // GEMM forms delta_prev on the fly (ozaki_slice_delta_prev, csrc/ozaki.cu).  `backward` then only means "accumulate dW".
-template <typename T, int MT, int R, int HEAD_WARPS, bool CSUM, bool DA = true>    // MT = hidden tiles (8 units) per warp: H <= 8 MT HEAD_WARPS
+// ZIN: `A` holds the hidden PRE-activations z (the forward digit GEMM ran with a plain-store epilogue) and the head applies the
+// hidden softplus itself: every landed tile is transformed in place (same routine, same arguments, hence the same bits as the GEMM
+// epilogue would have produced) and the slope values f'(z) go out to `deriv_out` for the digit kernel.  Why here: FP64
+// instructions do not overlap tcgen05.mma (profiles/r02_ozaki_epilogue_decomposition.txt) -- in the GEMM epilogue the 27 FP64
+// instructions per element are exposed time on top of the MMAs, here they fill FP64 issue slots this latency-bound kernel leaves idle.
+template <typename T, int MT, int R, int HEAD_WARPS, bool CSUM, bool DA = true, bool ZIN = false>    // MT = hidden tiles (8 units) per warp: H <= 8 MT HEAD_WARPS
 __global__ void __launch_bounds__(HEAD_WARPS * 32, R == 16 ? 2 : 1) narrow_head_kernel(const HeadArgsT<T> p) {
+    static_assert(!ZIN || (sizeof(T) == 8 && !DA), "the late hidden transfer exists for the FP64 head without delta_prev");
     extern __shared__ double hsm[];
     __shared__ double scratch[33];
     constexpr int RM = R / 8, HEAD_THREADS = HEAD_WARPS * 32;
@@ -456,6 +463,39 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32, R == 16 ? 2 : 1) narrow_head_
         __syncthreads();                       // tile `buf` landed, Zs cleared, previous step done with the other buffer
         HEAD_STAMP(1);
         if (blk + gridDim.x < nblocks) fetch(blk + gridDim.x, buf ^ 1);
+        if (ZIN) {
+            // ---- hidden transfer, in place: a warp per row, 8 elements (four 16-byte chunks) per lane and pass so that eight
+            //      FP64 chains interleave; rows past the end stay zero ----
+            double *Az = reinterpret_cast<double *>(As0) + buf * R * ldA;
+            for (int r = warp; r < nr; r += HEAD_WARPS) {
+                double *row = Az + r * ldA;
+                double *dg = p.deriv_out ? reinterpret_cast<double *>(p.deriv_out) + (r0 + r) * p.ld : nullptr;
+                for (int cb = 0; cb < H; cb += 256) {      // warp-uniform trip count (the vote below needs every lane)
+                    const int c = cb + 2 * lane;
+                    double zz[8], sp[8], sg[8];
+                    bool regular = true;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int cq = c + 64 * q;
+                        const double2 v = cq < H ? *reinterpret_cast<const double2 *>(row + cq) : make_double2(0.0, 0.0);
+                        zz[2 * q] = v.x;
+                        zz[2 * q + 1] = v.y;
+                        regular &= ozt_is_regular(v.x) && ozt_is_regular(v.y);
+                    }
+                    if (__all_sync(0xffffffffu, regular)) ozt_softplus_logistic_regular_n<8>(zz, sp, sg);
+                    else ozt_softplus_logistic_n<8>(zz, sp, sg);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int cq = c + 64 * q;
+                        if (cq < H) {
+                            *reinterpret_cast<double2 *>(row + cq) = make_double2(sp[2 * q], sp[2 * q + 1]);
+                            if (dg) *reinterpret_cast<double2 *>(dg + cq) = make_double2(sg[2 * q], sg[2 * q + 1]);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
         // ---- logits: warp -> (row tile, class tile, K half); the two halves add up in Zs ----
         {
             const int mt = warp % RM, nt = (warp / RM) & 1, kh = warp / (2 * RM);
@@ -828,6 +868,8 @@ struct opl_mlp {
     int64_t launches = 0;
     // one-launch path for small networks (mlp_small.inl)
     bool direct_delta_digits = true;     // two-layer INT8 schedule: delta_0 only as digits (OPL_DIRECT_DELTA=0: materialise it)
+    bool late_transfer = true;           // two-layer INT8 schedule, softplus hidden layer: the forward GEMM stores z, the fused
+                                         // head applies the transfer (OPL_LATE_TRANSFER=0: in the GEMM epilogue)
     bool small_path = true;
     bool small_configured = false;
     size_t small_smem = 0;
@@ -1172,7 +1214,8 @@ bool head_skips_delta_prev(const opl_mlp *ws, int64_t rows) {
 }
 
 // fused head: objective (and, when want_grad, dW_{L-1} and delta_{L-2}); the caller continues back-propagation at L-2
-int fused_head(opl_mlp *ws, const double *w, const double *y, int64_t rows, bool want_grad, double *grad, double *obj_out) {
+int fused_head(opl_mlp *ws, const double *w, const double *y, int64_t rows, bool want_grad, double *grad, double *obj_out,
+               bool late_transfer = false) {
     const int L = ws->layers, R = head_rows_per_step(ws);
     const int H = (int)ws->width[L - 1], C = (int)ws->width[L];
     const size_t smem = head_smem(H, R);
@@ -1198,6 +1241,8 @@ int fused_head(opl_mlp *ws, const double *w, const double *y, int64_t rows, bool
     a.flag = ws->flag;
     a.loss_partial = ws->loss_partial;
     const bool no_da = want_grad && R == 16 && head_skips_delta_prev(ws, rows);
+    if (late_transfer && (R != 16 || (want_grad && !no_da))) return fail(OPL_E_STATE, "fused head: late transfer without its schedule");
+    if (late_transfer && want_grad) a.deriv_out = ws->deriv[L - 2];
     if (want_grad) {
         const int t = ws->transfer[L - 2];
         a.mode = (t == OPL_TRANSFER_SOFTPLUS || t == OPL_TRANSFER_GAUSSIAN) ? 1 : (t == OPL_TRANSFER_TANH ? 2 : 0);
@@ -1218,6 +1263,7 @@ int fused_head(opl_mlp *ws, const double *w, const double *y, int64_t rows, bool
         OPL_CUDA(cudaFuncSetAttribute(narrow_head_kernel<double, 2, 32, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_smem(256, 32)));
         OPL_CUDA(cudaFuncSetAttribute(narrow_head_kernel<double, 4, 16, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_smem(256, 16)));
         OPL_CUDA(cudaFuncSetAttribute(narrow_head_kernel<double, 4, 16, 8, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_smem(256, 16)));
+        OPL_CUDA(cudaFuncSetAttribute(narrow_head_kernel<double, 4, 16, 8, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)head_smem(256, 16)));
         configured = true;
     }
     static long long *head_trace = nullptr;
@@ -1238,6 +1284,8 @@ int fused_head(opl_mlp *ws, const double *w, const double *y, int64_t rows, bool
     mark(ws, STAGE_HEAD * 100 + L - 1);
     if (R == 32)
         narrow_head_kernel<double, 2, 32, 16, false><<<grid, 512, smem, ws->stream>>>(a);
+    else if (late_transfer)
+        narrow_head_kernel<double, 4, 16, 8, false, false, true><<<grid, 256, smem, ws->stream>>>(a);
     else if (no_da)
         narrow_head_kernel<double, 4, 16, 8, false, false><<<grid, 256, smem, ws->stream>>>(a);
     else
@@ -1330,9 +1378,16 @@ int evaluate(opl_mlp *ws, const double *x_dev, double alpha, const double *dir_d
         ++ws->launches;
     }
     if (head_rows_per_step(ws) > 0) {
+        // two-layer INT8 network with a softplus hidden layer: the forward GEMM stores the pre-activations and the head applies
+        // the transfer (see narrow_head_kernel, ZIN)
+        const bool late = ws->late_transfer && ws->layers == 2 && !ws->masks && ws->transfer[0] == OPL_TRANSFER_SOFTPLUS &&
+                          head_rows_per_step(ws) == 16 && int8_fwd_ok(ws, 0, ws->x, ws->rows) &&
+                          (!want_grad || head_skips_delta_prev(ws, ws->rows));
+        if (ws->int8) ws->int8->store_z0 = late;
         rc = forward(ws, ws->w_trial, ws->x, ws->rows, want_grad, true, ws->layers - 1);
+        if (ws->int8) ws->int8->store_z0 = false;
         if (rc != OPL_OK) return rc;
-        rc = fused_head(ws, ws->w_trial, ws->y, ws->rows, want_grad, grad_out_dev, grad_out_dev + n);
+        rc = fused_head(ws, ws->w_trial, ws->y, ws->rows, want_grad, grad_out_dev, grad_out_dev + n, late);
         if (rc != OPL_OK) return rc;
         if (want_grad && head_rows_per_step(ws) == 16 && head_skips_delta_prev(ws, ws->rows)) {
             // two-layer network: delta_0 exists only as the digit operand of the dW_0 GEMM, cut from (delta_L, W_1, slope)
@@ -1497,6 +1552,7 @@ int opl_mlp_create(opl_mlp **out, int32_t n_widths, const int64_t *widths, const
     OPL_TRY(cudaMemset(ws->ticket, 0, sizeof(unsigned int)));
     if (const char *env = getenv("OPL_SMALL_PATH")) ws->small_path = atoi(env) != 0;
     if (const char *env = getenv("OPL_DIRECT_DELTA")) ws->direct_delta_digits = atoi(env) != 0;
+    if (const char *env = getenv("OPL_LATE_TRANSFER")) ws->late_transfer = atoi(env) != 0;
 #undef OPL_TRY
     if (precision == OPL_PRECISION_TF32) {
         int rc = fast_create(ws);

@@ -33,6 +33,7 @@ struct Int8State {
     double *classmax = nullptr;        // 16 entries: max |delta_L[:, c]| of the fused head when it leaves delta_prev to the digit kernel
     double *dmax = nullptr;            // max |delta_l[:, j]| gathered by the kernel that writes delta_l (atomicMax), or unused
     int dmax_layer = -1;               // layer whose delta the maxima in dmax belong to (-1: none)
+    bool store_z0 = false;             // this evaluation's layer-0 GEMM stores z (plain epilogue): the fused head applies the transfer
     bool w0_digits_ready = false;      // the evaluation's first launch already cut the digits of W_0^T (ozaki_trial_w0_digits)
     int64_t colmax_len = 0;
 };
@@ -234,6 +235,10 @@ int int8_forward_layer(opl_mlp *ws, int l, const double *w, const double *in, in
     }
     g.aux_out = (!last && keep_deriv) ? ws->deriv[l] : nullptr;
     g.colmask = (!last && ws->masks && masked) ? ws->masks + ws->mask_off[l + 1] : nullptr;
+    if (l == 0 && s->store_z0) {       // late transfer: z = X W_0 + b as it stands
+        g.epi = OZ_EPI_STORE;
+        g.aux_out = nullptr;
+    }
     if (kp > OZ_MAX_K) return fail(OPL_E_STATE, "int8 forward: layer %d is wider than %d inputs", l, OZ_MAX_K);
     mark(ws, STAGE_FWD * 100 + l);
     return launch_ozaki_gemm(a_dig, a_rows_pad, s->w_dig, np, kp, g, ws->stream, &ws->launches);

@@ -189,6 +189,35 @@ def test_delta_digits_formed_on_the_fly_match_the_materialised_schedule(L, hidde
     print("delta digits on the fly: grad vs oracle %.1e, vs materialised schedule %.1e" % (rel_err(grad_d, want_grad), rel_err(grad_d, grad_p)))
 
 
+@pytest.mark.parametrize("rows,big", [(3000, False), (2999, True)])
+def test_hidden_transfer_applied_by_the_head_is_bit_identical(L, rows, big, monkeypatch):
+    """Two-layer softplus networks on the INT8 engine: the forward digit GEMM stores the pre-activations and the fused head
+    applies softplus / logistic to every tile it stages (csrc/mlp.cu narrow_head_kernel, ZIN) instead of the GEMM epilogue.
+    Same routine on the same arguments, so objective and gradient must be BIT-identical to the epilogue schedule
+    (OPL_LATE_TRANSFER=0) -- also with a ragged last tile and with pre-activations beyond +-708 (the full-form fix-up), for the
+    objective-only evaluation too -- and both within the gate of the oracle."""
+    rng = numpy.random.default_rng(23)
+    shape, transfers, eid = (200, 128, 10), [(2, 0), (4, 0)], 1
+    x, y = mo.random_classification(rows, 200, 10, rng)
+    w = mo.random_params(shape, rng)
+    if big:
+        x[::7] *= 900.0                                                  # |z| up to ~1e4: the irregular-argument branch
+        w[128 + 200 * 128:] *= 1e-3
+    with numpy.errstate(all="ignore"):
+        want_obj, want_grad = mo.objective_gradient(w, shape, transfers, eid, x, y, literal_softmax=False)
+    late = _model(L, shape, transfers, eid)
+    obj_l, grad_l = late._get_obj_jac(w.copy(), x, y)
+    only_l = late._get_obj(w.copy(), x, y)
+    monkeypatch.setenv("OPL_LATE_TRANSFER", "0")
+    epi = _model(L, shape, transfers, eid)
+    obj_e, grad_e = epi._get_obj_jac(w.copy(), x, y)
+    only_e = epi._get_obj(w.copy(), x, y)
+    monkeypatch.delenv("OPL_LATE_TRANSFER")
+    assert obj_l == obj_e and only_l == only_e and numpy.array_equal(grad_l, grad_e)
+    assert rel_err(obj_l, want_obj) <= TOL and rel_err(grad_l, want_grad) <= TOL, (rel_err(obj_l, want_obj), rel_err(grad_l, want_grad))
+    assert rel_err(only_l, want_obj) <= TOL
+
+
 @pytest.mark.parametrize("precision", ["f64", "f64-dmma"])
 def test_saturated_head_keeps_reference_semantics(L, precision):
     """Degenerate numerics on the fused-head / INT8 path: logits so large that target-class probabilities underflow to

@@ -544,7 +544,8 @@ def run_gpu(args):
             "achieved": achieved, "peak": peak_equiv, "unit": "TFLOP/s", "frac": achieved / peak_equiv if achieved else None,
             "traffic": tr.get("bytes"),
             "traffic_note": "dram__bytes_read+write of the forward launch, ncu --set full (%s); "
-                            "algorithmic bytes of that launch = X digits 323 MB + A1 and D0 246 MB" % tr.get("source"),
+                            "algorithmic bytes of that launch = X digits 323 MB + the pre-activations 123 MB (the fused head "
+                            "applies the hidden transfer)" % tr.get("source"),
             "peak_source": "max(2 x bf16_tflops of %s, INT8 library GEMM measured in this run) / 21 INT8 multiply-adds per FP64 "
                            "multiply-add" % peak_src,
             "int8_tops_achieved": 21.0 * achieved if achieved else None, "int8_tops_peak": int8_peak,

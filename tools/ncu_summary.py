@@ -3,8 +3,10 @@
 
     ncu_summary.py launches gpurun_out/launches.csv            per-kernel totals of a `--metrics gpu__time_duration.sum --csv` list
     ncu_summary.py full gpurun_out/prof.ncu-rep [regex]        selected metrics per launch of a `--set full` report
-    ncu_summary.py traffic gpurun_out/prof.ncu-rep regex key [n]   dram bytes (read + write) of the LAST launch matching regex
-                                                               -> profiles/ncu_traffic.json[key] (what bench.py reports as roofline.traffic)
+    ncu_summary.py traffic gpurun_out/prof.ncu-rep regex key [n] [source] [which]
+                                                               dram bytes (read + write) of the LAST launch matching regex (which = -2: the
+                                                               one before it, ...) -> profiles/ncu_traffic.json[key] (what bench.py reports
+                                                               as roofline.traffic)
 """
 import collections
 import csv
@@ -60,7 +62,7 @@ def full(path, pattern=None):
                 print("  %-92s %s %s" % (m, r[head.index(m)], units[head.index(m)]))
 
 
-def traffic(path, pattern, key, n=None, source=None):
+def traffic(path, pattern, key, n=None, source=None, which=-1):
     import json
     import os
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -68,14 +70,15 @@ def traffic(path, pattern, key, n=None, source=None):
     head, units = rows[0], rows[1]
     ki = head.index("Kernel Name")
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    found = None
+    matches = []
     for r in rows[2:]:
         if re.search(pattern, r[ki]):
             total = 0.0
             for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                 i = head.index(m)
                 total += float(r[i].replace(",", "")) * scale[units[i]]
-            found = (r[ki], total)
+            matches.append((r[ki], total))
+    found = matches[int(which)] if len(matches) >= abs(int(which)) else None
     if found is None:
         sys.exit("no launch matches %r" % pattern)
     dest = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic.json")
@@ -95,7 +98,7 @@ def traffic(path, pattern, key, n=None, source=None):
 if __name__ == "__main__":
     if len(sys.argv) >= 5 and sys.argv[1] == "traffic":
         traffic(sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5] if len(sys.argv) > 5 else None,
-                sys.argv[6] if len(sys.argv) > 6 else None)
+                sys.argv[6] if len(sys.argv) > 6 else None, sys.argv[7] if len(sys.argv) > 7 else -1)
     elif len(sys.argv) >= 3 and sys.argv[1] == "launches":
         launches(sys.argv[2])
     elif len(sys.argv) >= 3 and sys.argv[1] == "full":

@@ -689,6 +689,19 @@ __global__ void colabsmax_final_kernel(const double *__restrict__ partial, int n
 // matrices) every block first scans its 32 columns over ALL rows itself, then walks all row chunks (grid.x == 1);
 // MODE 3 (cooperative launch, matrices whose grid is co-resident: the weight matrices) every block leaves the maxima of
 // its own 128 x 32 patch in `partial`, the grid synchronises, and the maxima are folded from there: one launch instead of three.
+// Tile order of the streaming transposed-digit passes: a 1-D grid walks 8 x 8 patches of (column tile, row tile), so the CTAs that
+// run at the same time read 2 KB runs of the source rows AND write 1 KB runs of the digit rows (row-tile-fast order scatters the
+// reads into 256-byte pieces, column-tile-fast order scatters the writes into 128-byte pieces).
+__device__ __forceinline__ bool oz_patch_raster(int64_t b, int64_t ctiles, int64_t rtiles, int64_t &ct, int64_t &rt) {
+    const int64_t pc = (ctiles + 7) >> 3, p = b >> 6;
+    const int w = (int)(b & 63);
+    const int64_t pr = p / pc;
+    ct = (p - pr * pc) * 8 + (w & 7);
+    rt = pr * 8 + (w >> 3);
+    return ct < ctiles && rt < rtiles;
+}
+static int64_t oz_patch_grid(int64_t ctiles, int64_t rtiles) { return ((ctiles + 7) >> 3) * ((rtiles + 7) >> 3) * 64; }
+
 template <int MODE>
 __global__ void __launch_bounds__(256) slice_cols_transposed_kernel(const double *__restrict__ src, int64_t rows, int64_t cols,
                                                                     int64_t ld, double *__restrict__ scale,
@@ -697,7 +710,14 @@ __global__ void __launch_bounds__(256) slice_cols_transposed_kernel(const double
                                                                     int64_t row_off, double *partial) {
     __shared__ uint32_t tile[OZ_S][32][33];    // [digit][col][word along rows], padded
     __shared__ double smax[8][33];
-    const int64_t c0 = blockIdx.y * 32;
+    // MODE 0 / 1 (streaming passes over big matrices): 1-D grid in patch order, one tile per CTA
+    constexpr bool PATCHES = MODE == 0 || MODE == 1;
+    int64_t row_blk = blockIdx.x, row_blks = gridDim.x, col_blk = blockIdx.y;
+    if (PATCHES) {
+        row_blks = rows_pad >> 7;
+        if (!oz_patch_raster(blockIdx.x, (cols + 31) >> 5, row_blks, col_blk, row_blk)) return;
+    }
+    const int64_t c0 = col_blk * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 8 warps
     const int64_t c = c0 + tx;
     double sc = 1.0;
@@ -706,7 +726,7 @@ __global__ void __launch_bounds__(256) slice_cols_transposed_kernel(const double
     } else if (MODE == 1) {
         if (c < cols) {
             sc = oz_scale_of(colmax[c]);
-            if (blockIdx.x == 0 && ty == 0) scale[c] = sc;
+            if (row_blk == 0 && ty == 0) scale[c] = sc;
         }
     } else if (MODE == 3) {
         double m = 0.0;
@@ -767,7 +787,39 @@ __global__ void __launch_bounds__(256) slice_cols_transposed_kernel(const double
         if (c < cols && ty == 0) scale[c] = sc;
     }
     const double inv = sc == sc ? 1.0 / sc : 0.0;
-    for (int64_t r0 = blockIdx.x * 128; r0 < rows_pad; r0 += (int64_t)gridDim.x * 128) {
+    const int64_t plane = cols_pad * rows_pad;
+    for (int64_t r0 = (int64_t)row_blk * 128; r0 < rows_pad; r0 += (int64_t)row_blks * 128) {
+        if (r0 + 128 <= rows && c0 + 32 <= cols) {
+            // interior tile: all 16 values of the thread requested up front through a stepped pointer, no bounds tests
+            const double *sp = src + (r0 + ty * 16) * ld + c;
+            double v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j, sp += ld) v[j] = *sp;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                uint32_t w[OZ_S];
+                double q4[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) q4[j] = v[4 * g + j] * inv;
+                oz_digits4(q4, w);
+#pragma unroll
+                for (int s = 0; s < OZ_S; ++s) tile[s][tx][ty * 4 + g] = w[s];
+            }
+            __syncthreads();
+            const int cc = threadIdx.x >> 3, seg = threadIdx.x & 7;     // one 16-byte segment of one output row per digit plane
+            int8_t *op = out + (c0 + cc + row_off) * rows_pad + r0 + seg * 16;
+#pragma unroll
+            for (int s = 0; s < OZ_S; ++s, op += plane) {
+                uint4 q;
+                q.x = tile[s][cc][seg * 4 + 0];
+                q.y = tile[s][cc][seg * 4 + 1];
+                q.z = tile[s][cc][seg * 4 + 2];
+                q.w = tile[s][cc][seg * 4 + 3];
+                *reinterpret_cast<uint4 *>(op) = q;
+            }
+            __syncthreads();
+            continue;
+        }
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             const int wq = ty * 4 + g;             // word index along rows: rows r0 + 4 wq ..
@@ -821,6 +873,9 @@ __global__ void __launch_bounds__(256, 4) slice_delta_prev_transposed_kernel(con
                                                                           int64_t cols_pad, int64_t rows_pad, int64_t row_off) {
     __shared__ uint32_t tile[OZ_S][32][33];
     __shared__ __align__(16) double dl[128][MAXC];
+    // (row tile = fast grid index here: the patch order of the plain transposed pass measured 0.076 against 0.070 ms at config 2,
+    //  whose 256 columns are a single patch across)
+    const int64_t row_blk = blockIdx.x;
     const int64_t c0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int64_t c = c0 + tx;
@@ -833,11 +888,11 @@ __global__ void __launch_bounds__(256, 4) slice_delta_prev_transposed_kernel(con
     }
     const double sc = oz_scale_of(bound);
     unsigned long long *scale_bits = reinterpret_cast<unsigned long long *>(scale + row_off);
-    if (c < cols && blockIdx.x == 0 && ty == 0) atomicMax(scale_bits + c, (unsigned long long)__double_as_longlong(sc));
+    if (c < cols && row_blk == 0 && ty == 0) atomicMax(scale_bits + c, (unsigned long long)__double_as_longlong(sc));
     const double inv = sc == sc ? 1.0 / sc : 0.0;
     bool bad = false;
     const int64_t plane = cols_pad * rows_pad;
-    for (int64_t r0 = blockIdx.x * 128; r0 < rows_pad; r0 += (int64_t)gridDim.x * 128) {
+    for (int64_t r0 = row_blk * 128; r0 < rows_pad; r0 += (int64_t)gridDim.x * 128) {
         if (r0 + 128 <= rows && c0 + 32 <= cols) {
             // ---- interior tile: no bounds tests, pointers stepped instead of re-derived (the kernel was bound by its
             //      integer / predicate instructions, ~60 of 119 per element; profiles/r02_ncu_eval_kernels.txt) ----
@@ -1136,7 +1191,7 @@ int ozaki_slice_cols_transposed(const double *src, int64_t rows, int64_t cols, i
     const int64_t cp = m_pad > 0 ? m_pad : ozaki_pad(cols + row_off), rp = ozaki_pad(rows);
     const unsigned gy = (unsigned)ceil_div(cols, 32);
     if (colmax_raw) {            // maxima gathered by the kernel that produced src
-        slice_cols_transposed_kernel<1><<<dim3((unsigned)ceil_div(rp, 128), gy), 256, 0, stream>>>(
+        slice_cols_transposed_kernel<1><<<(unsigned)oz_patch_grid(gy, rp / 128), 256, 0, stream>>>(
             src, rows, cols, ld, scale + row_off, colmax_raw, slices, cp, rp, row_off, nullptr);
         OPL_LAUNCH_CHECK();
         if (launches) *launches += 1;
@@ -1175,7 +1230,7 @@ int ozaki_slice_cols_transposed(const double *src, int64_t rows, int64_t cols, i
     dim3 g1((unsigned)ceil_div(cols, 32), (unsigned)nblk);
     colabsmax_partial_kernel<<<g1, dim3(32, 8), 0, stream>>>(src, rows, cols, ld, rpb, scratch);
     colabsmax_final_kernel<<<(unsigned)ceil_div(cols, 256), 256, 0, stream>>>(scratch, (int)nblk, cols, scale + row_off);
-    slice_cols_transposed_kernel<0><<<dim3((unsigned)ceil_div(rp, 128), gy), 256, 0, stream>>>(
+    slice_cols_transposed_kernel<0><<<(unsigned)oz_patch_grid(gy, rp / 128), 256, 0, stream>>>(
         src, rows, cols, ld, scale + row_off, nullptr, slices, cp, rp, row_off, nullptr);
     OPL_LAUNCH_CHECK();
     if (launches) *launches += 3;

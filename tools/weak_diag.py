@@ -12,7 +12,8 @@ from bench import synthetic, ROWS, SHAPE
 
 local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
-dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+dist.init_process_group("nccl", device_id=torch.device("cuda", local), init_method=None if "RANK" in os.environ else "tcp://127.0.0.1:29531",
+                        rank=int(os.environ.get("RANK", "0")), world_size=int(os.environ.get("WORLD_SIZE", "1")))
 rank, world = dist.get_rank(), dist.get_world_size()
 x, y, w = synthetic(ROWS, 100 + rank)
 _, _, w = synthetic(8, 0)
@@ -22,7 +23,7 @@ xd, yd = dev.to_device(x), dev.to_device(y)
 ws = model._make_resident(xd, yd)
 wd = dev.to_device(w)
 out = torch.empty(n + 2, dtype=torch.float64, device="cuda")
-peer = model._peer_allreduce(ws, n + 2)
+peer = model._peer_allreduce(ws, n + 2) if world > 1 else None
 
 
 def ev(dst):
@@ -50,10 +51,16 @@ def timed(fn, k=40):
 
 res = {}
 res["eval only (into a plain buffer)"] = timed(lambda: ev(out))
-res["eval only (into the symmetric slot)"] = timed(lambda: ev(peer.next_slot()))
-res["eval + peer all-reduce"] = timed(lambda: (ev(peer.next_slot()), peer.reduce(out)))
-res["peer all-reduce only"] = timed(lambda: (peer.next_slot(), peer.reduce(out)))
-res["eval + NCCL all-reduce"] = timed(lambda: (ev(out), dist.all_reduce(out)))
+cycles = int(0.028e-3 * 1.9e9)
+res["eval + 28 us sleep kernel"] = timed(lambda: (ev(out), torch.cuda._sleep(cycles)))
+res["28 us sleep kernel only"] = timed(lambda: torch.cuda._sleep(cycles))
+scratch = torch.empty(n + 2, dtype=torch.float64, device="cuda")
+res["eval + device copy of the vector"] = timed(lambda: (ev(out), scratch.copy_(out)))
+if peer is not None:
+    res["eval only (into the symmetric slot)"] = timed(lambda: ev(peer.next_slot()))
+    res["eval + peer all-reduce"] = timed(lambda: (ev(peer.next_slot()), peer.reduce(out)))
+    res["peer all-reduce only"] = timed(lambda: (peer.next_slot(), peer.reduce(out)))
+    res["eval + NCCL all-reduce"] = timed(lambda: (ev(out), dist.all_reduce(out)))
 if rank == 0:
     for k, (per_rank, host) in res.items():
         print("%-40s per-rank ms %s   host issue ms/step %.4f" % (k, per_rank, host), flush=True)

@@ -1251,7 +1251,7 @@ int fused_head(opl_mlp *ws, const double *w, const double *y, int64_t rows, bool
         if (no_da) {
             a.delta_out = ws->delta[L - 1];          // rows x C: delta_L
             a.classmax = ws->int8->classmax;
-            OPL_CUDA(cudaMemsetAsync(a.classmax, 0, sizeof(double) * 16, ws->stream));
+            if (!ws->int8->accumulators_cleared) OPL_CUDA(cudaMemsetAsync(a.classmax, 0, sizeof(double) * 16, ws->stream));
         } else {
             a.delta_prev = ws->delta[L - 2];
             a.colmax = int8_arm_delta_max(ws, L - 2, rows);
@@ -1355,15 +1355,19 @@ int evaluate(opl_mlp *ws, const double *x_dev, double alpha, const double *dir_d
         return rc;
     }
     bool fused_trial = false;
-    if (ws->int8) ws->int8->w0_digits_ready = false;
+    if (ws->int8) ws->int8->w0_digits_ready = ws->int8->accumulators_cleared = false;
     if (!ws->masks && int8_fwd_ok(ws, 0, ws->x, ws->rows)) {
         // INT8 forward layer 0: the trial point and the digits of W_0^T in one cooperative launch
         Int8State *s8 = ws->int8;
+        // (it also clears the class maxima and the delta scales the two-layer schedule accumulates into by atomicMax)
+        const bool two_layer = want_grad && head_rows_per_step(ws) == 16 && head_skips_delta_prev(ws, ws->rows);
         rc = ozaki_trial_w0_digits(x_dev, dir_dev, alpha, ws->w_trial, n, ws->w_off[0], ws->width[0], ws->width[1], s8->w_dig,
-                                   s8->w_scale, s8->colmax, s8->colmax_len, ozaki_pad(ws->width[1]), ws->flag, ws->stream,
-                                   &ws->launches, &fused_trial);
+                                   s8->w_scale, s8->colmax, s8->colmax_len, ozaki_pad(ws->width[1]), ws->flag,
+                                   two_layer ? s8->classmax : nullptr, 16, two_layer ? s8->d_scale : nullptr, (int)ws->width[1],
+                                   ws->stream, &ws->launches, &fused_trial);
         if (rc != OPL_OK) return rc;
         s8->w0_digits_ready = fused_trial;
+        s8->accumulators_cleared = fused_trial && two_layer;
     }
     if (!fused_trial) {
         trial_point_kernel<<<tgrid, 256, 0, ws->stream>>>(n, x_dev, alpha, dir_dev, ws->w_trial, ws->flag);

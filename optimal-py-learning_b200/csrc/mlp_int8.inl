@@ -34,6 +34,7 @@ struct Int8State {
     double *dmax = nullptr;            // max |delta_l[:, j]| gathered by the kernel that writes delta_l (atomicMax), or unused
     int dmax_layer = -1;               // layer whose delta the maxima in dmax belong to (-1: none)
     bool store_z0 = false;             // this evaluation's layer-0 GEMM stores z (plain epilogue): the fused head applies the transfer
+    bool accumulators_cleared = false; // classmax and d_scale were zeroed by the evaluation's first launch (no memsets needed)
     bool w0_digits_ready = false;      // the evaluation's first launch already cut the digits of W_0^T (ozaki_trial_w0_digits)
     int64_t colmax_len = 0;
 };
@@ -310,7 +311,7 @@ int int8_dw_layer(opl_mlp *ws, int l, const double *in, int64_t rows, double *gr
     int rc;
     if (otf)
         rc = ozaki_slice_delta_prev(otf->deltaL, otf->C, otf->W, otf->aux, otf->mode, rows, dout, dout, s->classmax, s->d_dig, s->d_scale,
-                                    np, ws->stream, &ws->launches);
+                                    np, ws->stream, &ws->launches, s->accumulators_cleared);
     else
         rc = ozaki_slice_cols_transposed(ws->delta[l], rows, dout, dout, s->d_dig, s->d_scale, s->colmax, s->colmax_len, 0, np, colmax_raw,
                                          ws->stream, &ws->launches);

@@ -1030,6 +1030,8 @@ struct TrialW0Args {
     int64_t cols_pad, rows_pad;
     double *partial;           // gridDim.x x cols column maxima
     int *flag;                 // domain flag of the evaluation, reset here
+    double *zero_a, *zero_b;   // two small arrays the evaluation accumulates into by atomicMax later (class maxima, delta scales),
+    int zero_a_len, zero_b_len;   // cleared here instead of by two memset launches; may be null
 };
 
 __global__ void __launch_bounds__(256) trial_w0_digits_kernel(const TrialW0Args a) {
@@ -1040,7 +1042,11 @@ __global__ void __launch_bounds__(256) trial_w0_digits_kernel(const TrialW0Args 
     const int64_t rb = blockIdx.x * 128;
     const double *x0 = a.x + a.off, *d0 = a.dir ? a.dir + a.off : nullptr;
     double *w0 = a.w + a.off;
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *a.flag = 0;
+    if (blockIdx.x == 0 && blockIdx.y == 0) {
+        if (threadIdx.x == 0) *a.flag = 0;
+        for (int i = threadIdx.x; i < a.zero_a_len; i += 256) a.zero_a[i] = 0.0;
+        for (int i = threadIdx.x; i < a.zero_b_len; i += 256) a.zero_b[i] = 0.0;
+    }
     // ---- the rest of the vector (everything outside W_0), shared by all blocks ----
     {
         const int64_t nb = (int64_t)gridDim.x * gridDim.y, b = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
@@ -1241,7 +1247,8 @@ int ozaki_slice_cols_transposed(const double *src, int64_t rows, int64_t cols, i
 // trial-point kernel and the plain digit pass
 int ozaki_trial_w0_digits(const double *x, const double *dir, double alpha, double *w, int64_t n, int64_t off, int64_t rows,
                           int64_t cols, int8_t *slices, double *scale, double *scratch, int64_t scratch_len, int64_t m_pad,
-                          int *flag, cudaStream_t stream, int64_t *launches, bool *done) {
+                          int *flag, double *zero_a, int zero_a_len, double *zero_b, int zero_b_len, cudaStream_t stream,
+                          int64_t *launches, bool *done) {
     *done = false;
     const int64_t rp = ozaki_pad(rows), cp = m_pad > 0 ? m_pad : ozaki_pad(cols);
     const int64_t gx = ceil_div(rp, 128), gy = ceil_div(cols, 32);
@@ -1267,6 +1274,10 @@ int ozaki_trial_w0_digits(const double *x, const double *dir, double alpha, doub
     a.rows_pad = rp;
     a.partial = scratch;
     a.flag = flag;
+    a.zero_a = zero_a;
+    a.zero_a_len = zero_a ? zero_a_len : 0;
+    a.zero_b = zero_b;
+    a.zero_b_len = zero_b ? zero_b_len : 0;
     void *params[] = {(void *)&a};
     OPL_CUDA(cudaLaunchCooperativeKernel((const void *)trial_w0_digits_kernel, dim3((unsigned)gx, (unsigned)gy), dim3(256), params, 0,
                                          stream));
@@ -1277,10 +1288,11 @@ int ozaki_trial_w0_digits(const double *x, const double *dir, double alpha, doub
 
 int ozaki_slice_delta_prev(const double *deltaL, int C, const double *W, const double *aux, int mode, int64_t rows, int64_t cols,
                            int64_t ld, const double *classmax, int8_t *slices, double *scale, int64_t m_pad,
-                           cudaStream_t stream, int64_t *launches) {
+                           cudaStream_t stream, int64_t *launches, bool scale_cleared) {
     if (C < 1 || C > 16) return fail(OPL_E_ARG, "ozaki_slice_delta_prev: C must be in [1, 16]");
     const int64_t cp = m_pad > 0 ? m_pad : ozaki_pad(cols), rp = ozaki_pad(rows);
-    OPL_CUDA(cudaMemsetAsync(scale, 0, sizeof(double) * (size_t)cols, stream));     // scales arrive by atomicMax on their bit patterns
+    if (!scale_cleared)      // scales arrive by atomicMax on their bit patterns
+        OPL_CUDA(cudaMemsetAsync(scale, 0, sizeof(double) * (size_t)cols, stream));
     const dim3 grid((unsigned)ceil_div(rp, 128), (unsigned)ceil_div(cols, 32));
 #define OPL_DP_LAUNCH(CE, MD)                                                                                               \
     slice_delta_prev_transposed_kernel<CE, MD><<<grid, 256, 0, stream>>>(deltaL, C, W, aux, rows, cols, ld, classmax, scale, \

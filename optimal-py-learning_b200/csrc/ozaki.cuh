@@ -56,16 +56,17 @@ int ozaki_slice_cols_transposed(const double *src, int64_t rows, int64_t cols, i
                                 cudaStream_t stream, int64_t *launches);
 // trial point w = x + fl(alpha dir) (whole flat vector, n entries) AND the digits of W_0^T (W_0 = w[off : off + rows cols],
 // rows x cols row-major; output as ozaki_slice_cols_transposed) in ONE cooperative launch; also resets the evaluation's
-// domain flag.  *done = false: the grid does not fit, nothing was enqueued.
+// domain flag and clears up to two small accumulator arrays (zero_a, zero_b; may be null).  *done = false: the grid does not fit, nothing was enqueued.
 int ozaki_trial_w0_digits(const double *x, const double *dir, double alpha, double *w, int64_t n, int64_t off, int64_t rows,
                           int64_t cols, int8_t *slices, double *scale, double *scratch, int64_t scratch_len, int64_t m_pad,
-                          int *flag, cudaStream_t stream, int64_t *launches, bool *done);
+                          int *flag, double *zero_a, int zero_a_len, double *zero_b, int zero_b_len, cudaStream_t stream,
+                          int64_t *launches, bool *done);
 // digits of delta_prev^T = ((deltaL W^T) o slope)^T formed on the fly from deltaL (rows x C, C <= 16), W (cols x C) and the slope
 // matrix aux (rows x cols, pitch ld; mode 0 none, 1 aux = f', 2 aux = tanh activation); classmax[c] = max_r |deltaL[r][c]| (raw
 // bit patterns as gathered by atomicMax).  Same output layout as ozaki_slice_cols_transposed: INT8 [S][m_pad][pad(rows)], scale[cols].
 int ozaki_slice_delta_prev(const double *deltaL, int C, const double *W, const double *aux, int mode, int64_t rows, int64_t cols,
                            int64_t ld, const double *classmax, int8_t *slices, double *scale, int64_t m_pad,
-                           cudaStream_t stream, int64_t *launches);
+                           cudaStream_t stream, int64_t *launches, bool scale_cleared = false);
 // row 0 of a transposed digit array [S][m_pad][pad(rows)] := a row of ones (scale[0] = 4): the bias-gradient row
 int ozaki_ones_row(int8_t *slices, double *scale, int64_t rows, int64_t m_pad, cudaStream_t stream, int64_t *launches);
 // FP64 fold of split-K partials is done by the caller (launch_reduce_partials)

@@ -843,6 +843,11 @@ struct opl_mlp {
     int precision = 0;
     int64_t n = 0, max_rows = 0, rows = 0, norm_rows = 0;
     cudaStream_t stream = nullptr;
+    // the fused head's folds (dW_{L-1}, loss) run beside the delta digits and the dW_0 GEMM on a stream of their own: nothing
+    // reads their results before the evaluation ends (OPL_SIDE_FOLD=0: in line)
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_head = nullptr, ev_fold = nullptr;
+    bool fold_pending = false, side_fold = true;
 
     double *x_own = nullptr, *y_own = nullptr;   // owned copies (set_data_host)
     const double *x = nullptr, *y = nullptr;     // resident data (owned or borrowed)
@@ -941,6 +946,15 @@ void fast_free(FastState *f);
 void int8_free(Int8State *s);
 
 int free_all(opl_mlp *ws) {
+    if (ws->side) {
+        cudaStreamSynchronize(ws->side);
+        cudaEventDestroy(ws->ev_head);
+        cudaEventDestroy(ws->ev_fold);
+        cudaStreamDestroy(ws->side);
+        ws->side = nullptr;
+        ws->ev_head = ws->ev_fold = nullptr;
+        ws->fold_pending = false;
+    }
     fast_free(ws->fast);
     ws->fast = nullptr;
     int8_free(ws->int8);
@@ -1307,14 +1321,31 @@ int fused_head(opl_mlp *ws, const double *w, const double *y, int64_t rows, bool
     ++ws->launches;
     if (want_grad && grid >= 16) {
         // one launch folds the per-CTA dW partials AND the loss partials (objective + domain flag)
-        mark(ws, STAGE_DW_REDUCE * 100 + L - 1);
         const int64_t count = (int64_t)H * C;
         const int64_t fgrid = std::min<int64_t>(ceil_div(count * 32, 256), 4 * (int64_t)sm_count());
-        head_fold_kernel<<<(unsigned)fgrid, 256, 0, ws->stream>>>(ws->partials, grid, count, count, grad + ws->w_off[L - 1],
-                                                                  ws->loss_partial, ws->error_id, (double)ws->norm_rows,
-                                                                  (double)C, obj_out, ws->flag);
+        cudaStream_t fold_stream = ws->stream;
+        if (no_da && ws->side_fold && !ws->profiling) {
+            // two-layer schedule: the digit kernel and the dW_0 GEMM follow and need nothing from the folds
+            if (!ws->side) {
+                OPL_CUDA(cudaStreamCreateWithFlags(&ws->side, cudaStreamNonBlocking));
+                OPL_CUDA(cudaEventCreateWithFlags(&ws->ev_head, cudaEventDisableTiming));
+                OPL_CUDA(cudaEventCreateWithFlags(&ws->ev_fold, cudaEventDisableTiming));
+            }
+            OPL_CUDA(cudaEventRecord(ws->ev_head, ws->stream));
+            OPL_CUDA(cudaStreamWaitEvent(ws->side, ws->ev_head, 0));
+            fold_stream = ws->side;
+        } else {
+            mark(ws, STAGE_DW_REDUCE * 100 + L - 1);
+        }
+        head_fold_kernel<<<(unsigned)fgrid, 256, 0, fold_stream>>>(ws->partials, grid, count, count, grad + ws->w_off[L - 1],
+                                                                ws->loss_partial, ws->error_id, (double)ws->norm_rows,
+                                                                (double)C, obj_out, ws->flag);
         OPL_LAUNCH_CHECK();
         ++ws->launches;
+        if (fold_stream != ws->stream) {
+            OPL_CUDA(cudaEventRecord(ws->ev_fold, fold_stream));
+            ws->fold_pending = true;             // evaluate() joins before it returns
+        }
         return OPL_OK;
     }
     mark(ws, STAGE_LOSS * 100);
@@ -1417,6 +1448,10 @@ int evaluate(opl_mlp *ws, const double *x_dev, double alpha, const double *dir_d
         scale_rows_kernel<<<mgrid, 256, 0, ws->stream>>>(grad_out_dev + ws->w_off[0], ws->width[0], ws->width[1], ws->masks);
         OPL_LAUNCH_CHECK();
         ++ws->launches;
+    }
+    if (ws->fold_pending) {                      // the head's folds rejoin the launch stream
+        ws->fold_pending = false;
+        OPL_CUDA(cudaStreamWaitEvent(ws->stream, ws->ev_fold, 0));
     }
     mark(ws, STAGE_END * 100);
     return rc;
@@ -1557,6 +1592,7 @@ int opl_mlp_create(opl_mlp **out, int32_t n_widths, const int64_t *widths, const
     if (const char *env = getenv("OPL_SMALL_PATH")) ws->small_path = atoi(env) != 0;
     if (const char *env = getenv("OPL_DIRECT_DELTA")) ws->direct_delta_digits = atoi(env) != 0;
     if (const char *env = getenv("OPL_LATE_TRANSFER")) ws->late_transfer = atoi(env) != 0;
+    if (const char *env = getenv("OPL_SIDE_FOLD")) ws->side_fold = atoi(env) != 0;
 #undef OPL_TRY
     if (precision == OPL_PRECISION_TF32) {
         int rc = fast_create(ws);

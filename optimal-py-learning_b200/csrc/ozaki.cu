@@ -1059,15 +1059,28 @@ __global__ void __launch_bounds__(256) trial_w0_digits_kernel(const TrialW0Args 
     // ---- pass 1: trial values of this patch, written out, and their column maxima ----
     double m = 0.0;
     bool bad = false;
-    if (c < a.cols)
-        for (int64_t r = rb + ty; r < min(a.rows, rb + 128); r += 8) {
-            const int64_t e = r * a.cols + c;
-            const double v = d0 ? __dadd_rn(x0[e], __dmul_rn(a.alpha, d0[e])) : x0[e];
-            w0[e] = v;
-            const double av = fabs(v);
-            bad |= !(av <= 1.7976931348623157e308);
-            m = fmax(m, av);
+    if (c < a.cols) {
+        // all 16 rows of the thread requested back to back (a loop with a run-time bound serialises the DRAM latencies)
+        double xv[16], dv[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int64_t r = rb + ty + 8 * i;
+            const bool ok = r < a.rows;
+            xv[i] = ok ? x0[r * a.cols + c] : 0.0;
+            dv[i] = (ok && d0) ? d0[r * a.cols + c] : 0.0;
         }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int64_t r = rb + ty + 8 * i;
+            if (r < a.rows) {
+                const double v = d0 ? __dadd_rn(xv[i], __dmul_rn(a.alpha, dv[i])) : xv[i];
+                w0[r * a.cols + c] = v;
+                const double av = fabs(v);
+                bad |= !(av <= 1.7976931348623157e308);
+                m = fmax(m, av);
+            }
+        }
+    }
     smax[ty][tx] = bad ? __longlong_as_double(0x7ff8000000000000LL) : m;
     __syncthreads();
     if (ty == 0 && c < a.cols) {

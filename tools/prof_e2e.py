@@ -12,13 +12,13 @@ y = numpy.zeros((60000, 10)); y[numpy.arange(60000), rng.integers(0, 10, 60000)]
 m = L.MLP((784, 256, 10), transfers=L.SoftmaxTransfer(), error_func=L.CrossEntropyError(), optimizer=L.optimize.LBFGS())
 n = 256 + 784 * 256 + 2560
 w = torch.empty(n, dtype=torch.float64).pin_memory().numpy(); w[:] = (rng.random(n) * 2 - 1) * 0.25
+scope = m.resident(x, y); scope.__enter__()          # what Model.train opens around its train_steps
 for _ in range(5): m._get_obj_jac(w, x, y)
 def timeit(f, k=200):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     for _ in range(k): f()
     torch.cuda.synchronize(); return (time.perf_counter() - t0) / k * 1e6
 print("full _get_obj_jac           %8.1f us" % timeit(lambda: m._get_obj_jac(w, x, y), 100))
-print("_fingerprint                %8.1f us" % timeit(lambda: M._fingerprint(x, y)))
 print("pinned torch.empty().numpy()%8.1f us" % timeit(lambda: torch.empty(n, dtype=torch.float64, pin_memory=True).numpy()))
 ws = m._workspace
 g = torch.empty(n, dtype=torch.float64, pin_memory=True).numpy(); obj = ctypes.c_double()

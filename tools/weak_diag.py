@@ -61,7 +61,21 @@ if peer is not None:
     res["eval + peer all-reduce"] = timed(lambda: (ev(peer.next_slot()), peer.reduce(out)))
     res["peer all-reduce only"] = timed(lambda: (peer.next_slot(), peer.reduce(out)))
     res["eval + NCCL all-reduce"] = timed(lambda: (ev(out), dist.all_reduce(out)))
+# step-to-step jitter of the evaluation: one event per step
+for _ in range(5):
+    ev(out)
+torch.cuda.synchronize()
+marks = [torch.cuda.Event(enable_timing=True) for _ in range(201)]
+marks[0].record()
+for i in range(200):
+    ev(out)
+    marks[i + 1].record()
+torch.cuda.synchronize()
+import numpy
+dts = numpy.array([marks[i].elapsed_time(marks[i + 1]) for i in range(200)])
 if rank == 0:
+    print("per-step evaluation time over 200 steps: mean %.4f  std %.4f  min %.4f  p5 %.4f  p50 %.4f  p95 %.4f  max %.4f ms"
+          % (dts.mean(), dts.std(), dts.min(), numpy.percentile(dts, 5), numpy.percentile(dts, 50), numpy.percentile(dts, 95), dts.max()), flush=True)
     for k, (per_rank, host) in res.items():
         print("%-40s per-rank ms %s   host issue ms/step %.4f" % (k, per_rank, host), flush=True)
 dist.destroy_process_group()

@@ -218,6 +218,40 @@ def test_hidden_transfer_applied_by_the_head_is_bit_identical(L, rows, big, monk
     assert rel_err(only_l, want_obj) <= TOL
 
 
+def test_two_layer_schedule_probe_with_direction_and_foreign_stream(L):
+    """The two-layer INT8 schedule end to end through the fused probe: the trial point x + alpha d is formed by the same
+    cooperative launch that cuts the digits of W_0 (csrc/ozaki.cu trial_w0_digits_kernel), the head's folds run on the workspace's
+    side stream (OPL_SIDE_FOLD) and rejoin before the probe scalars are read.  The probe must equal the evaluation at the explicit
+    point bit for bit, its slope must be grad . d, and issuing everything under a non-default torch stream must change nothing."""
+    import torch
+    from learning_b200 import _device as dev
+    rng = numpy.random.default_rng(31)
+    shape, transfers, eid = (200, 128, 10), [(2, 0), (4, 0)], 1
+    x, y = mo.random_classification(3000, 200, 10, rng)
+    w = mo.random_params(shape, rng)
+    d = rng.standard_normal(w.size) * 0.05
+    alpha = 0.37
+    model = _model(L, shape, transfers, eid)
+    obj_e, grad_e = model._get_obj_jac(w + alpha * d, x, y)
+    want_obj, want_grad = mo.objective_gradient(w + alpha * d, shape, transfers, eid, x, y, literal_softmax=False)
+    assert rel_err(obj_e, want_obj) <= TOL and rel_err(grad_e, want_grad) <= TOL
+    ws = model._make_resident(x, y)
+    wd, dd = dev.to_device(w), dev.to_device(d)
+    obj_p, slope_p, grad_p = model._probe(ws, wd, alpha, dd, True)
+    assert obj_p == obj_e and numpy.array_equal(dev.to_host(grad_p), grad_e)
+    assert rel_err(slope_p, grad_e.dot(d)) <= 1e-12
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        other = _model(L, shape, transfers, eid)
+        ws2 = other._make_resident(x, y)
+        for _ in range(3):                       # back to back: the side-stream fold of one probe against the next probe's kernels
+            obj_s, slope_s, grad_s = other._probe(ws2, wd, alpha, dd, True)
+        host_s = dev.to_host(grad_s)
+    side.synchronize()
+    assert obj_s == obj_e and slope_s == slope_p and numpy.array_equal(host_s, grad_e)
+
+
 @pytest.mark.parametrize("precision", ["f64", "f64-dmma"])
 def test_saturated_head_keeps_reference_semantics(L, precision):
     """Degenerate numerics on the fused-head / INT8 path: logits so large that target-class probabilities underflow to

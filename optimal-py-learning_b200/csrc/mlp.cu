@@ -843,8 +843,9 @@ struct opl_mlp {
     int precision = 0;
     int64_t n = 0, max_rows = 0, rows = 0, norm_rows = 0;
     cudaStream_t stream = nullptr;
-    // the fused head's folds (dW_{L-1}, loss) run beside the delta digits and the dW_0 GEMM on a stream of their own: nothing
-    // reads their results before the evaluation ends (OPL_SIDE_FOLD=0: in line)
+    // the fused head's folds (dW_{L-1}, loss) run beside the delta digit kernel on a stream of their own: nothing reads their
+    // results before the evaluation ends, and their INPUT (the head's partials in ws->partials) is safe until the dW_0 GEMM
+    // reuses that buffer for its split-K partials -- int8_dw_layer rejoins the streams right before it (OPL_SIDE_FOLD=0: in line)
     cudaStream_t side = nullptr;
     cudaEvent_t ev_head = nullptr, ev_fold = nullptr;
     bool fold_pending = false, side_fold = true;

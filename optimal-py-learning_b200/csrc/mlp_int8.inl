@@ -343,6 +343,12 @@ int int8_dw_layer(opl_mlp *ws, int l, const double *in, int64_t rows, double *gr
     g.scale_b = s->d_scale;
     g.epi = OZ_EPI_STORE;
     g.ldaux = dout;
+    if (ws->fold_pending && plan.splits > 1) {
+        // the fused head's folds (side stream) read the head's per-CTA partials out of ws->partials, which this GEMM is about to
+        // overwrite with its split-K partials: they rejoin the launch stream HERE (they have had the digit kernel's time to run)
+        ws->fold_pending = false;
+        OPL_CUDA(cudaStreamWaitEvent(ws->stream, ws->ev_fold, 0));
+    }
     mark(ws, STAGE_DW * 100 + l);
     // digit arrays are pitched by the PADDED row count of the resident batch
     rc = launch_ozaki_gemm(a_dig, mp, s->d_dig, np, kp, g, ws->stream, &ws->launches);

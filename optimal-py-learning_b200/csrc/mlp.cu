@@ -1383,6 +1383,10 @@ int evaluate(opl_mlp *ws, const double *x_dev, double alpha, const double *dir_d
     if (ws->precision == OPL_PRECISION_TF32) {
         rc = fast_trial_convert(ws, x_dev, alpha, dir_dev);      // trial point + padded TF32 copy of the weights: one launch
         if (rc == OPL_OK) rc = fast_evaluate(ws, want_grad, grad_out_dev);
+        if (ws->fold_pending) {                  // the head's folds rejoin the launch stream
+            ws->fold_pending = false;
+            OPL_CUDA(cudaStreamWaitEvent(ws->stream, ws->ev_fold, 0));
+        }
         mark(ws, STAGE_END * 100);
         return rc;
     }

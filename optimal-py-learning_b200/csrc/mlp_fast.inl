@@ -849,15 +849,33 @@ int fast_fused_head(opl_mlp *ws, bool want_grad, double *grad, double *obj_out) 
     ++ws->launches;
     if (want_grad && grid >= 16) {
         // one launch folds the per-CTA dW partials, the bias-gradient column sums and the loss partials
-        mark(ws, STAGE_DW_REDUCE * 100 + L - 1);
         const int64_t count = (int64_t)H * C, count2 = bias_here ? H : 0;
         const int64_t fgrid = std::min<int64_t>(ceil_div((count + count2) * 32, 256), 4 * (int64_t)sm_count());
-        head_fold_kernel<<<(unsigned)fgrid, 256, 0, ws->stream>>>(ws->partials, grid, count, count, grad + ws->w_off[L - 1],
-                                                                  ws->loss_partial, ws->error_id, (double)ws->norm_rows,
-                                                                  (double)C, obj_out, ws->flag, a.colsum_partial, (int64_t)H,
-                                                                  count2, grad);
+        cudaStream_t fold_stream = ws->stream;
+        if (L == 2 && bias_here && ws->side_fold && !ws->profiling) {
+            // two-layer network: only the dW_0 GEMM follows, with FP32 split-K partials of its own (f->partial): the folds run
+            // beside it on the workspace's side stream and rejoin before the evaluation returns (as in the parity mode)
+            if (!ws->side) {
+                OPL_CUDA(cudaStreamCreateWithFlags(&ws->side, cudaStreamNonBlocking));
+                OPL_CUDA(cudaEventCreateWithFlags(&ws->ev_head, cudaEventDisableTiming));
+                OPL_CUDA(cudaEventCreateWithFlags(&ws->ev_fold, cudaEventDisableTiming));
+            }
+            OPL_CUDA(cudaEventRecord(ws->ev_head, ws->stream));
+            OPL_CUDA(cudaStreamWaitEvent(ws->side, ws->ev_head, 0));
+            fold_stream = ws->side;
+        } else {
+            mark(ws, STAGE_DW_REDUCE * 100 + L - 1);
+        }
+        head_fold_kernel<<<(unsigned)fgrid, 256, 0, fold_stream>>>(ws->partials, grid, count, count, grad + ws->w_off[L - 1],
+                                                                ws->loss_partial, ws->error_id, (double)ws->norm_rows,
+                                                                (double)C, obj_out, ws->flag, a.colsum_partial, (int64_t)H,
+                                                                count2, grad);
         OPL_LAUNCH_CHECK();
         ++ws->launches;
+        if (fold_stream != ws->stream) {
+            OPL_CUDA(cudaEventRecord(ws->ev_fold, fold_stream));
+            ws->fold_pending = true;
+        }
         return OPL_OK;
     }
     mark(ws, STAGE_LOSS * 100);
